@@ -1,0 +1,202 @@
+// common.h — internal definitions shared by the provider's translation units.
+// The public surface is include/rm_accel.h; nothing here is exported.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rm_accel.h"
+
+#define RM_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace rm {
+
+// ---- error plumbing: every entry point returns rm_status; the message is thread-local (anyhow::Error) --
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+struct Status {
+  rm_status code;
+  Status(rm_status c = RM_OK) : code(c) {}
+  bool ok() const { return code == RM_OK; }
+};
+
+rm_status fail(rm_status code, const char* fmt, ...);
+
+#define RM_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      cudaGetLastError();                                                                          \
+      return ::rm::fail(_e == cudaErrorMemoryAllocation ? RM_OOM : RM_ERROR, "%s failed: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+    }                                                                                              \
+  } while (0)
+
+#define RM_TRY(expr)                       \
+  do {                                     \
+    rm_status _s = (expr);                 \
+    if (_s != RM_OK) return _s;            \
+  } while (0)
+
+#define RM_REQUIRE(cond, code, ...)                       \
+  do {                                                    \
+    if (!(cond)) return ::rm::fail((code), __VA_ARGS__);  \
+  } while (0)
+
+// ---- buffer table -----------------------------------------------------------------------------------------
+struct Buffer {
+  void* ptr = nullptr;
+  uint64_t elems = 0;  // logical elements (real storage only)
+};
+
+struct DispatchCounter {
+  std::atomic<uint64_t> count{0};
+  std::atomic<uint64_t> wall_ns{0};
+  void record(uint64_t ns) { count.fetch_add(1, std::memory_order_relaxed); wall_ns.fetch_add(ns, std::memory_order_relaxed); }
+  void reset() { count = 0; wall_ns = 0; }
+};
+
+struct ScopedWall {
+  DispatchCounter& c;
+  std::chrono::steady_clock::time_point t0;
+  explicit ScopedWall(DispatchCounter& c_) : c(c_), t0(std::chrono::steady_clock::now()) {}
+  ~ScopedWall() {
+    c.record((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
+struct FusedCache;  // fused.cu
+
+}  // namespace rm
+
+// The opaque provider. One CUDA device, one stream, one buffer table (SURVEY.md §8b "Ownership").
+struct rm_provider {
+  int ordinal = 0;
+  uint32_t device_id = 0;
+  rm_precision precision = RM_F64;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  cudaDeviceProp prop{};
+  cudaMemPool_t pool = nullptr;
+
+  std::mutex mu;  // guards `buffers`
+  std::unordered_map<uint64_t, rm::Buffer> buffers;
+  std::atomic<uint64_t> next_id{1};
+  std::atomic<uint64_t> live_bytes{0};
+
+  // RNG (simple_provider.rs:62, :3627-3640): host-LCG-compatible stream
+  std::mutex rng_mu;
+  uint64_t rng_state = 0x9e3779b97f4a7c15ULL;
+
+  // telemetry (accelerate/src/telemetry.rs:15-250)
+  rm::DispatchCounter t_fused_elementwise, t_fused_reduction, t_matmul, t_linsolve, t_mldivide, t_mrdivide;
+  std::atomic<uint64_t> upload_bytes{0}, download_bytes{0}, cache_hits{0}, cache_misses{0}, kernel_launches{0};
+
+  // scratch
+  void* reduce_scratch = nullptr;   // partial sums + tickets for two-stage reductions
+  size_t reduce_scratch_bytes = 0;
+  void* l2_flush = nullptr;
+  size_t l2_flush_bytes = 0;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  int matmul_engine = 0;
+
+  rm::FusedCache* fused = nullptr;
+
+  size_t elem_size() const { return precision == RM_F64 ? 8 : 4; }
+};
+
+namespace rm {
+
+// RAII device selection: every entry point runs with the provider's device current.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int ordinal) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != ordinal) { cudaSetDevice(ordinal); changed = true; }
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+inline uint64_t shape_elems(const uint64_t* shape, uint32_t rank) {
+  uint64_t n = 1;
+  for (uint32_t i = 0; i < rank; ++i) n *= shape[i];
+  return n;
+}
+inline uint64_t handle_elems(const rm_handle* h) { return shape_elems(h->shape, h->rank); }
+
+// Allocates a device buffer of `elems` elements (provider precision) and fills `out` with a fresh handle.
+rm_status alloc_tensor(rm_provider* p, const uint64_t* shape, uint32_t rank, rm_handle* out, void** dptr);
+// Resolves a handle to its device pointer, validating device_id and element count.
+rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* elems);
+rm_status ensure_scratch(rm_provider* p, size_t bytes);
+inline void count_launch(rm_provider* p, uint64_t n = 1) { p->kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// normalize_scalar_shape-style helper: MATLAB values are rank >= 2.
+inline void make_shape2(uint64_t r, uint64_t c, uint64_t* shape) { shape[0] = r; shape[1] = c; }
+
+#define RM_LAUNCH_CHECK()                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) return ::rm::fail(RM_ERROR, "kernel launch failed: %s (%s:%d)",         \
+                                             cudaGetErrorString(_e), __FILE__, __LINE__);          \
+  } while (0)
+
+// ---- fused program lowering (fusion_lower.cpp) ---------------------------------------------------------
+struct ElementwiseProgram {
+  std::string scalar_ty;             // "f64" | "f32"
+  uint32_t n_inputs = 0;
+  uint32_t n_outputs = 0;
+  std::vector<std::string> stmts;    // "T tmpK = <cuda expr>;"
+  std::vector<std::string> outputs;  // cuda expr per output
+};
+struct ReductionProgram {
+  std::string scalar_ty;
+  uint32_t n_inputs = 0;
+  int axis = 0;        // 0: reduce over rows of a column-major [nrows x ncols]; 1: reduce over cols
+  bool omit_nan = false;
+  std::string val_expr;  // cuda expr over v, v1, v2...
+};
+// Parse the reference planner's WGSL (fusion.rs:1525-1763 / :1765-2077). Returns false + message on failure.
+bool parse_elementwise_wgsl(const char* shader, ElementwiseProgram* prog, std::string* err);
+bool parse_reduction_wgsl(const char* shader, ReductionProgram* prog, std::string* err);
+// Translate one WGSL expression to CUDA C (identifier/function rewrite, literal typing).
+bool translate_expr(const std::string& wgsl, const std::string& scalar_ty, std::string* cuda, std::string* err);
+
+enum class EwVariant { Flat = 0, Broadcast = 1 };
+// scalar_mask bit k set => input k is a 1-element tensor (hoisted scalar load) in the Flat variant.
+std::string emit_elementwise_cuda(const ElementwiseProgram& prog, EwVariant variant, uint32_t scalar_mask);
+enum class RedOp { Sum = 0, Prod = 1, Max = 2, Min = 3 };
+enum class RedLayout { Contig = 0, Strided = 1 };  // Contig: slice s at [s*len, (s+1)*len); Strided: elem r of slice s at s + r*num_slices
+std::string emit_reduction_cuda(const ReductionProgram& prog, RedOp op, RedLayout layout);
+
+// ---- fused module cache / launch (fused.cu) -----------------------------------------------------------------
+rm_status fused_cache_create(rm_provider* p);
+void fused_cache_destroy(rm_provider* p);
+rm_status run_elementwise_program(rm_provider* p, const ElementwiseProgram& prog, const std::string& key,
+                                  const rm_handle* inputs, uint32_t n_inputs, const uint64_t* out_shape,
+                                  uint32_t rank, uint64_t len, rm_handle* outs);
+// Runs a reduction program. `out_shape/rank` describe the result handle. scale: result = use_div ? acc/factor : acc*factor.
+// Strided layout: element r of slice s lives at (s % inner) + (s / inner) * inner * reduce_len + r * inner.
+rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, const std::string& key, RedOp op,
+                                RedLayout layout, const rm_handle* inputs, uint32_t n_inputs,
+                                const uint64_t* out_shape, uint32_t rank, uint64_t reduce_len,
+                                uint64_t num_slices, uint64_t inner, int use_div, double factor, rm_handle* out);
+// NVRTC-only compile (no device needed): used by CPU tests of the lowering and by rm_warmup.
+rm_status compile_cuda_to_cubin(const std::string& src, const char* name, std::vector<char>* cubin, std::string* log);
+
+// ---- other translation units ---------------------------------------------------------------------------------
+rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, const rm_matmul_epilogue* ep, rm_handle* out);
+
+}  // namespace rm
