@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — measures the hot path on N B200s of one node (contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA provider (through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    the reference's CPU path (oracle port), host cores
+
+Workload (BASELINE.json configs[1]): fused chain + sum() reduction on 4096x4096 f64, per GPU.
+One "step" = one pass of the hot path over one batch:
+    (i)  C = sin(A) .* B + 1        fused elementwise, C materialised      24 B/elem algorithmic
+    (ii) s = sum(sin(A).*B + 1)     fused one-pass reduction               16 B/elem algorithmic
+At N > 1 each rank owns an independent batch (weak scaling, no data-path collective) and the per-rank sums
+meet in ONE NCCL all-reduce of a single f64 per step (the path's only exchange).
+`value` = algorithmic bytes of all ranks / device time (CUDA events, max over ranks): achieved HBM GB/s.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+N_SIDE = 4096
+ELEMS = N_SIDE * N_SIDE
+BYTES_EW = 24 * ELEMS   # read A, read B, write C
+BYTES_RED = 16 * ELEMS  # read A, read B (+8 B result)
+BYTES_STEP = BYTES_EW + BYTES_RED
+METRIC = "achieved HBM GB/s, fused sin(A).*B+1 (+sum) on 4096x4096 f64 per GPU"
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in Path(self.path).read_text().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(rank: int):
+    """Synthetic data of the named shape: A ~ U(0,4pi), B ~ U(-1,1), seeded per rank."""
+    rng = np.random.default_rng(1234 + rank)
+    A = rng.uniform(0.0, 4.0 * math.pi, ELEMS)
+    B = rng.uniform(-1.0, 1.0, ELEMS)
+    return A, B
+
+
+# =====================================================================================================================
+# reference arm: the reference's CPU implementation of the path (oracle port; the Rust reference cannot be built here)
+# =====================================================================================================================
+def cpu_reference_step(orc, A2, B2, one):
+    """The unfused builtin sequence the reference CPU path executes (one host tensor per op, BroadcastPlan index math):
+    sin (sin.rs:265-270) -> times (times.rs:682-700) -> plus -> sum 'all' (sum.rs:996-1079)."""
+    t0 = orc.unary("sin", A2)
+    t1 = orc.elem_binary("mul", t0, B2)
+    C = orc.elem_binary("add", t1, one)
+    s = orc.sum_dims(C, [0, 1])
+    return C, float(s[0, 0])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle_binding import Oracle
+
+    orc = Oracle()
+    A, B = synth_inputs(0)
+    A2, B2 = A.reshape((N_SIDE, N_SIDE), order="F"), B.reshape((N_SIDE, N_SIDE), order="F")
+    one = np.array([[1.0]])
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_step(orc, A2, B2, one)
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(orc, A2, B2, one)
+        times.append(time.perf_counter() - t0)
+    total = time.perf_counter() - t_all
+    value = BYTES_STEP * args.steps / total / 1e9
+    sample = f"{args.steps} full passes of the 4096x4096 f64 step on 1 core (the reference CPU path is single-threaded: no rayon/BLAS on it)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": "elementwise-math fused chain + sum(), 4096x4096 f64, CPU reference path"},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from runmat_b200 import B200Provider, fusion_text as ft
+    from runmat_b200.provider import pinned_empty
+
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    p = B200Provider(local_rank, device_id=rank)
+    if world > 1:
+        # share ONE stream with torch so the NCCL all-reduce is ordered with the provider's kernels
+        p_stream = torch.cuda.current_stream().cuda_stream
+        from runmat_b200._capi import lib
+        import ctypes as C
+
+        lib.rm_set_stream(p._p, C.c_void_p(p_stream))
+
+    ew_shader, red_shader = ft.sin_mul_add_wgsl(), ft.sum_sin_mul_add_wgsl()
+    A, B = synth_inputs(rank)
+    shape = (N_SIDE, N_SIDE)
+    hA, hB = p.upload(A, shape), p.upload(B, shape)
+    hOne = p.upload(np.array([1.0]), (1, 1))
+
+    class CudaArray:  # zero-copy torch view of a provider buffer (for the NCCL all-reduce)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def step():
+        hC = p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS)
+        hS = p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1)
+        if world > 1:
+            ptr, n = p.device_ptr(hS)
+            t = torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}")
+            dist.all_reduce(t)
+        return hC, hS
+
+    def sync_all():
+        p.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        hC, hS = step()
+        p.free(hC)
+        p.free(hS)
+    sync_all()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier+sync on both sides ----------
+    t_before = p.telemetry_snapshot().kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    p.timer_begin()
+    last_sum = None
+    for _ in range(args.steps):
+        hC, hS = step()
+        p.free(hC)
+        if last_sum is not None:
+            p.free(last_sum)
+        last_sum = hS
+    ms = p.timer_end_ms()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = p.telemetry_snapshot().kernel_launches - t_before
+    checksum = float(p.download(last_sum)[0, 0])
+    p.free(last_sum)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = BYTES_STEP * world * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (fused elementwise, 24 B/elem): isolated launches, CUDA events ------------
+    def time_kernel(fn, reps):
+        p.synchronize()
+        p.timer_begin()
+        hs = [fn() for _ in range(reps)]
+        t = p.timer_end_ms()
+        for h in hs:
+            p.free(h)
+        return t / reps
+
+    reps = max(args.steps, 10)
+    ew_ms = time_kernel(lambda: p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS), reps)
+    red_ms = time_kernel(lambda: p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1), reps)
+    peak, peak_src = measured_peaks()
+    achieved = BYTES_EW / (ew_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "rm_fused_ew (C = sin(A).*B+1, 24 B/elem)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": ew_ms * 1e3,
+                "reduction_kernel": {"kernel": "rm_fused_red (sum(sin(A).*B+1), 16 B/elem)", "achieved": BYTES_RED / (red_ms * 1e-3) / 1e9,
+                                     "frac": BYTES_RED / (red_ms * 1e-3) / 1e9 / peak, "us_per_launch": red_ms * 1e3}}
+    prof = ROOT / "profiles" / "r01_traffic.json"
+    if prof.exists():
+        try:
+            roofline["traffic"] = json.loads(prof.read_text()).get("rm_fused_ew_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the same step through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----------
+    hostA, hostB, hostC = pinned_empty(ELEMS), pinned_empty(ELEMS), pinned_empty(ELEMS)
+    hostA[:] = A
+    hostB[:] = B
+
+    def e2e_step():
+        a = p.upload_ptr(hostA.ctypes.data, shape)
+        b = p.upload_ptr(hostB.ctypes.data, shape)
+        c = p.fused_elementwise(ew_shader, [a, b, hOne], shape, ELEMS)
+        s = p.fused_reduction(red_shader, [a, b], (1, 1), ELEMS, 1)
+        if world > 1:
+            ptr, n = p.device_ptr(s)
+            dist.all_reduce(torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}"))
+        p.download_into_ptr(c, hostC.ctypes.data, ELEMS)   # C back to the host (synchronises)
+        val = p.read_scalar(s, 0)
+        for h in (a, b, c, s):
+            p.free(h)
+        return val
+
+    e2e_step()
+    sync_all()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    p.timer_begin()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_ms = p.timer_end_ms()
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, wall_ms if world == 1 else e2e_ms)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e = {"value": BYTES_STEP * world * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 2 * ELEMS * 8,
+           "d2h_bytes_per_step": ELEMS * 8 + 8, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+           "note": "upload A,B from pinned host, fused elementwise + fused sum, download C and the sum"}
+
+    # ---- other configs of BASELINE.json, reported beside the headline (not the metric) --------------------------------
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra = extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray)
+        except Exception as e:  # an optional workload must never take the headline line down
+            extra = {"error": str(e)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle_binding import Oracle
+
+        orc = Oracle()
+        A2, B2 = A.reshape(shape, order="F"), B.reshape(shape, order="F")
+        one = np.array([[1.0]])
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            _, cpu_sum = cpu_reference_step(orc, A2, B2, one)
+            ts.append(time.perf_counter() - t0)
+        med = statistics.median(ts)
+        cpu_baseline = {"value": BYTES_STEP / med / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                        "sample": "3 full passes of the same 4096x4096 f64 step (median), oracle port of the unfused CPU builtins, 1 core",
+                        "seconds_per_step": med, "checksum_rel_diff_vs_gpu": abs(cpu_sum - checksum) / abs(cpu_sum)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "elementwise-math fused chain + sum(), 4096x4096 f64 per GPU (BASELINE.json configs[1])",
+                       "bytes_per_step_per_gpu": BYTES_STEP, "l2": "inputs (2x128 MiB) + output (128 MiB) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"{world} independent batches, one NCCL all-reduce of 1 f64 per step" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "checksum": checksum, "extra": extra,
+        }
+        print(json.dumps(line))
+    p.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
+    """configs[2] (matmul 8192^3, single GPU) and configs[4] (Monte-Carlo 1e8 x 256, sharded + one all-reduce)."""
+    out = {}
+    # Monte-Carlo: paths sharded in contiguous ranges; RNG addressing is global, result independent of `world`
+    M, T = 100_000_000, 256
+    lo, hi = rank * M // world, (rank + 1) * M // world
+    drift, scale = (0.05 - 0.5 * 0.2 ** 2) / 252.0, 0.2 * math.sqrt(1.0 / 252.0)
+    hS0 = p.fill((hi - lo, 1), 100.0)
+    p.set_rng_state(0)
+    for it in range(2):
+        p.set_rng_state(0)
+        p.synchronize()
+        if world > 1:
+            dist.barrier()
+        p.timer_begin()
+        hS = p.stochastic_evolution_sharded(hS0, drift, scale, T, lo, M)
+        hP = p.payoff_partial_sum(hS, 100.0)
+        if world > 1:
+            ptr, n = p.device_ptr(hP)
+            dist.all_reduce(torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}"))
+        ms = p.timer_end_ms()
+        price = p.read_scalar(hP, 0) / M * math.exp(-0.05 * T / 252.0)
+        p.free(hS)
+        p.free(hP)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    p.free(hS0)
+    out["monte_carlo"] = {"paths": M, "steps": T, "ms": ms, "path_steps_per_s": M * T / (ms * 1e-3), "price": price, "scaling": "strong",
+                          "collective": "one NCCL all-reduce of 1 f64" if world > 1 else None}
+    if world == 1:
+        n = 8192
+        rng = np.random.default_rng(7)
+        hA = p.upload(rng.uniform(-1, 1, n * n), (n, n))
+        hB = p.upload(rng.uniform(-1, 1, n * n), (n, n))
+        hC = p.matmul(hA, hB)
+        p.free(hC)
+        p.synchronize()
+        p.timer_begin()
+        reps = 2
+        for _ in range(reps):
+            p.free(p.matmul(hA, hB))
+        ms = p.timer_end_ms() / reps
+        out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "engine": "FP64 DMMA mma.sync.m8n8k4"}
+        p.free(hA)
+        p.free(hB)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 50:
+            args.steps = 5
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -293,7 +293,7 @@ typedef struct rm_image_normalize_desc {
 rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, const rm_image_normalize_desc* d,
                              rm_handle* out);
 typedef enum rm_imfilter_padding { RM_PAD_CONSTANT = 0, RM_PAD_REPLICATE, RM_PAD_SYMMETRIC, RM_PAD_CIRCULAR } rm_imfilter_padding;
-typedef enum rm_imfilter_shape { RM_IMF_SAME = 0, RM_IMF_FULL = 1 } rm_imfilter_shape;
+typedef enum rm_imfilter_shape { RM_IMF_SAME = 0, RM_IMF_FULL = 1, RM_IMF_VALID = 2 } rm_imfilter_shape;
 typedef enum rm_imfilter_mode { RM_IMF_CORR = 0, RM_IMF_CONV = 1 } rm_imfilter_mode;
 typedef struct rm_imfilter_options {
   rm_imfilter_padding padding;
@@ -313,6 +313,8 @@ rm_status rm_reset_telemetry(rm_provider* p);
 rm_status rm_timer_begin(rm_provider* p);
 rm_status rm_timer_end_ms(rm_provider* p, double* elapsed_ms); /* records + synchronises the end event */
 rm_status rm_flush_l2(rm_provider* p);                         /* writes a 256 MiB scratch buffer */
+rm_status rm_pinned_alloc(size_t bytes, void** out);           /* page-locked host memory for the e2e leg */
+rm_status rm_pinned_free(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,344 @@
+// image.cu — image_normalize (row a12), imfilter (row a13) and the value+index dim reductions (row a6).
+//
+// image_normalize reference semantics: crates/runmat-accelerate/src/simple_provider.rs:7893-7994
+//   per image b of a [B,H,W] column-major tensor (batch is the STRIDE-1 axis: stride_h = B, stride_w = B*H):
+//   mu = sum(x)/P; sigma = sqrt(sum((x-mu)^2)/P + eps); y = (x-mu)*(1/sigma) [*gain] [+bias] [max 0] [pow gamma].
+// The wgpu provider streams this in batch windows with three sweeps (shaders/image_normalize.rs,
+// provider/helpers.rs:96-380). B200 design: because batch is stride-1 the whole tensor is one contiguous
+// [B x P] matrix, so both sweeps are fully coalesced flat streams:
+//   sweep 1  per-image shifted moments (sum(x-K), sum((x-K)^2), K = first pixel) accumulated in f64 —
+//            algebraically the two-pass population variance, without a second statistics pass;
+//            per-block partials are combined in fixed order by a tiny finalize kernel (deterministic);
+//   sweep 2  normalise + gain/bias/clamp/gamma, one read + one write.
+// HBM traffic: 2 reads + 1 write per pixel (12 B/px f32); a 4K batch is far larger than L2, so the second
+// read cannot be served on-chip with a batch-fastest layout (DESIGN.md "image_normalize").
+#include "common.h"
+
+namespace rm {
+
+namespace {
+
+// ---- sweep 1: thread (b, lane) = (tid % B, tid / B); each lane strides over pixels ------------------------------
+// Works for any B <= 1024: consecutive threads read consecutive addresses (b fastest), fixed image per thread.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+moments_partial_kernel(const T* __restrict__ x, uint64_t B, uint64_t P, double* __restrict__ partial /*[grid][2][B]*/) {
+  extern __shared__ double sh[];  // [lanes][2][B]
+  const uint32_t lanes = blockDim.x / (uint32_t)B;  // >= 1
+  const uint32_t b = threadIdx.x % (uint32_t)B, lane = threadIdx.x / (uint32_t)B;
+  double s1 = 0.0, s2 = 0.0;
+  if (lane < lanes) {
+    const double K = (double)x[b];  // pixel 0 of image b
+    const uint64_t stride = (uint64_t)gridDim.x * lanes;
+    uint64_t p = (uint64_t)blockIdx.x * lanes + lane;
+    // 4 independent loads in flight per thread
+    for (; p + 3 * stride < P; p += 4 * stride) {
+      const double d0 = (double)x[b + p * B] - K, d1 = (double)x[b + (p + stride) * B] - K;
+      const double d2 = (double)x[b + (p + 2 * stride) * B] - K, d3 = (double)x[b + (p + 3 * stride) * B] - K;
+      s1 += (d0 + d1) + (d2 + d3);
+      s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    for (; p < P; p += stride) { const double d = (double)x[b + p * B] - K; s1 += d; s2 += d * d; }
+    sh[(lane * 2 + 0) * B + b] = s1;
+    sh[(lane * 2 + 1) * B + b] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < B) {
+    double a1 = 0.0, a2 = 0.0;
+    for (uint32_t l = 0; l < lanes; ++l) { a1 += sh[(l * 2 + 0) * B + threadIdx.x]; a2 += sh[(l * 2 + 1) * B + threadIdx.x]; }
+    partial[((uint64_t)blockIdx.x * 2 + 0) * B + threadIdx.x] = a1;
+    partial[((uint64_t)blockIdx.x * 2 + 1) * B + threadIdx.x] = a2;
+  }
+}
+
+// stats[b] = {mean, inv_sigma}
+template <typename T>
+__global__ void moments_finalize_kernel(const T* __restrict__ x, const double* __restrict__ partial, uint32_t nblocks, uint64_t B, uint64_t P,
+                                        double eps, double* __restrict__ stats) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (uint32_t i = 0; i < nblocks; ++i) { s1 += partial[((uint64_t)i * 2 + 0) * B + b]; s2 += partial[((uint64_t)i * 2 + 1) * B + b]; }
+  const double K = (double)x[b];
+  const double n = (double)P;
+  const double dm = s1 / n;                       // mean of (x-K)
+  double var = (s2 - s1 * dm) / n;                // sum((x-mean)^2)/P
+  if (var < 0.0) var = 0.0;
+  const double sigma = sqrt(var + eps);
+  stats[2 * b] = K + dm;
+  stats[2 * b + 1] = sigma > 0.0 ? 1.0 / sigma : 0.0;  // simple_provider.rs:7962
+}
+
+struct NormParams {
+  int has_gain, has_bias, has_gamma, clamp_zero;
+  double gain, bias, gamma;
+};
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_kernel(const T* __restrict__ x, T* __restrict__ y, uint64_t B, uint64_t total, const double* __restrict__ stats,
+                 const __grid_constant__ NormParams np) {
+  // flat stream; image index = e % B. VEC elements per thread per iteration (16-byte accesses when VEC>1).
+  const uint64_t nvec = total / VEC;
+  const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += nthr) {
+    T v[VEC];
+    if (VEC == 4) *reinterpret_cast<float4*>(v) = __ldcs(reinterpret_cast<const float4*>(x) + i);
+    else if (VEC == 2) *reinterpret_cast<double2*>(v) = __ldcs(reinterpret_cast<const double2*>(x) + i);
+    else v[0] = x[i];
+    const uint64_t e0 = i * VEC;
+    uint32_t b = (uint32_t)(e0 % B);
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) {
+      const T mean = (T)stats[2 * b], inv = (T)stats[2 * b + 1];
+      T val = (v[l] - mean) * inv;
+      if (np.has_gain) val *= (T)np.gain;
+      if (np.has_bias) val += (T)np.bias;
+      if (np.clamp_zero) val = val > (T)0 ? val : (T)0;  // f64::max(v, 0.0): NaN -> 0
+      if (np.has_gamma) val = sizeof(T) == 4 ? (T)powf((float)val, (float)np.gamma) : (T)pow((double)val, np.gamma);
+      v[l] = val;
+      if (++b == B) b = 0;
+    }
+    if (VEC == 4) __stcs(reinterpret_cast<float4*>(y) + i, *reinterpret_cast<float4*>(v));
+    else if (VEC == 2) __stcs(reinterpret_cast<double2*>(y) + i, *reinterpret_cast<double2*>(v));
+    else y[i] = v[0];
+  }
+  // ragged tail
+  for (uint64_t e = nvec * VEC + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthr) {
+    const uint32_t b = (uint32_t)(e % B);
+    const T mean = (T)stats[2 * b], inv = (T)stats[2 * b + 1];
+    T val = (x[e] - mean) * inv;
+    if (np.has_gain) val *= (T)np.gain;
+    if (np.has_bias) val += (T)np.bias;
+    if (np.clamp_zero) val = val > (T)0 ? val : (T)0;
+    if (np.has_gamma) val = sizeof(T) == 4 ? (T)powf((float)val, (float)np.gamma) : (T)pow((double)val, np.gamma);
+    y[e] = val;
+  }
+}
+
+// ---- imfilter (image/filters/imfilter.rs:476-745) ---------------------------------------------------------------------
+struct FilterParams {
+  uint64_t ie[3], ke[3], oe[3];
+  int64_t origin[3], base[3];
+  int padding, mode;
+  double cval;
+};
+__device__ __forceinline__ int64_t clamp_index(int64_t c, int64_t len) { return (len <= 0 || c <= 0) ? 0 : (c >= len ? len - 1 : c); }
+__device__ __forceinline__ int64_t wrap_index(int64_t c, int64_t len) { if (len <= 0) return 0; c %= len; if (c < 0) c += len; return c; }
+__device__ __forceinline__ int64_t reflect_index(int64_t c, int64_t len) {
+  if (len <= 1) return 0;
+  const int64_t period = 2 * len - 2;
+  int64_t v = c % period;
+  if (v < 0) v += period;
+  if (v >= len) v = period - v;
+  return v;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+imfilter_kernel(const T* __restrict__ img, const T* __restrict__ ker, T* __restrict__ out, uint64_t total, const __grid_constant__ FilterParams fp) {
+  const uint64_t istr1 = fp.ie[0], istr2 = fp.ie[0] * fp.ie[1];
+  const uint64_t kstr1 = fp.ke[0], kstr2 = fp.ke[0] * fp.ke[1];
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (uint64_t)gridDim.x * blockDim.x) {
+    const int64_t o0 = (int64_t)(o % fp.oe[0]), o1 = (int64_t)((o / fp.oe[0]) % fp.oe[1]), o2 = (int64_t)(o / (fp.oe[0] * fp.oe[1]));
+    T sum = (T)0;
+    // kernel points in column-major order; sum += k * sample (imfilter.rs:731-745), no FMA
+    for (uint64_t k2 = 0; k2 < fp.ke[2]; ++k2)
+      for (uint64_t k1 = 0; k1 < fp.ke[1]; ++k1)
+        for (uint64_t k0 = 0; k0 < fp.ke[0]; ++k0) {
+          const uint64_t lin = fp.mode == 0 ? k0 + k1 * kstr1 + k2 * kstr2
+                                            : (fp.ke[0] - 1 - k0) + (fp.ke[1] - 1 - k1) * kstr1 + (fp.ke[2] - 1 - k2) * kstr2;
+          const T kv = __ldg(ker + lin);
+          int64_t c[3] = {o0 + fp.base[0] + ((int64_t)k0 - fp.origin[0]), o1 + fp.base[1] + ((int64_t)k1 - fp.origin[1]),
+                          o2 + fp.base[2] + ((int64_t)k2 - fp.origin[2])};
+          bool constant = false;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int64_t len = (int64_t)fp.ie[d];
+            if (c[d] < 0 || c[d] >= len) {
+              if (fp.padding == 0) constant = true;
+              else c[d] = fp.padding == 1 ? clamp_index(c[d], len) : (fp.padding == 3 ? wrap_index(c[d], len) : reflect_index(c[d], len));
+            }
+          }
+          const T sample = constant ? (T)fp.cval : img[(uint64_t)c[0] + (uint64_t)c[1] * istr1 + (uint64_t)c[2] * istr2];
+          sum += kv * sample;
+        }
+    out[o] = sum;
+  }
+}
+
+// ---- value + index reductions along one dim of [pre, n, post] (simple_provider.rs:7387-7445) ---------------------------
+template <typename T, bool IS_MIN>
+__global__ void minmax_dim_kernel(const T* __restrict__ a, T* __restrict__ vals, T* __restrict__ idx, uint64_t pre, uint64_t n, uint64_t post) {
+  // one warp per slice; lanes stride over n, then a shuffle argmin/argmax with smallest-index tie-break
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= pre * post) return;
+  const uint64_t s_lo = warp % pre, s_hi = warp / pre;
+  const T* base = a + s_lo + s_hi * pre * n;
+  T best = IS_MIN ? (T)INFINITY : (T)-INFINITY;
+  uint64_t best_i = 0;  // host: idx initialised to 1 (first element) when nothing compares strictly better
+  for (uint64_t r = lane; r < n; r += 32) {
+    const T v = base[r * pre];
+    if (IS_MIN ? v < best : v > best) { best = v; best_i = r; }
+  }
+  // lanes that saw no strictly-better value keep (identity, 0); ties resolve to the smallest index
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const T ov = __shfl_xor_sync(0xffffffffu, best, off);
+    const uint64_t oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+    const bool better = IS_MIN ? ov < best : ov > best;
+    if (better || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if (lane == 0) { vals[warp] = best; idx[warp] = (T)(best_i + 1); }
+}
+
+}  // namespace
+
+}  // namespace rm
+
+using namespace rm;
+
+RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, const rm_image_normalize_desc* d, rm_handle* out) {
+  RM_REQUIRE(p && input && d && out, RM_INVALID_ARG, "image_normalize: bad arguments");
+  // simple_provider.rs:7899-7917
+  RM_REQUIRE(isfinite(d->epsilon), RM_ERROR, "image_normalize: epsilon must be finite");
+  RM_REQUIRE(d->epsilon >= 0.0, RM_ERROR, "image_normalize: epsilon must be non-negative");
+  RM_REQUIRE(input->rank == 3, RM_ERROR, "image_normalize: expected 3-D tensor, got rank %u", input->rank);
+  RM_REQUIRE(input->shape[0] == d->batch && input->shape[1] == d->height && input->shape[2] == d->width, RM_ERROR,
+             "image_normalize: descriptor dims (%llu, %llu, %llu) do not match tensor shape", (unsigned long long)d->batch,
+             (unsigned long long)d->height, (unsigned long long)d->width);
+  DeviceGuard g(p->ordinal);
+  void* src;
+  RM_TRY(resolve(p, input, &src, nullptr));
+  const uint64_t B = d->batch, P = d->height * d->width, total = B * P;
+  void* dst;
+  RM_TRY(alloc_tensor(p, input->shape, 3, out, &dst));
+  if (total == 0) return RM_OK;
+  RM_REQUIRE(B <= 1024, RM_UNSUPPORTED, "image_normalize: batch %llu > 1024 not supported by provider", (unsigned long long)B);
+
+  const uint32_t threads = 1024 - (1024 % (uint32_t)B);  // whole number of pixel lanes
+  const uint32_t lanes = threads / (uint32_t)B;
+  uint32_t nblocks = (uint32_t)std::min<uint64_t>((uint64_t)p->prop.multiProcessorCount * 2, std::max<uint64_t>(1, P / (lanes * 4ull)));
+  const size_t partial_bytes = (size_t)nblocks * 2 * B * sizeof(double);
+  const size_t stats_off = ((partial_bytes + 255) / 256) * 256;
+  rm_status st = ensure_scratch(p, stats_off + 2 * B * sizeof(double));
+  if (st != RM_OK) { rm_free(p, out); return st; }
+  double* partial = (double*)p->reduce_scratch;
+  double* stats = (double*)((char*)p->reduce_scratch + stats_off);
+  const size_t sh = (size_t)lanes * 2 * B * sizeof(double);
+  NormParams np{d->has_gain, d->has_bias, d->has_gamma, d->clamp_zero, d->gain, d->bias, d->gamma};
+  const unsigned ngrid = (unsigned)std::min<uint64_t>((total / 4 + 255) / 256 + 1, (uint64_t)p->prop.multiProcessorCount * 16);
+  if (p->precision == RM_F64) {
+    cudaFuncSetAttribute(moments_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    moments_partial_kernel<double><<<nblocks, threads, sh, p->stream>>>((const double*)src, B, P, partial);
+    moments_finalize_kernel<double><<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>((const double*)src, partial, nblocks, B, P, d->epsilon, stats);
+    normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
+  } else {
+    cudaFuncSetAttribute(moments_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
+    moments_finalize_kernel<float><<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
+    normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "image_normalize launch failed: %s", cudaGetErrorString(e)); }
+  count_launch(p, 3);
+  return RM_OK;
+}
+
+RM_EXPORT rm_status rm_imfilter(rm_provider* p, const rm_handle* image, const rm_handle* kernel, const rm_imfilter_options* opt, rm_handle* out) {
+  RM_REQUIRE(p && image && kernel && opt && out, RM_INVALID_ARG, "imfilter: bad arguments");
+  DeviceGuard g(p->ordinal);
+  void *pi, *pk;
+  uint64_t ni, nk;
+  RM_TRY(resolve(p, image, &pi, &ni));
+  RM_TRY(resolve(p, kernel, &pk, &nk));
+  RM_REQUIRE(nk > 0, RM_ERROR, "imfilter: filter must be non-empty along every dimension");  // imfilter.rs:483-488
+  const uint32_t rank = std::max<uint32_t>(std::max(image->rank, kernel->rank), 2);
+  RM_REQUIRE(rank <= 3, RM_UNSUPPORTED, "imfilter: rank %u not supported by provider (max 3)", rank);
+  FilterParams fp{};
+  for (int d = 0; d < 3; ++d) {
+    fp.ie[d] = d < (int)image->rank ? image->shape[d] : 1;
+    fp.ke[d] = d < (int)kernel->rank ? kernel->shape[d] : 1;
+    RM_REQUIRE(!(d >= (int)std::max<uint32_t>(image->rank, 2) && fp.ke[d] > 1), RM_ERROR,
+               "imfilter: filter dimension %d is %llu, but the image has no corresponding axis", d + 1, (unsigned long long)fp.ke[d]);
+    RM_REQUIRE(fp.ie[d] != 0, RM_ERROR, "imfilter: image must not have zero-length dimensions");
+    fp.origin[d] = (int64_t)(fp.ke[d] / 2);
+    if (opt->shape == RM_IMF_FULL) { fp.oe[d] = fp.ie[d] + fp.ke[d] - 1; fp.base[d] = fp.origin[d] - ((int64_t)fp.ke[d] - 1); }
+    else if (opt->shape == RM_IMF_SAME) { fp.oe[d] = fp.ie[d]; fp.base[d] = 0; }
+    else { fp.oe[d] = fp.ie[d] >= fp.ke[d] ? fp.ie[d] - fp.ke[d] + 1 : 0; fp.base[d] = fp.origin[d]; }
+  }
+  fp.padding = (int)opt->padding;
+  fp.mode = (int)opt->mode;
+  fp.cval = opt->constant_value;
+  // final_shape: trailing singleton dims beyond the image rank are dropped (imfilter.rs:541-547)
+  uint64_t oshape[3] = {fp.oe[0], fp.oe[1], fp.oe[2]};
+  uint32_t orank = 3;
+  while (orank > std::max<uint32_t>(image->rank, 2) && oshape[orank - 1] == 1) --orank;
+  void* po;
+  RM_TRY(alloc_tensor(p, oshape, orank, out, &po));
+  const uint64_t total = fp.oe[0] * fp.oe[1] * fp.oe[2];
+  if (total == 0) return RM_OK;
+  const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 32);
+  if (p->precision == RM_F64) imfilter_kernel<double><<<grid, 256, 0, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, total, fp);
+  else imfilter_kernel<float><<<grid, 256, 0, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, total, fp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "imfilter launch failed: %s", cudaGetErrorString(e)); }
+  count_launch(p);
+  return RM_OK;
+}
+
+static rm_status minmax_dim(rm_provider* p, const rm_handle* a, uint32_t dim, bool is_min, rm_handle* values, rm_handle* indices) {
+  RM_REQUIRE(p && a && values && indices, RM_INVALID_ARG, "reduce_min/max_dim: bad arguments");
+  const uint32_t rank = std::max<uint32_t>(a->rank, 2);
+  RM_REQUIRE(dim < rank, RM_ERROR, "reduce_%s_dim: dim %u out of range", is_min ? "min" : "max", dim);
+  DeviceGuard g(p->ordinal);
+  void* src;
+  RM_TRY(resolve(p, a, &src, nullptr));
+  uint64_t pre = 1, n = 1, post = 1, oshape[RM_MAX_RANK];
+  for (uint32_t d = 0; d < rank; ++d) {
+    const uint64_t e = d < a->rank ? a->shape[d] : 1;
+    if (d < dim) pre *= e; else if (d == dim) n = e; else post *= e;
+    oshape[d] = d == dim ? 1 : e;
+  }
+  void *pv, *pidx;
+  RM_TRY(alloc_tensor(p, oshape, rank, values, &pv));
+  rm_status st = alloc_tensor(p, oshape, rank, indices, &pidx);
+  if (st != RM_OK) { rm_free(p, values); return st; }
+  const uint64_t slices = pre * post;
+  if (slices == 0) return RM_OK;
+  const uint64_t blocks = (slices * 32 + 255) / 256;
+  if (p->precision == RM_F64) {
+    if (is_min) minmax_dim_kernel<double, true><<<(unsigned)blocks, 256, 0, p->stream>>>((const double*)src, (double*)pv, (double*)pidx, pre, n, post);
+    else minmax_dim_kernel<double, false><<<(unsigned)blocks, 256, 0, p->stream>>>((const double*)src, (double*)pv, (double*)pidx, pre, n, post);
+  } else {
+    if (is_min) minmax_dim_kernel<float, true><<<(unsigned)blocks, 256, 0, p->stream>>>((const float*)src, (float*)pv, (float*)pidx, pre, n, post);
+    else minmax_dim_kernel<float, false><<<(unsigned)blocks, 256, 0, p->stream>>>((const float*)src, (float*)pv, (float*)pidx, pre, n, post);
+  }
+  RM_LAUNCH_CHECK();
+  count_launch(p);
+  return RM_OK;
+}
+RM_EXPORT rm_status rm_reduce_max_dim(rm_provider* p, const rm_handle* a, uint32_t dim, rm_handle* values, rm_handle* indices) { return minmax_dim(p, a, dim, false, values, indices); }
+RM_EXPORT rm_status rm_reduce_min_dim(rm_provider* p, const rm_handle* a, uint32_t dim, rm_handle* values, rm_handle* indices) { return minmax_dim(p, a, dim, true, values, indices); }
+
+// a9 (mldivide) is a "next" row: not yet provided; callers fall back to host exactly as the
+// wgpu provider's own implementation does today (download -> host solve -> upload, provider/ops/solve.rs:131-205).
+RM_EXPORT rm_status rm_mldivide(rm_provider*, const rm_handle*, const rm_handle*, rm_handle*) {
+  return fail(RM_UNSUPPORTED, "mldivide not supported by provider");
+}
+
+RM_EXPORT rm_status rm_warmup(rm_provider* p) {
+  RM_REQUIRE(p, RM_INVALID_ARG, "null provider");
+  DeviceGuard g(p->ordinal);
+  // pre-compile the most common fused programs (mirrors AccelProvider::warmup, lib.rs:3010)
+  uint64_t shp[2] = {8, 8};
+  rm_handle a, b, c;
+  RM_TRY(rm_ones(p, shp, 2, &a));
+  rm_status st = rm_elem_add(p, &a, &a, &b);
+  if (st == RM_OK) { rm_free(p, &b); st = rm_elem_mul(p, &a, &a, &b); }
+  if (st == RM_OK) { rm_free(p, &b); st = rm_reduce_sum(p, &a, &c); }
+  if (st == RM_OK) rm_free(p, &c);
+  rm_free(p, &a);
+  if (st == RM_OK) RM_CUDA(cudaStreamSynchronize(p->stream));
+  return st;
+}

@@ -7,6 +7,7 @@
 // (the reference keeps two: BINARY/UNARY/SCALAR_SHADER op-code switches in backend/wgpu/shaders/elementwise.rs
 // next to the runtime-generated fused shaders).
 #include <algorithm>
+#include <memory>
 
 #include "common.h"
 
@@ -120,6 +121,45 @@ rm_status broadcast_shape(const rm_handle* a, const rm_handle* b, uint64_t* out,
 
 rm_status empty_result(rm_provider* p, const uint64_t* shape, uint32_t rank, rm_handle* out) { return alloc_tensor(p, shape, rank, out, nullptr); }
 
+// Parsed-program cache keyed by a 64-bit hash of the shader text (+length): a repeated fused call costs one hash of
+// the text instead of a re-parse, and the kernel-cache key stays short. Mirrors the reference's thread-local plan
+// cache (fusion.rs:679-747) on the provider side.
+uint64_t text_hash(const char* s, size_t* len_out) {
+  uint64_t h = 1469598103934665603ULL;
+  size_t n = 0;
+  for (; s[n]; ++n) { h ^= (unsigned char)s[n]; h *= 1099511628211ULL; }
+  *len_out = n;
+  return h;
+}
+template <typename Prog>
+struct ParsedCache {
+  std::mutex mu;
+  std::unordered_map<std::string, std::shared_ptr<Prog>> map;
+};
+ParsedCache<ElementwiseProgram> g_ew_cache;
+ParsedCache<ReductionProgram> g_red_cache;
+
+template <typename Prog, typename ParseFn>
+rm_status parsed(ParsedCache<Prog>& cache, const char* shader, ParseFn parse, std::shared_ptr<Prog>* out, std::string* key) {
+  size_t len;
+  const uint64_t h = text_hash(shader, &len);
+  char buf[48];
+  snprintf(buf, sizeof buf, "%016llx:%zu", (unsigned long long)h, len);
+  *key = buf;
+  {
+    std::lock_guard<std::mutex> lk(cache.mu);
+    auto it = cache.map.find(*key);
+    if (it != cache.map.end()) { *out = it->second; return RM_OK; }
+  }
+  auto prog = std::make_shared<Prog>();
+  std::string err;
+  if (!parse(shader, prog.get(), &err)) return fail(RM_COMPILE_ERROR, "%s", err.c_str());
+  std::lock_guard<std::mutex> lk(cache.mu);
+  cache.map[*key] = prog;
+  *out = prog;
+  return RM_OK;
+}
+
 }  // namespace
 
 // =============================================================================================================
@@ -212,11 +252,11 @@ RM_EXPORT rm_status rm_fused_elementwise_multi(rm_provider* p, const char* shade
   RM_REQUIRE(n_inputs > 0, RM_ERROR, "fused_elementwise: no inputs");
   DeviceGuard g(p->ordinal);
   ScopedWall wall(p->t_fused_elementwise);
-  ElementwiseProgram prog;
-  std::string err;
-  if (!parse_elementwise_wgsl(shader, &prog, &err)) return fail(RM_COMPILE_ERROR, "%s", err.c_str());
-  RM_REQUIRE(prog.n_outputs == num_outputs, RM_INVALID_ARG, "fused_elementwise: shader writes %u outputs, caller expects %u", prog.n_outputs, num_outputs);
-  return run_elementwise_program(p, prog, std::string("wgsl:") + shader, inputs, n_inputs, output_shape, rank, len, outs);
+  std::shared_ptr<ElementwiseProgram> prog;
+  std::string key;
+  RM_TRY(parsed(g_ew_cache, shader, parse_elementwise_wgsl, &prog, &key));
+  RM_REQUIRE(prog->n_outputs == num_outputs, RM_INVALID_ARG, "fused_elementwise: shader writes %u outputs, caller expects %u", prog->n_outputs, num_outputs);
+  return run_elementwise_program(p, *prog, "wgsl:" + key, inputs, n_inputs, output_shape, rank, len, outs);
 }
 
 RM_EXPORT rm_status rm_fused_elementwise(rm_provider* p, const char* shader, const rm_handle* inputs, uint32_t n_inputs,
@@ -234,16 +274,17 @@ RM_EXPORT rm_status rm_fused_reduction(rm_provider* p, const char* shader, const
   RM_REQUIRE(p && shader && inputs && out, RM_INVALID_ARG, "fused_reduction: bad arguments");
   DeviceGuard g(p->ordinal);
   ScopedWall wall(p->t_fused_reduction);
-  ReductionProgram prog;
-  std::string err;
-  if (!parse_reduction_wgsl(shader, &prog, &err)) return fail(RM_COMPILE_ERROR, "%s", err.c_str());
+  std::shared_ptr<ReductionProgram> progp;
+  std::string key;
+  RM_TRY(parsed(g_red_cache, shader, parse_reduction_wgsl, &progp, &key));
+  const ReductionProgram& prog = *progp;
   // ReductionFlavor::scale (lib.rs:876-887)
   int use_div = 0;
   double factor = 1.0;
   if (flavor == RM_FLAVOR_MEAN) { use_div = reduce_len ? 1 : 0; factor = reduce_len ? (double)reduce_len : 1.0; }
   else if (flavor == RM_FLAVOR_CUSTOM) factor = custom_scale;
   const RedLayout layout = prog.axis == 0 ? RedLayout::Contig : RedLayout::Strided;
-  return run_reduction_program(p, prog, std::string("wgsl:") + shader, RedOp::Sum, layout, inputs, n_inputs, output_shape, rank,
+  return run_reduction_program(p, prog, "wgsl:" + key, RedOp::Sum, layout, inputs, n_inputs, output_shape, rank,
                                reduce_len, num_slices, /*inner=*/num_slices, use_div, factor, out);
 }
 
@@ -361,4 +402,38 @@ RM_EXPORT rm_status rm_reduce_moments_nd(rm_provider* p, const rm_handle* a, con
   rm_status st = reduce_nd(p, a, dims, n_dims, "(v0 * v0)", ex2_out);
   if (st != RM_OK) { std::string msg = last_error(); rm_free(p, mean_out); set_error("%s", msg.c_str()); }
   return st;
+}
+
+// Device-free: NVRTC-compiles the unfused operator surface into the on-disk cubin cache (build() calls this on the
+// CPU box so a fresh GPU box does not pay ~0.3 s of NVRTC per first use of each operator).
+RM_EXPORT rm_status rm_debug_precompile_ops(rm_precision precision, uint32_t* compiled) {
+  rm_provider fake;
+  fake.precision = precision;
+  uint32_t n = 0;
+  std::vector<char> cubin;
+  std::string log;
+  auto ew = [&](uint32_t n_in, const char* expr, EwVariant v, uint32_t mask) -> rm_status {
+    ElementwiseProgram prog = one_node(&fake, n_in, expr);
+    RM_TRY(compile_cuda_to_cubin(emit_elementwise_cuda(prog, v, mask), "rm_fused_ew", &cubin, &log));
+    ++n;
+    return RM_OK;
+  };
+  for (int op = 0; op < RM_BIN__COUNT; ++op) {
+    RM_TRY(ew(2, binary_expr((rm_binary_op)op), EwVariant::Flat, 0));
+    RM_TRY(ew(2, binary_expr((rm_binary_op)op), EwVariant::Flat, 2));
+    RM_TRY(ew(2, binary_expr((rm_binary_op)op), EwVariant::Broadcast, 0));
+  }
+  for (int op = 0; op < RM_UN__COUNT; ++op) RM_TRY(ew(1, unary_expr((rm_unary_op)op), EwVariant::Flat, 0));
+  for (int op = 0; op < RM_SC__COUNT; ++op) RM_TRY(ew(2, scalar_expr((rm_scalar_op)op), EwVariant::Flat, 2));
+  const char* vals[] = {"v0", "(v0 * v0)"};
+  for (const char* val : vals)
+    for (int op = 0; op < 4; ++op)
+      for (int layout = 0; layout < 2; ++layout) {
+        if (val != vals[0] && op != 0) continue;
+        ReductionProgram prog = red_program(&fake, val, false);
+        RM_TRY(compile_cuda_to_cubin(emit_reduction_cuda(prog, (RedOp)op, layout ? RedLayout::Strided : RedLayout::Contig), "rm_fused_red", &cubin, &log));
+        ++n;
+      }
+  if (compiled) *compiled = n;
+  return RM_OK;
 }

@@ -153,6 +153,11 @@ __global__ void scatter_linear_kernel(T* __restrict__ dst, const uint32_t* __res
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[idx[i]] = vals[i];
 }
 
+template <typename T>
+__global__ void scatter_pos_kernel(T* __restrict__ dst, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ pos, const T* __restrict__ vals, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[idx[i]] = vals[pos[i]];
+}
+
 static inline unsigned grid_for(rm_provider* p, uint64_t n, unsigned block = 256) {
   uint64_t b = (n + block - 1) / block;
   uint64_t cap = (uint64_t)p->prop.multiProcessorCount * 16;
@@ -563,16 +568,45 @@ RM_EXPORT rm_status rm_scatter_linear(rm_provider* p, const rm_handle* target, c
   RM_TRY(resolve(p, target, &dst, &len));
   RM_TRY(resolve(p, values, &vals, &vlen));
   RM_REQUIRE(vlen == n, RM_INVALID_ARG, "scatter_linear: values raw length %llu does not match index count %llu", (unsigned long long)vlen, (unsigned long long)n);
-  uint32_t* didx = nullptr;
-  RM_TRY(upload_indices(p, indices, n, len, "scatter_linear", &didx));
-  if (n) {
-    // duplicates: the host loop lets the LAST position win (simple_provider.rs:2699-2711); a parallel scatter
-    // cannot order writes, so duplicate indices are resolved on the host by keeping only the last occurrence.
-    DISPATCH_T(p, (scatter_linear_kernel<double><<<grid_for(p, n), 256, 0, p->stream>>>((double*)dst, didx, (const double*)vals, n)),
-               (scatter_linear_kernel<float><<<grid_for(p, n), 256, 0, p->stream>>>((float*)dst, didx, (const float*)vals, n)));
-    count_launch(p);
+  // duplicates: the host loop lets the LAST position win (simple_provider.rs:2699-2711). A parallel scatter cannot
+  // order writes, so when duplicates exist only the last occurrence of each index is kept (host-side filter).
+  std::vector<uint32_t> fidx;
+  std::vector<uint32_t> fpos;
+  {
+    std::unordered_map<uint32_t, uint64_t> last;
+    last.reserve(n * 2);
+    bool dup = false;
+    for (uint64_t i = 0; i < n; ++i) {
+      auto it = last.find(indices[i]);
+      if (it != last.end()) { dup = true; it->second = i; } else last.emplace(indices[i], i);
+    }
+    if (dup) {
+      RM_REQUIRE(n < (1ull << 32), RM_UNSUPPORTED, "scatter_linear: too many indices");
+      for (uint64_t i = 0; i < n; ++i)
+        if (last[indices[i]] == i) { fidx.push_back(indices[i]); fpos.push_back((uint32_t)i); }
+    }
   }
-  cudaFreeAsync(didx, p->stream);
+  uint32_t* didx = nullptr;
+  if (fidx.empty()) {
+    RM_TRY(upload_indices(p, indices, n, len, "scatter_linear", &didx));
+    if (n) {
+      DISPATCH_T(p, (scatter_linear_kernel<double><<<grid_for(p, n), 256, 0, p->stream>>>((double*)dst, didx, (const double*)vals, n)),
+                 (scatter_linear_kernel<float><<<grid_for(p, n), 256, 0, p->stream>>>((float*)dst, didx, (const float*)vals, n)));
+      count_launch(p);
+    }
+    cudaFreeAsync(didx, p->stream);
+  } else {
+    const uint64_t m = fidx.size();
+    uint32_t* dpos = nullptr;
+    RM_TRY(upload_indices(p, fidx.data(), m, len, "scatter_linear", &didx));
+    rm_status st = upload_indices(p, fpos.data(), m, n, "scatter_linear", &dpos);
+    if (st != RM_OK) { cudaFreeAsync(didx, p->stream); return st; }
+    DISPATCH_T(p, (scatter_pos_kernel<double><<<grid_for(p, m), 256, 0, p->stream>>>((double*)dst, didx, dpos, (const double*)vals, m)),
+               (scatter_pos_kernel<float><<<grid_for(p, m), 256, 0, p->stream>>>((float*)dst, didx, dpos, (const float*)vals, m)));
+    count_launch(p);
+    cudaFreeAsync(didx, p->stream);
+    cudaFreeAsync(dpos, p->stream);
+  }
   RM_LAUNCH_CHECK();
   return RM_OK;
 }

@@ -454,5 +454,8 @@ def pinned_empty(n: int, dtype=np.float64) -> np.ndarray:
     _check(lib.rm_pinned_alloc(C.c_size_t(nbytes), C.byref(ptr)))
     buf = (C.c_char * nbytes).from_address(ptr.value)
     arr = np.frombuffer(buf, dtype=dtype, count=n)
-    arr._rm_pinned_ptr = ptr  # type: ignore[attr-defined]
+    _PINNED.append((ptr, buf))  # freed at process exit
     return arr
+
+
+_PINNED: list = []

@@ -1,0 +1,88 @@
+"""Writes tests/golden/reference_kats.json: literal known-answer vectors transcribed from the reference's own
+unit tests (paths relative to /root/reference/crates). The reference is Rust and cannot be executed here, so
+these are the literals its tests assert, not outputs of running it. Re-run to regenerate the JSON."""
+import json
+from pathlib import Path
+
+NAN, INF = "nan", "inf"
+kats = {
+    "elem_binary": [
+        {"src": "runmat-runtime/src/builtins/math/elementwise/times.rs:932-943 times_matrix_scalar", "op": "mul",
+         "a": {"shape": [2, 2], "data": [1, 2, 3, 4]}, "b": {"shape": [1, 1], "data": [2]},
+         "out": {"shape": [2, 2], "data": [2, 4, 6, 8]}},
+        {"src": "runmat-runtime/src/builtins/math/elementwise/times.rs:947-962 times_row_column_broadcast", "op": "mul",
+         "a": {"shape": [3, 1], "data": [1, 2, 3]}, "b": {"shape": [1, 3], "data": [10, 20, 30]},
+         "out": {"shape": [3, 3], "data": [10, 20, 30, 20, 40, 60, 30, 60, 90]}},
+    ],
+    # MATLAB-semantics values of mod/rem for the inputs of mod_real_parity_matrix_matches_expected_values /
+    # rem_real_parity_matrix_matches_expected_values (runmat-vm/tests/fusion_gpu.rs:3056-3222), evaluated by
+    # hand from mod_real_expected/rem_real_expected (:2965-3030); b==0 -> NaN is the reference's choice.
+    "mod": [[-5.5, 2, 0.5], [-1.25, 2, 0.75], [5.5, 2, 1.5], [6, 2, 0], [6, 3, 0], [6, 4, 2], [-1.25, 3, 1.75], [5.5, 4, 1.5],
+            [6, 0, NAN], [6, INF, 6], [NAN, 2, NAN], [5, INF, 5], [INF, 2, NAN], [4, 0, NAN],
+            [5, "-inf", "-inf"], [-5, "-inf", -5], [-5, INF, INF], [0, "-inf", 0]],
+    "rem": [[-5.5, 2, -1.5], [-1.25, 2, -1.25], [5.5, 2, 1.5], [6, 2, 0], [6, 3, 0], [6, 4, 2], [-1.25, 3, -1.25], [5.5, 4, 1.5],
+            [6, 0, NAN], [6, INF, 6], [NAN, 2, NAN], [5, INF, 5], [INF, 2, NAN], [4, 0, NAN]],
+    "sum": [
+        {"src": "runmat-runtime/src/builtins/math/reduction/sum.rs:1445-1456 sum_matrix_default_dimension",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "dims": [0], "omitnan": False, "out": {"shape": [1, 3], "data": [5, 7, 9]}},
+        {"src": "sum.rs:1460-1472 sum_matrix_dimension_two",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "dims": [1], "omitnan": False, "out": {"shape": [2, 1], "data": [6, 15]}},
+        {"src": "sum.rs:1476-1481 sum_all_dimension",
+         "a": {"shape": [2, 3], "data": [1, 2, 3, 4, 5, 6]}, "dims": [0, 1], "omitnan": False, "out": {"shape": [1, 1], "data": [21]}},
+        {"src": "sum.rs:1485-1500 sum_vecdim_multiple_axes",
+         "a": {"shape": [3, 4, 2], "data": list(range(1, 25))}, "dims": [0, 2], "omitnan": False,
+         "out": {"shape": [1, 4, 1], "data": [48, 66, 84, 102]}},
+        {"src": "sum.rs:1504-1508 sum_with_omit_nan_default_dimension",
+         "a": {"shape": [3, 1], "data": [1, NAN, 3]}, "dims": [0], "omitnan": True, "out": {"shape": [1, 1], "data": [4]}},
+        {"src": "sum.rs:1512-1519 sum_with_include_nan_propagates",
+         "a": {"shape": [3, 1], "data": [1, NAN, 3]}, "dims": [0], "omitnan": False, "out": {"shape": [1, 1], "data": [NAN]}},
+    ],
+    "matmul": [
+        {"src": "runmat-runtime/src/builtins/math/linalg/ops/mtimes.rs:495-507 matrix_product_matches_expected",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "b": {"shape": [3, 2], "data": [7, 9, 11, 8, 10, 12]},
+         "out": {"shape": [2, 2], "data": [58, 139, 64, 154]}},
+    ],
+    "matmul_epilogue": [
+        {"src": "runmat-accelerate/tests/matmul_epilogue.rs:24-110 matmul_epilogue_row_col_alpha_beta (tol 1e-9; expected = (alpha*(A*B)+beta).*row.*col)",
+         "a": {"shape": [3, 2], "data": [1, 2, 3, 4, 5, 6]}, "b": {"shape": [2, 4], "data": [1, 3, 5, 7, 2, 4, 6, 8]},
+         "alpha": 1.25, "beta": -0.5, "row_scale": [2.0, 0.5, 1.0], "col_scale": [1.0, 2.0, 0.25, 1.5]},
+    ],
+    "imfilter": [
+        {"src": "runmat-runtime/src/builtins/image/filters/imfilter.rs:803-811 same_padding_default_zero",
+         "img": {"shape": [2, 2], "data": [1, 3, 2, 4]}, "ker": {"shape": [3, 3], "data": [1] * 9}, "opts": {}, "out": {"shape": [2, 2], "data": [10, 10, 10, 10]}},
+        {"src": "imfilter.rs:814-829 replicate_padding",
+         "img": {"shape": [2, 2], "data": [1, 3, 2, 4]}, "ker": {"shape": [3, 3], "data": [1] * 9}, "opts": {"padding": "replicate"},
+         "out": {"shape": [2, 2], "data": [18, 24, 21, 27]}},
+        {"src": "imfilter.rs:832-847 full_output_matches_expected_size",
+         "img": {"shape": [2, 2], "data": [1, 3, 2, 4]}, "ker": {"shape": [2, 2], "data": [1, 3, 2, 4]}, "opts": {"shape": "full"},
+         "out": {"shape": [3, 3], "data": [4, 14, 6, 11, 30, 11, 6, 14, 4]}},
+        {"src": "imfilter.rs:850-862 valid_output_respects_kernel_size",
+         "img": {"shape": [2, 2], "data": [1, 2, 3, 4]}, "ker": {"shape": [2, 2], "data": [1] * 4}, "opts": {"shape": "valid"},
+         "out": {"shape": [1, 1], "data": [10]}},
+        {"src": "imfilter.rs:897-912 circular_padding_wraps_indices",
+         "img": {"shape": [2, 2], "data": [1, 2, 3, 4]}, "ker": {"shape": [2, 2], "data": [0, 1, 1, 0]}, "opts": {"padding": "circular"},
+         "out": {"shape": [2, 2], "data": [5, 5, 5, 5]}},
+        {"src": "imfilter.rs:915-947 gpu_fallback_uses_provider_upload",
+         "img": {"shape": [2, 2], "data": [1, 4, 2, 5]}, "ker": {"shape": [2, 2], "data": [1, 1, 1, 1]}, "opts": {},
+         "out": {"shape": [2, 2], "data": [1, 5, 3, 12]}},
+        {"src": "imfilter.rs:967-984 doc_example_convolution_same_matches_expected",
+         "img": {"shape": [3, 2], "data": [1, 2, 3, 4, 5, 6]}, "ker": {"shape": [2, 2], "data": [1, 3, 2, 4]}, "opts": {"mode": "conv"},
+         "out": {"shape": [3, 2], "data": [1, 5, 9, 6, 25, 35]}},
+    ],
+    "stochastic_evolution": [
+        {"src": "runmat-runtime/src/builtins/stats/random/stochastic_evolution.rs:40-51 cpu_fallback_handles_zero_scale (tol 1e-12): S*exp(drift*steps)",
+         "state": [1.0, 2.0], "drift": 0.1, "scale": 0.0, "steps": 3},
+    ],
+    "linspace": [
+        {"src": "runmat-accelerate/src/simple_provider.rs:3488-3512 (last element forced to stop)", "start": 0.0, "stop": 1.0, "count": 5,
+         "out": [0.0, 0.25, 0.5, 0.75, 1.0]},
+    ],
+    "rng": {
+        "src": "runmat-runtime/src/builtins/common/random.rs:9-13 constants; DEFAULT_RNG_SEED 0x9e3779b97f4a7c15; stream values are pinned by "
+               "algorithm only (random.rs:609-644 helpers are self-referential)",
+        "default_seed": 0x9e3779b97f4a7c15, "multiplier": 6364136223846793005, "increment": 1, "shift": 11,
+    },
+}
+out = Path(__file__).with_name("reference_kats.json")
+out.write_text(json.dumps(kats, indent=1))
+print("wrote", out)

@@ -1,0 +1,712 @@
+"""Parity of the CUDA provider (through the C ABI) against the CPU oracle. Run with -m gpu on a B200.
+
+Tolerances (stated per BASELINE.json north_star):
+  * IEEE-exact ops (+ - * / sqrt, rounding, sign, abs, mod/rem, comparisons, all layout/indexing): BIT-EXACT.
+    The kernels are compiled with -fmad=false, so no a*b+c contraction changes a rounding.
+  * libm-backed ops (sin, exp, pow, ...): |got-want| <= 1e-10*|want| + 1e-13. CUDA's and glibc's implementations are
+    each within ~1-2 ulp of the true value but not bit-identical; the absolute floor covers cancellation to ~0.
+  * reductions / matmul: order of accumulation differs from the sequential host loop: 1e-10 relative to the
+    magnitude bound of the sum (sum |terms|).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from kat_util import KATS, arr, assert_same, num
+from runmat_b200 import ImageNormalizeDescriptor, MatmulEpilogue, ProviderError, fusion_text as ft
+
+pytestmark = pytest.mark.gpu
+
+EXACT_BIN = ["add", "sub", "mul", "div", "max", "min", "mod", "rem", "ge", "le", "lt", "gt", "eq", "ne"]
+LIBM_BIN = ["pow", "hypot", "atan2"]
+EXACT_UN = ["sqrt", "abs", "sign", "floor", "ceil", "round", "fix", "neg", "heaviside", "single", "double", "isnan", "isinf", "isfinite",
+            "nan_to_zero", "not_nan_mask"]
+LIBM_UN = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "expm1", "log", "log2",
+           "log10", "log1p", "pow2"]
+
+
+def close(got, want, rtol=1e-10, atol=1e-13):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    ng, nw = np.isnan(got), np.isnan(want)
+    assert np.array_equal(ng, nw), "NaN pattern differs"
+    inf = np.isinf(want)
+    assert np.array_equal(got[inf], want[inf])
+    m = ~(nw | inf)
+    err = np.abs(got[m] - want[m])
+    bound = rtol * np.abs(want[m]) + atol
+    assert np.all(err <= bound), f"max excess {np.max(err - bound)}, worst rel {np.max(err / np.maximum(np.abs(want[m]), 1e-300))}"
+
+
+def special_values():
+    return np.array([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 2.5, -2.5, 1e-300, 1e300, np.inf, -np.inf, np.nan, 3.0, -7.25, 1e-8])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a1/a2: handles, upload / download / free
+# ---------------------------------------------------------------------------------------------------------------
+def test_upload_download_roundtrip_and_free(prov):
+    rng = np.random.default_rng(0)
+    for shape in [(1, 1), (3, 1), (1, 5), (7, 9), (4, 3, 2), (0, 3), (1025, 3)]:
+        x = rng.uniform(-1, 1, shape)
+        h = prov.upload(x)
+        assert tuple(h.shape) == shape and h.device_id == 7
+        assert np.array_equal(prov.download(h), x)
+        prov.free(h)
+    n0 = prov.live_buffers()
+    h = prov.upload(np.ones((2, 2)))
+    assert prov.live_buffers() == n0 + 1
+    prov.free(h)
+    prov.free(h)  # double free of an unknown id is a no-op (simple_provider.rs:2761)
+    assert prov.live_buffers() == n0
+    with pytest.raises(ProviderError):
+        prov.download(h)
+    h.device_id = 99
+    with pytest.raises(ProviderError, match="belongs to device"):
+        prov.free(h)
+
+
+def test_precision_and_device_info(prov, prov32):
+    assert prov.precision() == "f64" and prov32.precision() == "f32"
+    info = prov.device_info_struct()
+    assert info.cc_major >= 10 and info.sm_count > 0 and b"cuda" in info.backend
+    assert "runmat-b200" in prov.device_info()
+    x = np.array([[1.0 + 1e-12, 2.0]])
+    h = prov32.upload(x)
+    assert np.array_equal(prov32.download(h), x.astype(np.float32).astype(np.float64))  # narrows on upload (io.rs:87)
+    prov32.free(h)
+
+
+def test_reshape_is_metadata_only_and_read_scalar(prov):
+    x = np.arange(12.0).reshape((3, 4), order="F")
+    h = prov.upload(x)
+    r = prov.reshape(h, (2, 6))
+    assert r.buffer_id == h.buffer_id
+    assert np.array_equal(prov.download(r), x.reshape((2, 6), order="F"))
+    assert prov.read_scalar(h, 5) == 5.0
+    with pytest.raises(ProviderError):
+        prov.reshape(h, (5, 5))
+    prov.free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a5: unfused operator surface
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op", EXACT_BIN + LIBM_BIN)
+def test_elem_binary(prov, orc, op):
+    rng = np.random.default_rng(1)
+    cases = [(rng.uniform(-3, 3, (37, 29)), rng.uniform(-3, 3, (37, 29))),       # same shape (flat path, ragged tail)
+             (rng.uniform(-3, 3, (33, 1)), rng.uniform(-3, 3, (1, 17))),         # row x column broadcast
+             (rng.uniform(-3, 3, (8, 5, 3)), rng.uniform(0.5, 3, (1, 5, 1))),    # N-D broadcast
+             (rng.uniform(0.1, 3, (64, 64)), np.array([[2.0]]))]                 # tensor x scalar tensor
+    sv = special_values()
+    cases.append((sv.reshape(-1, 1) * np.ones((1, sv.size)), np.ones((sv.size, 1)) * sv.reshape(1, -1)))
+    for a, b in cases:
+        if op == "pow":
+            a = np.abs(a)
+        ha, hb = prov.upload(a), prov.upload(b)
+        hc = prov.elem_binary(op, ha, hb)
+        got, want = prov.download(hc), orc.elem_binary(op, a, b)
+        if op in EXACT_BIN:
+            assert_same(got, want)
+        else:
+            close(got, want)
+        for h in (ha, hb, hc):
+            prov.free(h)
+
+
+def test_elem_binary_kats_and_errors(prov):
+    for k in KATS["elem_binary"]:
+        ha, hb = prov.upload(arr(k["a"])), prov.upload(arr(k["b"]))
+        hc = prov.elem_binary(k["op"], ha, hb)
+        assert_same(prov.download(hc), arr(k["out"]))
+        for h in (ha, hb, hc):
+            prov.free(h)
+    ha, hb = prov.upload(np.ones((2, 3))), prov.upload(np.ones((3, 2)))
+    with pytest.raises(ProviderError, match="size mismatch"):
+        prov.elem_add(ha, hb)
+    he = prov.upload(np.ones((0, 3)))
+    hz = prov.elem_add(he, prov.upload(np.ones((1, 3))))
+    assert tuple(hz.shape) == (0, 3)
+
+
+@pytest.mark.parametrize("name", ["mod", "rem"])
+def test_mod_rem_kats(prov, name):
+    a = np.array([[num(r[0]) for r in KATS[name]]])
+    b = np.array([[num(r[1]) for r in KATS[name]]])
+    want = np.array([[num(r[2]) for r in KATS[name]]])
+    ha, hb = prov.upload(a), prov.upload(b)
+    hc = prov.elem_binary(name, ha, hb)
+    assert_same(prov.download(hc), want)
+
+
+@pytest.mark.parametrize("op", EXACT_UN + LIBM_UN)
+def test_unary(prov, orc, op):
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-4, 4, (61, 47))
+    if op in ("log", "log2", "log10", "sqrt"):
+        x = np.abs(x) + 1e-3
+    if op in ("asin", "acos", "atanh"):
+        x = x / 4.001
+    if op == "acosh":
+        x = np.abs(x) + 1.0
+    if op == "log1p":
+        x = np.abs(x)
+    x.flat[: special_values().size] = special_values() if op in EXACT_UN else x.flat[: special_values().size]
+    h = prov.upload(x)
+    hr = prov.unary(op, h)
+    got, want = prov.download(hr), orc.unary(op, x)
+    if op in EXACT_UN:
+        assert_same(got, want)
+    else:
+        close(got, want)
+    prov.free(h)
+    prov.free(hr)
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div", "rsub", "rdiv", "max", "min"])
+def test_scalar_ops_exact(prov, orc, op):
+    x = np.random.default_rng(3).uniform(-5, 5, (129, 3))
+    h = prov.upload(x)
+    hr = prov.scalar_op(op, h, 1.7)
+    assert_same(prov.download(hr), orc.scalar_op(op, x, 1.7))
+    prov.free(h)
+    prov.free(hr)
+
+
+def test_named_wrappers_match_generic(prov, orc):
+    x = np.random.default_rng(4).uniform(0.1, 2, (50, 50))
+    h = prov.upload(x)
+    close(prov.download(prov.unary_sin(h)), orc.unary("sin", x))
+    close(prov.download(prov.unary_exp(h)), orc.unary("exp", x))
+    assert_same(prov.download(prov.unary_sqrt(h)), orc.unary("sqrt", x))
+    assert_same(prov.download(prov.elem_mul(h, h)), x * x)
+    assert_same(prov.download(prov.scalar_add(h, 1.0)), x + 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a3: fused elementwise (the WGSL the reference planner emits)
+# ---------------------------------------------------------------------------------------------------------------
+def test_fused_sin_mul_add_1024(prov, orc):
+    """BASELINE config[0]: C = sin(A).*B + 1 on 1024x1024 f64, constant passed as a 1-element tensor."""
+    rng = np.random.default_rng(0)
+    A, B = rng.uniform(0, 4 * math.pi, (1024, 1024)), rng.uniform(-1, 1, (1024, 1024))
+    ha, hb, h1 = prov.upload(A), prov.upload(B), prov.upload(np.array([[1.0]]))
+    hc = prov.fused_elementwise(ft.sin_mul_add_wgsl(), [ha, hb, h1], (1024, 1024), 1024 * 1024)
+    close(prov.download(hc), orc.sin_mul_add(A, B, 1.0))
+    hits0, miss0 = prov.fused_cache_counters()
+    hc2 = prov.fused_elementwise(ft.sin_mul_add_wgsl(), [ha, hb, h1], (1024, 1024), 1024 * 1024)
+    hits1, miss1 = prov.fused_cache_counters()
+    assert hits1 == hits0 + 1 and miss1 == miss0  # pipeline cache hit
+    assert np.array_equal(prov.download(hc), prov.download(hc2))  # deterministic
+    for h in (ha, hb, h1, hc, hc2):
+        prov.free(h)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 511, 512, 513, 2049, 100003])
+def test_fused_ragged_lengths(prov, orc, n):
+    rng = np.random.default_rng(n)
+    A, B = rng.uniform(0, 6, (n, 1)), rng.uniform(-1, 1, (n, 1))
+    ha, hb, h1 = prov.upload(A), prov.upload(B), prov.upload(np.array([[1.0]]))
+    hc = prov.fused_elementwise(ft.sin_mul_add_wgsl(), [ha, hb, h1], (n, 1), n)
+    close(prov.download(hc), orc.sin_mul_add(A, B, 1.0))
+    for h in (ha, hb, h1, hc):
+        prov.free(h)
+
+
+def test_fused_broadcast_and_multi_output(prov, orc):
+    rng = np.random.default_rng(5)
+    col, row = rng.uniform(-2, 2, (40, 1)), rng.uniform(-2, 2, (1, 30))
+    X, Y, T0, T1, T2 = 0, 1, 10, 11, 12
+    ops = [ft.FusionOp("primitive", "ElemMul", [X, Y], T0), ft.FusionOp("builtin", "tanh", [T0], T1), ft.FusionOp("primitive", "Sub", [T1, X], T2)]
+    hx, hy = prov.upload(col), prov.upload(row)
+    out1 = prov.fused_elementwise(ft.elementwise_wgsl([X, Y], ops, [T2]), [hx, hy], (40, 30), 1200)
+    want_t0 = orc.elem_binary("mul", col, row)
+    want_t1 = orc.unary("tanh", want_t0)
+    want_t2 = orc.elem_binary("sub", want_t1, col)
+    close(prov.download(out1), want_t2)
+    outs = prov.fused_elementwise_multi(ft.elementwise_wgsl([X, Y], ops, [T0, T2]), [hx, hy], (40, 30), 1200, 2)
+    assert_same(prov.download(outs[0]), want_t0)  # a product: bit-exact
+    close(prov.download(outs[1]), want_t2)
+
+
+def test_fused_mod_heaviside_pow2_expressions(prov, orc):
+    # the select()-based forms of fusion.rs:2944-2969 evaluated on the reference's own special-case inputs
+    a = np.array([[num(r[0]) for r in KATS["mod"]]])
+    b = np.array([[num(r[1]) for r in KATS["mod"]]])
+    want = np.array([[num(r[2]) for r in KATS["mod"]]])
+    X, Y, Z, T0 = 0, 1, 2, 10
+    ha, hb, h0 = prov.upload(a), prov.upload(b), prov.upload(np.array([[0.0]]))
+    ops = [ft.FusionOp("builtin", "mod", [X, Y], T0), ft.FusionOp("primitive", "Add", [T0, Z], 11)]
+    out = prov.fused_elementwise(ft.elementwise_wgsl([X, Y, Z], ops, [11]), [ha, hb, h0], a.shape, a.size)
+    got = prov.download(out)
+    # fused mod is a - b*floor(a/b) (+Inf special case): b == 0 gives NaN like the host; compare where defined equal
+    assert_same(got, want)
+    x = special_values().reshape(1, -1)
+    hx = prov.upload(x)
+    out = prov.fused_elementwise(ft.elementwise_wgsl([X], [ft.FusionOp("builtin", "heaviside", [X], T0)], [T0]), [hx], x.shape, x.size)
+    assert_same(prov.download(out), orc.unary("heaviside", x))
+    out = prov.fused_elementwise(ft.elementwise_wgsl([X], [ft.FusionOp("primitive", "ElemPow", [X, X], T0)], [T0]), [hx], x.shape, x.size)
+    close(prov.download(out), orc.elem_binary("pow", x, x))
+
+
+def test_fused_rejects_unknown_function_and_mismatched_inputs(prov):
+    sh = ft.sin_mul_add_wgsl().replace("sin(", "frobnicate(")
+    ha = prov.upload(np.ones((4, 4)))
+    with pytest.raises(ProviderError, match="unsupported function"):
+        prov.fused_elementwise(sh, [ha, ha, ha], (4, 4), 16)
+    with pytest.raises(ProviderError):
+        prov.fused_elementwise(ft.sin_mul_add_wgsl(), [ha, ha], (4, 4), 16)
+    with pytest.raises(ProviderError, match="scalar type"):
+        prov.fused_elementwise(ft.sin_mul_add_wgsl("f32"), [ha, ha, ha], (4, 4), 16)
+
+
+def test_fused_full_size_4096(prov, orc):
+    """BASELINE config[1] at full size, checked element-for-element against the oracle (oracle: ~1 s)."""
+    rng = np.random.default_rng(42)
+    n = 4096
+    A, B = rng.uniform(0, 4 * math.pi, (n, n)), rng.uniform(-1, 1, (n, n))
+    ha, hb, h1 = prov.upload(A), prov.upload(B), prov.upload(np.array([[1.0]]))
+    hc = prov.fused_elementwise(ft.sin_mul_add_wgsl(), [ha, hb, h1], (n, n), n * n)
+    C = orc.sin_mul_add(A, B, 1.0)
+    close(prov.download(hc), C)
+    hs = prov.fused_reduction(ft.sum_sin_mul_add_wgsl(), [ha, hb], (1, 1), n * n, 1)
+    got = prov.download(hs)[0, 0]
+    want = orc.reduce_sum(C)
+    assert abs(got - want) <= 1e-10 * np.abs(C).sum()
+    assert abs(got - want) <= 1e-10 * abs(want)
+    # reference-style two-kernel form gives the same answer: reduce the materialised C
+    hs2 = prov.reduce_sum(hc)
+    assert abs(prov.download(hs2)[0, 0] - want) <= 1e-10 * abs(want)
+    for h in (ha, hb, h1, hc, hs, hs2):
+        prov.free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a4 / a6: reductions
+# ---------------------------------------------------------------------------------------------------------------
+def test_sum_kats(prov):
+    for k in KATS["sum"]:
+        a = arr(k["a"])
+        h = prov.upload(a)
+        dims = k["dims"]
+        if k["omitnan"]:
+            continue  # omitnan goes through fused_reduction (below); reduce_sum_dim is include-NaN like the host provider
+        if len(dims) == a.ndim or (a.ndim == 2 and dims == [0, 1]):
+            out = prov.reduce_sum(h)
+            got = prov.download(out).reshape(arr(k["out"]).shape)
+        elif len(dims) == 1:
+            got = prov.download(prov.reduce_sum_dim(h, dims[0]))
+        else:
+            t = prov.reduce_sum_dim(h, dims[0])
+            got = prov.download(prov.reduce_sum_dim(t, dims[1]))
+        assert_same(got, arr(k["out"]))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 1), (1, 7), (257, 3), (3, 257), (64, 64), (1000, 37), (4, 5, 6), (100000, 2), (2, 100000)])
+def test_reduce_dims_vs_oracle(prov, orc, shape):
+    x = np.random.default_rng(7).uniform(-1, 1, shape)
+    h = prov.upload(x)
+    tot = np.abs(x).sum()
+    assert abs(prov.download(prov.reduce_sum(h))[0, 0] - orc.reduce_sum(x)) <= 1e-12 * max(tot, 1)
+    assert abs(prov.download(prov.reduce_mean(h))[0, 0] - orc.reduce_mean(x)) <= 1e-12
+    assert prov.download(prov.reduce_max(h))[0, 0] == orc.reduce_max(x)
+    assert prov.download(prov.reduce_min(h))[0, 0] == orc.reduce_min(x)
+    for d in range(len(shape)):
+        got = prov.download(prov.reduce_sum_dim(h, d))
+        want = orc.sum_dims(x, [d])
+        assert got.shape == want.shape
+        assert np.all(np.abs(got - want) <= 1e-12 * max(np.abs(x).sum(axis=d).max(), 1))
+        gotm = prov.download(prov.reduce_mean_dim(h, d))
+        assert np.all(np.abs(gotm - want / shape[d]) <= 1e-13)
+    prov.free(h)
+
+
+def test_reduce_prod_and_nan_rules(prov, orc):
+    x = np.random.default_rng(8).uniform(0.9, 1.1, (333, 3))
+    h = prov.upload(x)
+    assert abs(prov.download(prov.reduce_prod(h))[0, 0] / orc.reduce_prod(x) - 1) < 1e-12
+    y = x.copy()
+    y[5, 1] = np.nan
+    hy = prov.upload(y)
+    assert math.isnan(prov.download(prov.reduce_sum(hy))[0, 0])
+    got = prov.download(prov.reduce_sum_dim(hy, 0))
+    assert math.isnan(got[0, 1]) and not math.isnan(got[0, 0])
+    # max ignores NaN (fold(NEG_INFINITY, f64::max), simple_provider.rs:7375)
+    assert prov.download(prov.reduce_max(hy))[0, 0] == np.nanmax(y)
+    # empty
+    he = prov.upload(np.ones((0, 3)))
+    assert prov.download(prov.reduce_sum(he))[0, 0] == 0.0
+
+
+def test_fused_reduction_axes_omitnan_mean(prov, orc):
+    rng = np.random.default_rng(9)
+    x, y = rng.uniform(-1, 1, (300, 70)), rng.uniform(-1, 1, (300, 70))
+    x[3, 4] = np.nan
+    X, Y, T0 = 0, 1, 10
+    ops = [ft.FusionOp("primitive", "ElemMul", [X, Y], T0)]
+    hx, hy = prov.upload(x), prov.upload(y)
+    prod = x * y
+    for axis, omit in [(0, False), (0, True), (1, False), (1, True)]:
+        sh = ft.reduction_wgsl([X, Y], ops, T0, axis=axis, omitnan=omit)
+        if axis == 0:
+            out = prov.fused_reduction(sh, [hx, hy], (1, 70), 300, 70)
+        else:
+            out = prov.fused_reduction(sh, [hx, hy], (300, 1), 70, 300)
+        got = prov.download(out)
+        want = orc.sum_dims(prod, [axis], omit_nan=omit)
+        close(got, want, rtol=1e-12, atol=1e-13)
+    # mean flavour: sum/n (ReductionFlavor::Mean, lib.rs:876-887); the reference test tolerance here is 1e-6
+    x2 = rng.uniform(-1, 1, (1000, 8))
+    h2 = prov.upload(x2)
+    sh = ft.reduction_wgsl([X], [ft.FusionOp("primitive", "ElemMul", [X, X], T0)], T0, axis=0, mean=True)
+    out = prov.fused_reduction(sh, [h2], (1, 1), 8000, 1, flavor="mean")
+    assert abs(prov.download(out)[0, 0] - (x2 * x2).sum() / 8000) < 1e-14
+    out = prov.fused_reduction(sh, [h2], (1, 1), 8000, 1, flavor="custom", custom_scale=0.5)
+    assert abs(prov.download(out)[0, 0] - (x2 * x2).sum() * 0.5) < 1e-10
+
+
+def test_reduction_is_deterministic(prov):
+    x = np.random.default_rng(10).uniform(-1, 1, (2048, 2048))
+    h = prov.upload(x)
+    vals = {prov.download(prov.reduce_sum(h))[0, 0] for _ in range(5)}
+    assert len(vals) == 1
+
+
+def test_minmax_dim_with_indices(prov, orc):
+    x = np.random.default_rng(11).integers(-5, 5, (37, 23)).astype(np.float64)  # ties: first occurrence wins
+    h = prov.upload(x)
+    for dim in (0, 1):
+        for is_min, fn in ((False, prov.reduce_max_dim), (True, prov.reduce_min_dim)):
+            v, i = fn(h, dim)
+            wv, wi = orc.reduce_minmax_dim(x, dim, is_min)
+            assert_same(prov.download(v), wv)
+            assert_same(prov.download(i), wi)
+
+
+def test_mean_nd_and_moments(prov):
+    x = np.random.default_rng(12).uniform(0, 1, (6, 20, 30))
+    h = prov.upload(x)
+    m = prov.download(prov.reduce_mean_nd(h, [1, 2]))
+    assert m.shape == (6, 1, 1) and np.allclose(m[:, 0, 0], x.mean(axis=(1, 2)), rtol=1e-13)
+    mean, ex2 = prov.reduce_moments_nd(h, [1, 2])
+    assert np.allclose(prov.download(ex2)[:, 0, 0], (x * x).mean(axis=(1, 2)), rtol=1e-13)
+    m02 = prov.download(prov.reduce_mean_nd(h, [0, 2]))
+    assert m02.shape == (1, 20, 1) and np.allclose(m02[0, :, 0], x.mean(axis=(0, 2)), rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a14: constructors, layout, indexing (bit-exact class)
+# ---------------------------------------------------------------------------------------------------------------
+def test_constructors(prov, orc):
+    assert np.array_equal(prov.download(prov.zeros((3, 4))), np.zeros((3, 4)))
+    assert np.array_equal(prov.download(prov.ones((2, 2, 2))), np.ones((2, 2, 2)))
+    assert np.array_equal(prov.download(prov.fill((5, 1), -2.5)), np.full((5, 1), -2.5))
+    assert np.array_equal(prov.download(prov.eye((3, 5))), np.eye(3, 5))
+    for start, stop, count in [(0.0, 1.0, 5), (0.0, 4 * math.pi, 1000), (-3.0, 7.0, 2), (2.0, 9.0, 1), (0.0, 1.0, 0), (0.0, 4 * math.pi, 100001)]:
+        got = prov.download(prov.linspace(start, stop, count))
+        assert_same(got, orc.linspace(start, stop, count))  # bit-exact incl. the forced last element
+
+
+def test_transpose_permute_repmat_exact(prov, orc):
+    rng = np.random.default_rng(13)
+    for shape in [(1, 1), (5, 3), (33, 65), (128, 100), (1, 1000)]:
+        x = rng.uniform(-1, 1, shape)
+        assert_same(prov.download(prov.transpose(prov.upload(x))), orc.transpose(x))
+    x = rng.uniform(-1, 1, (4, 5, 6))
+    h = prov.upload(x)
+    for order in [(0, 1, 2), (2, 0, 1), (1, 0, 2), (2, 1, 0)]:
+        assert np.array_equal(prov.download(prov.permute(h, order)), np.transpose(x, order))
+    y = rng.uniform(-1, 1, (3, 2))
+    assert np.array_equal(prov.download(prov.repmat(prov.upload(y), (2, 3))), np.tile(y, (2, 3)))
+    assert np.array_equal(prov.download(prov.repmat(prov.upload(y), (1, 1, 2))), np.tile(y[:, :, None], (1, 1, 2)))
+
+
+def test_gather_scatter_linear_exact(prov):
+    rng = np.random.default_rng(14)
+    x = rng.uniform(-1, 1, (50, 40))
+    h = prov.upload(x)
+    idx = rng.integers(0, x.size, 777).astype(np.uint32)
+    g = prov.gather_linear(h, idx, (777, 1))
+    assert np.array_equal(prov.download(g)[:, 0], x.reshape(-1, order="F")[idx])
+    with pytest.raises(ProviderError, match="out of bounds"):
+        prov.gather_linear(h, np.array([x.size], dtype=np.uint32), (1, 1))
+    uniq = rng.permutation(x.size)[:300].astype(np.uint32)
+    vals = rng.uniform(5, 6, (300, 1))
+    prov.scatter_linear(h, uniq, prov.upload(vals))  # in place
+    want = x.reshape(-1, order="F").copy()
+    want[uniq] = vals[:, 0]
+    assert np.array_equal(prov.download(h), want.reshape(x.shape, order="F"))
+    # duplicate indices: the LAST position wins, like the host loop (simple_provider.rs:2699-2711)
+    dup = np.array([3, 3, 3, 9], dtype=np.uint32)
+    prov.scatter_linear(h, dup, prov.upload(np.array([[1.0], [2.0], [3.0], [4.0]])))
+    got = prov.download(h).reshape(-1, order="F")
+    assert got[3] == 3.0 and got[9] == 4.0
+    with pytest.raises(ProviderError):
+        prov.scatter_linear(h, np.array([1, 2], dtype=np.uint32), prov.upload(np.ones((3, 1))))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a7 / a8: matmul
+# ---------------------------------------------------------------------------------------------------------------
+def matmul_close(got, a, b, want):
+    bound = 1e-10 * (np.abs(a) @ np.abs(b)) + 1e-300
+    assert np.all(np.abs(got - want) <= bound), f"worst ratio {np.max(np.abs(got - want) / bound)}"
+
+
+def test_matmul_kats(prov):
+    for k in KATS["matmul"]:
+        hc = prov.matmul(prov.upload(arr(k["a"])), prov.upload(arr(k["b"])))
+        assert_same(prov.download(hc), arr(k["out"]))  # small integers: exact
+    with pytest.raises(ProviderError, match="inner dims"):
+        prov.matmul(prov.upload(np.ones((2, 3))), prov.upload(np.ones((2, 3))))
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (3, 5, 2), (128, 128, 128), (129, 67, 131), (256, 1024, 64), (255, 33, 257), (512, 16, 512),
+                                   (1000, 1000, 10), (2, 4096, 2), (640, 640, 640)])
+def test_matmul_vs_oracle(prov, orc, m, k, n):
+    rng = np.random.default_rng(m * 7 + n)
+    a, b = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (k, n))
+    hc = prov.matmul(prov.upload(a), prov.upload(b))
+    got, want = prov.download(hc), orc.matmul(a, b)
+    assert got.shape == (m, n)
+    matmul_close(got, a, b, want)
+
+
+def test_matmul_epilogue_kat_and_order(prov, orc):
+    k = KATS["matmul_epilogue"][0]
+    a, b = arr(k["a"]), arr(k["b"])
+    ha, hb = prov.upload(a), prov.upload(b)
+    ep = MatmulEpilogue(alpha=k["alpha"], beta=k["beta"], row_scale=prov.upload(np.array(k["row_scale"]).reshape(-1, 1)),
+                        col_scale=prov.upload(np.array(k["col_scale"]).reshape(1, -1)))
+    got = prov.download(prov.matmul_epilogue(ha, hb, ep))
+    want, _ = orc.matmul_epilogue(orc.matmul(a, b), alpha=k["alpha"], beta=k["beta"], row_scale=k["row_scale"], col_scale=k["col_scale"])
+    assert np.all(np.abs(got - want) < 1e-9)  # reference tolerance (matmul_epilogue.rs:100-101)
+    rng = np.random.default_rng(15)
+    a, b = rng.uniform(0, 1, (70, 40)), rng.uniform(0, 1, (40, 90))
+    rs, cs = rng.uniform(0.5, 2, (70, 1)), rng.uniform(0.5, 2, (1, 90))
+    diag = prov.zeros((70, 1))
+    ep = MatmulEpilogue(alpha=0.5, beta=-3.0, row_scale=prov.upload(rs), col_scale=prov.upload(cs), row_op="divide", col_op="multiply",
+                        clamp_min=0.25, clamp_max=4.0, pow_exponent=1.5, diag_output=diag)
+    got = prov.download(prov.matmul_epilogue(prov.upload(a), prov.upload(b), ep))
+    want, wdiag = orc.matmul_epilogue(orc.matmul(a, b), alpha=0.5, beta=-3.0, row_scale=rs, row_div=True, col_scale=cs, clamp_min=0.25,
+                                      clamp_max=4.0, pow_exponent=1.5, diag=np.zeros(70))
+    close(got, want, rtol=1e-9)
+    close(prov.download(diag)[:, 0], wdiag, rtol=1e-9)  # written in place
+    # noop epilogue == plain matmul
+    plain = prov.download(prov.matmul(prov.upload(a), prov.upload(b)))
+    assert np.array_equal(prov.download(prov.matmul_epilogue(prov.upload(a), prov.upload(b), MatmulEpilogue())), plain)
+
+
+def test_syrk(prov, orc):
+    a = np.random.default_rng(16).uniform(-1, 1, (300, 40))
+    got = prov.download(prov.syrk(prov.upload(a)))
+    matmul_close(got, a.T, a, orc.matmul(np.asfortranarray(a.T), a))
+
+
+def test_matmul_8192_properties(prov, orc):
+    """BASELINE config[2] at full size. The naive oracle is ~1e12 flops single-threaded, so the full product is checked by
+    size-independent properties: (1) Freivalds: C*x == A*(B*x) for random x (oracle mat-vecs), (2) 256 sampled entries
+    recomputed with the oracle's k-ascending dot product, (3) linearity in A."""
+    n = 8192
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    ha, hb = prov.upload(a), prov.upload(b)
+    hc = prov.matmul(ha, hb)
+    c = prov.download(hc)
+    x = rng.uniform(-1, 1, (n, 1))
+    lhs = c @ x
+    rhs = a @ (b @ x)
+    scale = (np.abs(a) @ (np.abs(b) @ np.abs(x)))
+    assert np.all(np.abs(lhs - rhs) <= 1e-10 * scale)
+    ii, jj = rng.integers(0, n, 256), rng.integers(0, n, 256)
+    for i, j in zip(ii, jj):
+        want = orc.matmul(a[i:i + 1, :], b[:, j:j + 1])[0, 0]
+        assert abs(c[i, j] - want) <= 1e-10 * float(np.abs(a[i, :]) @ np.abs(b[:, j]))
+    h2 = prov.scalar_mul(ha, 2.0)
+    c2 = prov.download(prov.matmul(h2, hb))
+    assert np.array_equal(c2, 2.0 * c)  # scaling by 2 is exact
+    for h in (ha, hb, hc, h2):
+        prov.free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a10 / a11: RNG + Monte-Carlo evolution
+# ---------------------------------------------------------------------------------------------------------------
+def test_random_uniform_stream_is_bit_exact(prov, orc):
+    prov.set_rng_state(0)  # 0 -> default seed (simple_provider.rs:3627-3640)
+    s = orc.default_seed()
+    assert prov.get_rng_state() == s
+    for n in (1, 7, 1000, 100003):
+        got = prov.download(prov.random_uniform((n, 1)))[:, 0]
+        want, s = orc.generate_uniform(s, n)
+        assert np.array_equal(got, want)
+        assert prov.get_rng_state() == s  # provider state advanced exactly like the host's
+
+
+def test_random_normal_matches_host_stream(prov, orc):
+    prov.set_rng_state(12345)
+    s = 12345
+    for n in (2, 5, 4096, 100001):
+        got = prov.download(prov.random_normal((n, 1)))[:, 0]
+        want, s = orc.generate_normal(s, n)
+        close(got, want, rtol=1e-10, atol=1e-13)
+        assert prov.get_rng_state() == s
+
+
+def test_stochastic_evolution_zero_scale_kat(prov):
+    k = KATS["stochastic_evolution"][0]
+    h = prov.upload(np.array(k["state"]).reshape(2, 1))
+    got = prov.download(prov.stochastic_evolution(h, k["drift"], k["scale"], k["steps"]))[:, 0]
+    want = np.array(k["state"]) * math.exp(k["drift"] * k["steps"])
+    assert np.all(np.abs(got - want) < 1e-12)
+
+
+@pytest.mark.parametrize("n,steps", [(1, 1), (2, 3), (5, 4), (1000, 16), (4097, 8)])
+def test_stochastic_evolution_vs_host(prov, orc, n, steps):
+    drift, scale = (0.05 - 0.5 * 0.2 ** 2) / 252.0, 0.2 * math.sqrt(1.0 / 252.0)
+    s0 = np.full((n, 1), 100.0)
+    prov.set_rng_state(777)
+    got = prov.download(prov.stochastic_evolution(prov.upload(s0), drift, scale, steps))
+    want, new_state = orc.stochastic_evolution(777, s0, drift, scale, steps)
+    close(got, want, rtol=1e-10, atol=0)
+    assert prov.get_rng_state() == new_state
+
+
+def test_stochastic_evolution_sharding_is_invariant(prov, orc):
+    """Union of shards == single-GPU run, bit for bit."""
+    n, steps = 10001, 12
+    drift, scale = 1e-4, 0.0126
+    s0 = np.random.default_rng(17).uniform(90, 110, (n, 1))
+    prov.set_rng_state(42)
+    whole = prov.download(prov.stochastic_evolution(prov.upload(s0), drift, scale, steps))
+    end_state = prov.get_rng_state()
+    for cuts in ([0, 5000, n], [0, 3333, 3334, 7001, n], [0, 1, n]):
+        parts = []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            prov.set_rng_state(42)
+            part = prov.stochastic_evolution_sharded(prov.upload(s0[lo:hi]), drift, scale, steps, lo, n)
+            parts.append(prov.download(part))
+            assert prov.get_rng_state() == end_state
+        assert np.array_equal(np.vstack(parts), whole)
+    want, _ = orc.stochastic_evolution(42, s0, drift, scale, steps)
+    close(whole, want, rtol=1e-10, atol=0)
+
+
+def test_payoff_partial_sum(prov):
+    s = np.random.default_rng(18).uniform(50, 150, (100003, 1))
+    got = prov.download(prov.payoff_partial_sum(prov.upload(s), 100.0))[0, 0]
+    want = np.maximum(s - 100.0, 0.0).sum()
+    assert abs(got - want) <= 1e-12 * want
+
+
+def test_monte_carlo_full_size_properties(prov):
+    """BASELINE config[4] scale on one GPU: 1e8 paths x 256 steps. Zero-scale closed form at full size, and the
+    log-return moments of the stochastic run (mean = drift*T, var = scale^2*T) to Monte-Carlo accuracy."""
+    M, T = 100_000_000, 256
+    h = prov.fill((M, 1), 100.0)
+    out = prov.stochastic_evolution(h, 1e-3, 0.0, T)
+    tot = prov.download(prov.reduce_sum(out))[0, 0]
+    assert abs(tot / M - 100.0 * math.exp(1e-3 * T)) < 1e-9
+    prov.free(out)
+    drift, scale = (0.05 - 0.5 * 0.2 ** 2) / 252.0, 0.2 * math.sqrt(1.0 / 252.0)
+    prov.set_rng_state(0)
+    out = prov.stochastic_evolution(h, drift, scale, T)
+    lg = prov.unary("log", prov.scalar_div(out, 100.0))
+    mean = prov.download(prov.reduce_mean(lg))[0, 0]
+    ex2 = prov.download(prov.reduce_mean(prov.elem_mul(lg, lg)))[0, 0]
+    var = ex2 - mean * mean
+    assert abs(mean - drift * T) < 5 * scale * math.sqrt(T) / math.sqrt(M)
+    assert abs(var / (scale * scale * T) - 1.0) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a12 / a13: image normalise + imfilter
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W", [(1, 4, 4), (3, 5, 7), (4, 64, 48), (16, 33, 17), (5, 2, 3), (64, 16, 16)])
+def test_image_normalize_f64_vs_host(prov, orc, B, H, W):
+    x = np.random.default_rng(B * 100 + H).uniform(0, 1, (B, H, W))
+    h = prov.upload(x)
+    for kw in [dict(gain=1.0123, bias=-0.02, gamma=1.8, clamp_zero=True), dict(gain=None, bias=None, gamma=None, clamp_zero=False),
+               dict(gain=2.0, bias=None, gamma=None, clamp_zero=True)]:
+        d = ImageNormalizeDescriptor(B, H, W, 1e-6, **kw)
+        got = prov.download(prov.image_normalize(h, d))
+        want = orc.image_normalize(x, 1e-6, **kw)
+        # statistics are accumulated in a different order (and as shifted moments): 1e-10 relative, the pow amplifies slightly
+        close(got, want, rtol=1e-9, atol=1e-12)
+    with pytest.raises(ProviderError, match="descriptor dims"):
+        prov.image_normalize(h, ImageNormalizeDescriptor(B + 1, H, W, 1e-6))
+    with pytest.raises(ProviderError, match="epsilon"):
+        prov.image_normalize(h, ImageNormalizeDescriptor(B, H, W, -1.0))
+
+
+def test_image_normalize_constant_image_and_f32(prov, prov32, orc):
+    x = np.full((2, 8, 8), 0.25)
+    d = ImageNormalizeDescriptor(2, 8, 8, 0.0, clamp_zero=False)
+    assert np.array_equal(prov.download(prov.image_normalize(prov.upload(x), d)), np.zeros((2, 8, 8)))  # sigma == 0 -> inv_sigma = 0
+    img = orc.image_lcg_fill(4, 120, 160)  # benchmarks/4k-image-processing/runmat_lcg.m:59-79 field, small
+    h = prov32.upload(img)
+    d = ImageNormalizeDescriptor(4, 120, 160, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+    got = prov32.download(prov32.image_normalize(h, d), dtype=np.float32)
+    want = orc.image_normalize(img.astype(np.float64), 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+    assert np.all(np.abs(got - want) <= 5e-4 * np.maximum(np.abs(want), 1.0))  # the reference's f32 tolerance (matmul_small_k.rs:207 style)
+    assert np.all(np.abs(got - want) <= 2e-5 * np.maximum(np.abs(want), 1.0))
+
+
+def test_image_normalize_4k_batch8_f32(prov32, orc):
+    """BASELINE config[3] shape (per GPU at 8-way sharding of B=64): [8,2160,3840] f32, checked against the f64 oracle."""
+    B, H, W = 8, 2160, 3840
+    img = orc.image_lcg_fill(B, H, W)
+    h = prov32.upload(img)
+    d = ImageNormalizeDescriptor(B, H, W, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+    out = prov32.image_normalize(h, d)
+    got = prov32.download(out, dtype=np.float32)
+    want = orc.image_normalize(img.astype(np.float64), 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+    assert np.all(np.abs(got - want) <= 2e-5 * np.maximum(np.abs(want), 1.0))
+    mse_want = float(np.mean((want - img) ** 2))
+    X, Y, T0, T1 = 0, 1, 10, 11
+    ops = [ft.FusionOp("primitive", "Sub", [X, Y], T0), ft.FusionOp("primitive", "ElemMul", [T0, T0], T1)]
+    sh = ft.reduction_wgsl([X, Y], ops, T1, axis=0, mean=True, scalar_ty="f32")
+    mse = prov32.download(prov32.fused_reduction(sh, [out, h], (1, 1), B * H * W, 1, flavor="mean"))[0, 0]
+    assert abs(mse - mse_want) <= 1e-5 * mse_want
+
+
+def test_imfilter_kats_and_modes(prov, orc):
+    for k in KATS["imfilter"]:
+        o = k["opts"]
+        got = prov.download(prov.imfilter(prov.upload(arr(k["img"])), prov.upload(arr(k["ker"])), padding=o.get("padding", "constant"),
+                                          shape=o.get("shape", "same"), mode=o.get("mode", "corr")))
+        assert_same(got, arr(k["out"]))
+    rng = np.random.default_rng(19)
+    img = rng.uniform(0, 1, (37, 29, 3))
+    g = np.exp(-((np.arange(5) - 2)[:, None] ** 2 + (np.arange(5) - 2)[None, :] ** 2) / 2.0)
+    ker = g / g.sum()
+    hi, hk = prov.upload(img), prov.upload(ker)
+    for padding in ("constant", "replicate", "symmetric", "circular"):
+        for shape in ("same", "full", "valid"):
+            for mode in ("corr", "conv"):
+                got = prov.download(prov.imfilter(hi, hk, padding=padding, constant_value=0.5, shape=shape, mode=mode))
+                want = orc.imfilter(img, ker, padding=padding, cval=0.5, shape=shape, mode=mode)
+                assert_same(got, want)  # only mul/add in the host's order, no FMA: bit-exact
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a15: telemetry
+# ---------------------------------------------------------------------------------------------------------------
+def test_telemetry_counts(prov):
+    prov.reset_telemetry()
+    x = np.ones((16, 16))
+    h = prov.upload(x)
+    h1 = prov.upload(np.array([[1.0]]))
+    prov.fused_elementwise(ft.sin_mul_add_wgsl(), [h, h, h1], (16, 16), 256)
+    prov.fused_reduction(ft.sum_sin_mul_add_wgsl(), [h, h], (1, 1), 256, 1)
+    prov.matmul(h, h)
+    prov.download(h)
+    t = prov.telemetry_snapshot()
+    assert t.fused_elementwise.count == 1 and t.fused_reduction.count == 1 and t.matmul.count == 1
+    assert t.upload_bytes == 256 * 8 + 8 and t.download_bytes == 256 * 8
+    assert t.kernel_launches >= 3 and t.fused_elementwise.total_wall_time_ns > 0
+    assert prov.default_reduction_workgroup_size() == 256 and prov.two_pass_threshold() > 0
+    with pytest.raises(ProviderError, match="not supported by provider"):
+        prov.mldivide(h, h)

@@ -1,0 +1,160 @@
+"""Pins the CPU oracle against the literal known-answer vectors of the reference's own unit tests."""
+import math
+
+import numpy as np
+import pytest
+
+from kat_util import KATS, arr, assert_same, num
+
+
+def test_elem_binary_kats(orc):
+    for k in KATS["elem_binary"]:
+        assert_same(orc.elem_binary(k["op"], arr(k["a"]), arr(k["b"])), arr(k["out"]))
+
+
+@pytest.mark.parametrize("name", ["mod", "rem"])
+def test_mod_rem_kats(orc, name):
+    fn = orc.mod if name == "mod" else orc.rem
+    for a, b, want in KATS[name]:
+        got, want = fn(num(a), num(b)), num(want)
+        assert (math.isnan(got) and math.isnan(want)) or got == want, (name, a, b, got, want)
+        # the array path agrees with the scalar path
+        got2 = orc.elem_binary(name, np.array([[num(a)]]), np.array([[num(b)]]))[0, 0]
+        assert (math.isnan(got2) and math.isnan(want)) or got2 == want
+
+
+def test_mod_negative_zero_normalised(orc):
+    assert math.copysign(1.0, orc.mod(-4.0, 2.0)) == 1.0
+    assert math.copysign(1.0, orc.rem(-4.0, 2.0)) == 1.0
+
+
+def test_sum_kats(orc):
+    for k in KATS["sum"]:
+        assert_same(orc.sum_dims(arr(k["a"]), k["dims"], k["omitnan"]), arr(k["out"]))
+
+
+def test_matmul_kats(orc):
+    for k in KATS["matmul"]:
+        assert_same(orc.matmul(arr(k["a"]), arr(k["b"]), naive=True), arr(k["out"]))
+        assert_same(orc.matmul(arr(k["a"]), arr(k["b"]), naive=False), arr(k["out"]))
+
+
+def test_matmul_interchanged_is_bit_identical_to_naive(orc):
+    rng = np.random.default_rng(0)
+    for m, k, n in [(1, 1, 1), (7, 13, 5), (64, 257, 33), (130, 96, 70)]:
+        a, b = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (k, n))
+        assert np.array_equal(orc.matmul(a, b, naive=True), orc.matmul(a, b, naive=False))
+
+
+def test_matmul_epilogue_kat(orc):
+    k = KATS["matmul_epilogue"][0]
+    a, b = arr(k["a"]), arr(k["b"])
+    base = orc.matmul(a, b, naive=True)
+    got, _ = orc.matmul_epilogue(base, alpha=k["alpha"], beta=k["beta"], row_scale=k["row_scale"], col_scale=k["col_scale"])
+    want = (base * k["alpha"] + k["beta"]) * np.array(k["row_scale"])[:, None] * np.array(k["col_scale"])[None, :]
+    assert_same(got, want, tol=1e-9)  # the reference test's tolerance
+
+
+def test_matmul_epilogue_order_clamp_pow_diag(orc):
+    # simple_provider.rs:7805-7838: alpha/beta -> row -> col -> clamp_min -> clamp_max -> pow -> diag
+    c = np.array([[1.0, -2.0], [3.0, 4.0]])
+    diag0 = np.zeros(2)
+    got, diag = orc.matmul_epilogue(c, alpha=2.0, beta=1.0, row_scale=[2.0, 4.0], row_div=True, clamp_min=0.0, clamp_max=2.0,
+                                    pow_exponent=2.0, diag=diag0)
+    want = np.minimum(np.maximum((c * 2.0 + 1.0) / np.array([2.0, 4.0])[:, None], 0.0), 2.0) ** 2.0
+    assert_same(got, want)
+    assert_same(diag, np.array([want[0, 0], want[1, 1]]))
+
+
+def test_imfilter_kats(orc):
+    for k in KATS["imfilter"]:
+        o = k["opts"]
+        got = orc.imfilter(arr(k["img"]), arr(k["ker"]), padding=o.get("padding", "constant"), shape=o.get("shape", "same"), mode=o.get("mode", "corr"))
+        assert_same(got, arr(k["out"]), tol=1e-12)
+
+
+def test_imfilter_conv_equals_corr_with_flipped_kernel(orc):
+    # imfilter.rs:865-894
+    img = np.array([1.0, 4, 2, 5, 3, 6]).reshape((3, 2), order="F")
+    ker = np.array([1.0, 2, 3, 4]).reshape((2, 2), order="F")
+    flipped = np.array([4.0, 3, 2, 1]).reshape((2, 2), order="F")
+    assert_same(orc.imfilter(img, ker, mode="conv"), orc.imfilter(img, flipped, mode="corr"))
+
+
+def test_imfilter_symmetric_padding_reflects(orc):
+    img = np.arange(1.0, 7.0).reshape((2, 3), order="F")
+    ker = np.ones((3, 3))
+    got = orc.imfilter(img, ker, padding="symmetric")
+    padded = np.pad(img, 1, mode="reflect")  # period 2*len-2 (imfilter.rs:777-792)
+    want = np.array([[padded[i:i + 3, j:j + 3].sum() for j in range(3)] for i in range(2)])
+    assert_same(got, want)
+
+
+def test_stochastic_evolution_zero_scale_kat(orc):
+    k = KATS["stochastic_evolution"][0]
+    got, _ = orc.stochastic_evolution(orc.default_seed(), np.array(k["state"]).reshape(2, 1), k["drift"], k["scale"], k["steps"])
+    want = np.array(k["state"]) * math.exp(k["drift"] * k["steps"])
+    assert np.all(np.abs(got.ravel() - want) < 1e-12)
+
+
+def test_linspace_kat(orc):
+    k = KATS["linspace"][0]
+    assert_same(orc.linspace(k["start"], k["stop"], k["count"]).ravel(), np.array(k["out"]))
+    assert orc.linspace(0.0, 4 * math.pi, 1000)[0, -1] == 4 * math.pi
+
+
+def test_rng_constants_and_jump_ahead(orc):
+    r = KATS["rng"]
+    assert orc.default_seed() == r["default_seed"]
+    assert orc.mix_seed(0) == r["default_seed"]
+    s = r["default_seed"]
+    # one LCG step by hand: state*mult+inc mod 2^64, >>11, *2^-53 (random.rs:271-277)
+    s1 = (s * r["multiplier"] + r["increment"]) % (1 << 64)
+    u, new = orc.generate_uniform(s, 1)
+    assert new == s1 and u[0] == (s1 >> r["shift"]) * (1.0 / (1 << 53))
+    # advance_state(state, n) == n sequential steps (random.rs:238-257)
+    for n in (0, 1, 2, 3, 17, 1000, 12345):
+        _, seq = orc.generate_uniform(s, n)
+        assert orc.advance_state(s, n) == seq
+    u = orc.generate_uniform(s, 4096)[0]
+    assert np.all((u >= 0.0) & (u < 1.0))
+
+
+def test_normals_are_box_muller_pairs(orc):
+    s = orc.default_seed()
+    z, new = orc.generate_normal(s, 5)  # odd: the last pair still consumes two uniforms
+    u, new_u = orc.generate_uniform(s, 6)
+    assert new == new_u
+    r0 = math.sqrt(-2.0 * math.log(u[0]))
+    assert z[0] == r0 * math.cos(2.0 * math.pi * u[1]) and z[1] == r0 * math.sin(2.0 * math.pi * u[1])
+    big = orc.generate_normal(s, 200000)[0]
+    assert abs(big.mean()) < 0.01 and abs(big.std() - 1.0) < 0.01  # runmat-runtime/tests/rng.rs:21-62 style moments
+
+
+def test_unary_and_scalar_tables(orc):
+    x = np.array([[-2.5, -0.0, 0.0, 0.5, 2.5, np.nan, np.inf]])
+    assert_same(orc.unary("round", x), np.array([[-3.0, -0.0, 0.0, 1.0, 3.0, np.nan, np.inf]]))  # half away from zero
+    assert_same(orc.unary("sign", x), np.array([[-1.0, 0.0, 0.0, 1.0, 1.0, np.nan, 1.0]]))
+    assert_same(orc.unary("heaviside", x), np.array([[0.0, 0.5, 0.5, 1.0, 1.0, np.nan, 1.0]]))
+    assert_same(orc.unary("fix", x), np.array([[-2.0, -0.0, 0.0, 0.0, 2.0, np.nan, np.inf]]))
+    assert_same(orc.scalar_op("rsub", np.array([[1.0, 2.0]]), 10.0), np.array([[9.0, 8.0]]))
+    assert_same(orc.scalar_op("rdiv", np.array([[2.0, 4.0]]), 8.0), np.array([[4.0, 2.0]]))
+    # elementwise max/min: NaN loses unless both NaN (max.rs:2323-2343)
+    assert_same(orc.elem_binary("max", np.array([[np.nan, 1.0, np.nan]]), np.array([[2.0, np.nan, np.nan]])), np.array([[2.0, 1.0, np.nan]]))
+
+
+def test_broadcast_error_and_zero_dims(orc):
+    with pytest.raises(ValueError):
+        orc.elem_binary("add", np.ones((2, 3)), np.ones((3, 2)))
+    assert orc.elem_binary("add", np.ones((0, 3)), np.ones((1, 3))).shape == (0, 3)
+
+
+def test_image_normalize_matches_test_restatement(orc):
+    # runmat-accelerate/tests/image_normalize.rs:7-66 restates the provider code; check against a numpy form
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0, 1, (3, 5, 7))
+    got = orc.image_normalize(x, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+    mu = x.mean(axis=(1, 2), keepdims=True)
+    sig = np.sqrt(((x - mu) ** 2).mean(axis=(1, 2), keepdims=True) + 1e-6)
+    want = np.maximum((x - mu) / sig * 1.0123 - 0.02, 0.0) ** 1.8
+    assert_same(got, want, tol=1e-12)
