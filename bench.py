@@ -234,13 +234,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (fused elementwise, 24 B/elem): isolated launches, CUDA events ------------
     def time_kernel(fn, reps):
+        for _ in range(3):
+            p.free(fn())
         p.synchronize()
         p.timer_begin()
-        hs = [fn() for _ in range(reps)]
-        t = p.timer_end_ms()
-        for h in hs:
-            p.free(h)
-        return t / reps
+        for _ in range(reps):
+            p.free(fn())  # stream-ordered free: the pool hands the same block back, as in the step loop
+        return p.timer_end_ms() / reps
 
     reps = max(args.steps, 10)
     ew_ms = time_kernel(lambda: p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS), reps)

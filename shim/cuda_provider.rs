@@ -1,0 +1,400 @@
+//! shim/cuda_provider.rs — `impl AccelProvider for CudaProvider`, forwarding to the C ABI in include/rm_accel.h.
+//!
+//! This is the binding a RunMat maintainer adds under the dormant `cuda` feature of `crates/runmat-accelerate`
+//! (`Cargo.toml:12`, `DeviceKind::Cuda` at `src/lib.rs:373`). It is SOURCE ONLY in this repository: the image has no
+//! `cargo`/`rustc`, so it is not compiled or tested here (INTEGRATION.md says how it slots into the reference).
+//! Every method is a 1:1 forward; anything the C library reports as RM_UNSUPPORTED keeps the trait's default
+//! ("... not supported by provider"), so callers fall back to host exactly as they do today.
+
+use anyhow::{anyhow, Result};
+use runmat_accelerate_api::{
+    AccelDownloadFuture, AccelProvider, AccelProviderFuture, ApiDeviceInfo, GpuTensorHandle, GpuTensorStorage,
+    HostTensorOwned, HostTensorView, ImageNormalizeDescriptor, MatmulEpilogue, ProviderPrecision, ProviderTelemetry,
+    ProviderDispatchStats, ReduceDimResult, ReductionFlavor, ScaleOp,
+};
+use std::ffi::{c_char, c_int, c_void, CStr, CString};
+
+pub const RM_MAX_RANK: usize = 16;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct RmHandle {
+    pub buffer_id: u64,
+    pub device_id: u32,
+    pub rank: u32,
+    pub shape: [u64; RM_MAX_RANK],
+}
+
+#[repr(C)]
+pub struct RmMatmulEpilogue {
+    pub alpha: f64,
+    pub beta: f64,
+    pub row_scale: *const RmHandle,
+    pub col_scale: *const RmHandle,
+    pub row_op: c_int,
+    pub col_op: c_int,
+    pub has_clamp_min: c_int,
+    pub clamp_min: f64,
+    pub has_clamp_max: c_int,
+    pub clamp_max: f64,
+    pub has_pow: c_int,
+    pub pow_exponent: f64,
+    pub diag_output: *const RmHandle,
+}
+
+#[repr(C)]
+pub struct RmImageNormalizeDesc {
+    pub batch: u64,
+    pub height: u64,
+    pub width: u64,
+    pub epsilon: f64,
+    pub has_gain: c_int,
+    pub gain: f64,
+    pub has_bias: c_int,
+    pub bias: f64,
+    pub has_gamma: c_int,
+    pub gamma: f64,
+    pub clamp_zero: c_int,
+}
+
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct RmDispatchStats {
+    pub count: u64,
+    pub total_wall_time_ns: u64,
+}
+
+#[repr(C)]
+#[derive(Default)]
+pub struct RmTelemetry {
+    pub fused_elementwise: RmDispatchStats,
+    pub fused_reduction: RmDispatchStats,
+    pub matmul: RmDispatchStats,
+    pub linsolve: RmDispatchStats,
+    pub mldivide: RmDispatchStats,
+    pub mrdivide: RmDispatchStats,
+    pub upload_bytes: u64,
+    pub download_bytes: u64,
+    pub fusion_cache_hits: u64,
+    pub fusion_cache_misses: u64,
+    pub kernel_launches: u64,
+}
+
+#[link(name = "rm_accel_b200")]
+extern "C" {
+    fn rm_provider_create(cuda_ordinal: c_int, device_id: u32, precision: c_int, out: *mut *mut c_void) -> c_int;
+    fn rm_provider_destroy(p: *mut c_void) -> c_int;
+    fn rm_last_error() -> *const c_char;
+    fn rm_device_info_string(p: *mut c_void, buf: *mut c_char, len: usize) -> c_int;
+    fn rm_upload(p: *mut c_void, data: *const f64, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_download(p: *mut c_void, h: *const RmHandle, out: *mut f64, n: u64) -> c_int;
+    fn rm_free(p: *mut c_void, h: *const RmHandle) -> c_int;
+    fn rm_read_scalar(p: *mut c_void, h: *const RmHandle, idx: u64, out: *mut f64) -> c_int;
+    fn rm_zeros(p: *mut c_void, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_fill(p: *mut c_void, shape: *const u64, rank: u32, v: f64, out: *mut RmHandle) -> c_int;
+    fn rm_linspace(p: *mut c_void, start: f64, stop: f64, count: u64, out: *mut RmHandle) -> c_int;
+    fn rm_transpose(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_gather_linear(p: *mut c_void, src: *const RmHandle, idx: *const u32, n: u64, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_scatter_linear(p: *mut c_void, dst: *const RmHandle, idx: *const u32, n: u64, vals: *const RmHandle) -> c_int;
+    fn rm_elem_binary(p: *mut c_void, op: c_int, a: *const RmHandle, b: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_unary(p: *mut c_void, op: c_int, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_scalar_op_apply(p: *mut c_void, op: c_int, a: *const RmHandle, s: f64, out: *mut RmHandle) -> c_int;
+    fn rm_fused_elementwise(p: *mut c_void, shader: *const c_char, inputs: *const RmHandle, n_inputs: u32, shape: *const u64, rank: u32, len: u64, out: *mut RmHandle) -> c_int;
+    fn rm_fused_elementwise_multi(p: *mut c_void, shader: *const c_char, inputs: *const RmHandle, n_inputs: u32, shape: *const u64, rank: u32, len: u64, n_out: u32, outs: *mut RmHandle) -> c_int;
+    fn rm_fused_reduction(p: *mut c_void, shader: *const c_char, inputs: *const RmHandle, n_inputs: u32, shape: *const u64, rank: u32, reduce_len: u64, num_slices: u64, wg: u32, flavor: c_int, custom_scale: f64, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_sum(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_sum_dim(p: *mut c_void, a: *const RmHandle, dim: u32, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_mean(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_max_dim(p: *mut c_void, a: *const RmHandle, dim: u32, vals: *mut RmHandle, idx: *mut RmHandle) -> c_int;
+    fn rm_matmul(p: *mut c_void, a: *const RmHandle, b: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_matmul_epilogue_apply(p: *mut c_void, a: *const RmHandle, b: *const RmHandle, ep: *const RmMatmulEpilogue, out: *mut RmHandle) -> c_int;
+    fn rm_image_normalize(p: *mut c_void, a: *const RmHandle, d: *const RmImageNormalizeDesc, out: *mut RmHandle) -> c_int;
+    fn rm_stochastic_evolution(p: *mut c_void, s: *const RmHandle, drift: f64, scale: f64, steps: u32, out: *mut RmHandle) -> c_int;
+    fn rm_set_rng_state(p: *mut c_void, state: u64) -> c_int;
+    fn rm_telemetry_snapshot(p: *mut c_void, out: *mut RmTelemetry) -> c_int;
+    fn rm_reset_telemetry(p: *mut c_void) -> c_int;
+    fn rm_fused_cache_counters(p: *mut c_void, hits: *mut u64, misses: *mut u64);
+}
+
+pub struct CudaProvider {
+    raw: *mut c_void,
+    device_id: u32,
+}
+// The C library is thread-safe (one mutex around the buffer table, stream-ordered allocation): rm_accel.h header.
+unsafe impl Send for CudaProvider {}
+unsafe impl Sync for CudaProvider {}
+
+fn err() -> anyhow::Error {
+    let msg = unsafe { CStr::from_ptr(rm_last_error()) }.to_string_lossy().into_owned();
+    anyhow!(msg)
+}
+fn check(status: c_int) -> Result<()> {
+    if status == 0 { Ok(()) } else { Err(err()) }
+}
+fn to_raw(h: &GpuTensorHandle) -> Result<RmHandle> {
+    if h.shape.len() > RM_MAX_RANK {
+        return Err(anyhow!("tensor rank {} exceeds RM_MAX_RANK", h.shape.len()));
+    }
+    let mut shape = [0u64; RM_MAX_RANK];
+    for (d, &s) in h.shape.iter().enumerate() {
+        shape[d] = s as u64;
+    }
+    Ok(RmHandle { buffer_id: h.buffer_id, device_id: h.device_id, rank: h.shape.len() as u32, shape })
+}
+fn from_raw(h: &RmHandle) -> GpuTensorHandle {
+    let handle = GpuTensorHandle {
+        shape: h.shape[..h.rank as usize].iter().map(|&d| d as usize).collect(),
+        device_id: h.device_id,
+        buffer_id: h.buffer_id,
+    };
+    // the side tables the rest of the runtime consults (accelerate-api/src/lib.rs:132-245)
+    runmat_accelerate_api::set_handle_precision(&handle, ProviderPrecision::F64);
+    runmat_accelerate_api::set_handle_storage(&handle, GpuTensorStorage::Real);
+    runmat_accelerate_api::set_handle_logical(&handle, false);
+    handle
+}
+fn empty_raw() -> RmHandle {
+    RmHandle { buffer_id: 0, device_id: 0, rank: 0, shape: [0; RM_MAX_RANK] }
+}
+
+impl CudaProvider {
+    /// `cuda_ordinal`: CUDA device; `device_id`: the id from `runmat_accelerate_api::next_device_id()` (lib.rs:3279).
+    pub fn new(cuda_ordinal: i32, device_id: u32) -> Result<Self> {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { rm_provider_create(cuda_ordinal, device_id, 1 /* RM_F64 */, &mut raw) })?;
+        Ok(Self { raw, device_id })
+    }
+    fn binary(&self, op: c_int, a: &GpuTensorHandle, b: &GpuTensorHandle) -> Result<GpuTensorHandle> {
+        let (ra, rb, mut out) = (to_raw(a)?, to_raw(b)?, empty_raw());
+        check(unsafe { rm_elem_binary(self.raw, op, &ra, &rb, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn unary(&self, op: c_int, a: &GpuTensorHandle) -> Result<GpuTensorHandle> {
+        let (ra, mut out) = (to_raw(a)?, empty_raw());
+        check(unsafe { rm_unary(self.raw, op, &ra, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn scalar(&self, op: c_int, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> {
+        let (ra, mut out) = (to_raw(a)?, empty_raw());
+        check(unsafe { rm_scalar_op_apply(self.raw, op, &ra, s, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+}
+
+impl Drop for CudaProvider {
+    fn drop(&mut self) {
+        unsafe { rm_provider_destroy(self.raw) };
+    }
+}
+
+macro_rules! ready { ($e:expr) => { Box::pin(async move { $e }) }; }
+
+impl AccelProvider for CudaProvider {
+    fn upload(&self, host: &HostTensorView) -> Result<GpuTensorHandle> {
+        let shape: Vec<u64> = host.shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_upload(self.raw, host.data.as_ptr(), shape.as_ptr(), shape.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn download<'a>(&'a self, h: &'a GpuTensorHandle) -> AccelDownloadFuture<'a> {
+        ready!({
+            let raw = to_raw(h)?;
+            let n: usize = h.shape.iter().product();
+            let mut data = vec![0.0f64; n];
+            check(unsafe { rm_download(self.raw, &raw, data.as_mut_ptr(), n as u64) })?;
+            Ok(HostTensorOwned { data, shape: h.shape.clone(), storage: GpuTensorStorage::Real })
+        })
+    }
+    fn free(&self, h: &GpuTensorHandle) -> Result<()> {
+        check(unsafe { rm_free(self.raw, &to_raw(h)?) })?;
+        runmat_accelerate_api::clear_handle_precision(h);
+        runmat_accelerate_api::clear_handle_class_name(h);
+        runmat_accelerate_api::clear_handle_logical(h);
+        runmat_accelerate_api::clear_handle_storage(h);
+        Ok(())
+    }
+    fn device_info(&self) -> String {
+        let mut buf = vec![0 as c_char; 512];
+        unsafe { rm_device_info_string(self.raw, buf.as_mut_ptr(), buf.len()) };
+        unsafe { CStr::from_ptr(buf.as_ptr()) }.to_string_lossy().into_owned()
+    }
+    fn device_id(&self) -> u32 { self.device_id }
+    fn precision(&self) -> ProviderPrecision { ProviderPrecision::F64 }
+    fn device_info_struct(&self) -> ApiDeviceInfo {
+        ApiDeviceInfo { device_id: self.device_id, name: self.device_info(), vendor: "NVIDIA".into(), memory_bytes: None, backend: Some("cuda-sm_100a".into()) }
+    }
+    fn read_scalar(&self, h: &GpuTensorHandle, idx: usize) -> Result<f64> {
+        let mut v = 0.0;
+        check(unsafe { rm_read_scalar(self.raw, &to_raw(h)?, idx as u64, &mut v) })?;
+        Ok(v)
+    }
+    fn zeros(&self, shape: &[usize]) -> Result<GpuTensorHandle> {
+        let s: Vec<u64> = shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_zeros(self.raw, s.as_ptr(), s.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn fill(&self, shape: &[usize], value: f64) -> Result<GpuTensorHandle> {
+        let s: Vec<u64> = shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_fill(self.raw, s.as_ptr(), s.len() as u32, value, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn linspace(&self, start: f64, stop: f64, count: usize) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_linspace(self.raw, start, stop, count as u64, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn transpose(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_transpose(self.raw, &to_raw(a)?, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn gather_linear(&self, source: &GpuTensorHandle, indices: &[u32], output_shape: &[usize]) -> Result<GpuTensorHandle> {
+        let s: Vec<u64> = output_shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_gather_linear(self.raw, &to_raw(source)?, indices.as_ptr(), indices.len() as u64, s.as_ptr(), s.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn scatter_linear(&self, target: &GpuTensorHandle, indices: &[u32], values: &GpuTensorHandle) -> Result<()> {
+        check(unsafe { rm_scatter_linear(self.raw, &to_raw(target)?, indices.as_ptr(), indices.len() as u64, &to_raw(values)?) })
+    }
+
+    // rm_binary_op / rm_unary_op / rm_scalar_op numbering: include/rm_accel.h
+    fn elem_add<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(0, a, b)) }
+    fn elem_sub<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(1, a, b)) }
+    fn elem_mul<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(2, a, b)) }
+    fn elem_div<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(3, a, b)) }
+    fn elem_pow<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(4, a, b)) }
+    fn elem_max<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(5, a, b)) }
+    fn elem_min<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(6, a, b)) }
+    fn unary_sin<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(0, a)) }
+    fn unary_cos<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(1, a)) }
+    fn unary_tanh<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(8, a)) }
+    fn unary_exp<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(12, a)) }
+    fn unary_log<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(14, a)) }
+    fn unary_sqrt<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(18, a)) }
+    fn unary_abs<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(19, a)) }
+    // ... the remaining unary_* methods forward the same way with their rm_unary_op code.
+    fn scalar_add(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(0, a, s) }
+    fn scalar_sub(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(1, a, s) }
+    fn scalar_mul(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(2, a, s) }
+    fn scalar_div(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(3, a, s) }
+    fn scalar_rsub(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(4, a, s) }
+    fn scalar_rdiv(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(5, a, s) }
+    fn scalar_max(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(6, a, s) }
+    fn scalar_min(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(7, a, s) }
+
+    fn fused_elementwise(&self, shader: &str, inputs: &[GpuTensorHandle], output_shape: &[usize], len: usize) -> Result<GpuTensorHandle> {
+        let sh = CString::new(shader)?;
+        let raws: Vec<RmHandle> = inputs.iter().map(to_raw).collect::<Result<_>>()?;
+        let s: Vec<u64> = output_shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_fused_elementwise(self.raw, sh.as_ptr(), raws.as_ptr(), raws.len() as u32, s.as_ptr(), s.len() as u32, len as u64, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn fused_elementwise_multi(&self, shader: &str, inputs: &[GpuTensorHandle], output_shape: &[usize], len: usize, num_outputs: usize) -> Result<Vec<GpuTensorHandle>> {
+        let sh = CString::new(shader)?;
+        let raws: Vec<RmHandle> = inputs.iter().map(to_raw).collect::<Result<_>>()?;
+        let s: Vec<u64> = output_shape.iter().map(|&d| d as u64).collect();
+        let mut outs = vec![empty_raw(); num_outputs];
+        check(unsafe { rm_fused_elementwise_multi(self.raw, sh.as_ptr(), raws.as_ptr(), raws.len() as u32, s.as_ptr(), s.len() as u32, len as u64, num_outputs as u32, outs.as_mut_ptr()) })?;
+        Ok(outs.iter().map(from_raw).collect())
+    }
+    #[allow(clippy::too_many_arguments)]
+    fn fused_reduction(&self, shader: &str, inputs: &[GpuTensorHandle], output_shape: &[usize], reduce_len: usize, num_slices: usize, workgroup_size: u32, flavor: ReductionFlavor) -> Result<GpuTensorHandle> {
+        let sh = CString::new(shader)?;
+        let raws: Vec<RmHandle> = inputs.iter().map(to_raw).collect::<Result<_>>()?;
+        let s: Vec<u64> = output_shape.iter().map(|&d| d as u64).collect();
+        let (kind, scale) = match flavor { ReductionFlavor::Sum => (0, 1.0), ReductionFlavor::Mean => (1, 1.0), ReductionFlavor::CustomScale(v) => (2, v) };
+        let mut out = empty_raw();
+        check(unsafe { rm_fused_reduction(self.raw, sh.as_ptr(), raws.as_ptr(), raws.len() as u32, s.as_ptr(), s.len() as u32, reduce_len as u64, num_slices as u64, workgroup_size, kind, scale, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn fused_cache_counters(&self) -> (u64, u64) {
+        let (mut h, mut m) = (0u64, 0u64);
+        unsafe { rm_fused_cache_counters(self.raw, &mut h, &mut m) };
+        (h, m)
+    }
+
+    fn reduce_sum<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_sum(self.raw, &to_raw(a)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_sum_dim<'a>(&'a self, a: &'a GpuTensorHandle, dim: usize) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_sum_dim(self.raw, &to_raw(a)?, dim as u32, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_mean<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_mean(self.raw, &to_raw(a)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_max_dim<'a>(&'a self, a: &'a GpuTensorHandle, dim: usize) -> AccelProviderFuture<'a, ReduceDimResult> {
+        ready!({
+            let (mut v, mut i) = (empty_raw(), empty_raw());
+            check(unsafe { rm_reduce_max_dim(self.raw, &to_raw(a)?, dim as u32, &mut v, &mut i) })?;
+            Ok(ReduceDimResult { values: from_raw(&v), indices: from_raw(&i) })
+        })
+    }
+
+    fn matmul<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_matmul(self.raw, &to_raw(a)?, &to_raw(b)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn matmul_epilogue<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle, ep: &'a MatmulEpilogue) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({
+            let row = ep.row_scale.as_ref().map(to_raw).transpose()?;
+            let col = ep.col_scale.as_ref().map(to_raw).transpose()?;
+            let diag = ep.diag_output.as_ref().map(to_raw).transpose()?;
+            let raw = RmMatmulEpilogue {
+                alpha: ep.alpha, beta: ep.beta,
+                row_scale: row.as_ref().map_or(std::ptr::null(), |h| h as *const _),
+                col_scale: col.as_ref().map_or(std::ptr::null(), |h| h as *const _),
+                row_op: matches!(ep.row_op, ScaleOp::Divide) as c_int, col_op: matches!(ep.col_op, ScaleOp::Divide) as c_int,
+                has_clamp_min: ep.clamp_min.is_some() as c_int, clamp_min: ep.clamp_min.unwrap_or(0.0),
+                has_clamp_max: ep.clamp_max.is_some() as c_int, clamp_max: ep.clamp_max.unwrap_or(0.0),
+                has_pow: ep.pow_exponent.is_some() as c_int, pow_exponent: ep.pow_exponent.unwrap_or(0.0),
+                diag_output: diag.as_ref().map_or(std::ptr::null(), |h| h as *const _),
+            };
+            let mut out = empty_raw();
+            check(unsafe { rm_matmul_epilogue_apply(self.raw, &to_raw(a)?, &to_raw(b)?, &raw, &mut out) })?;
+            Ok(from_raw(&out))
+        })
+    }
+    fn image_normalize<'a>(&'a self, input: &'a GpuTensorHandle, d: &'a ImageNormalizeDescriptor) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({
+            let raw = RmImageNormalizeDesc {
+                batch: d.batch as u64, height: d.height as u64, width: d.width as u64, epsilon: d.epsilon,
+                has_gain: d.gain.is_some() as c_int, gain: d.gain.unwrap_or(1.0), has_bias: d.bias.is_some() as c_int, bias: d.bias.unwrap_or(0.0),
+                has_gamma: d.gamma.is_some() as c_int, gamma: d.gamma.unwrap_or(1.0), clamp_zero: d.clamp_zero as c_int,
+            };
+            let mut out = empty_raw();
+            check(unsafe { rm_image_normalize(self.raw, &to_raw(input)?, &raw, &mut out) })?;
+            Ok(from_raw(&out))
+        })
+    }
+    fn stochastic_evolution(&self, state: &GpuTensorHandle, drift: f64, scale: f64, steps: u32) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_stochastic_evolution(self.raw, &to_raw(state)?, drift, scale, steps, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn set_rng_state(&self, state: u64) -> Result<()> { check(unsafe { rm_set_rng_state(self.raw, state) }) }
+
+    fn telemetry_snapshot(&self) -> ProviderTelemetry {
+        let mut t = RmTelemetry::default();
+        unsafe { rm_telemetry_snapshot(self.raw, &mut t) };
+        let cv = |s: RmDispatchStats| ProviderDispatchStats { count: s.count, total_wall_time_ns: s.total_wall_time_ns };
+        ProviderTelemetry {
+            fused_elementwise: cv(t.fused_elementwise), fused_reduction: cv(t.fused_reduction), matmul: cv(t.matmul),
+            linsolve: cv(t.linsolve), mldivide: cv(t.mldivide), mrdivide: cv(t.mrdivide),
+            upload_bytes: t.upload_bytes, download_bytes: t.download_bytes, solve_fallbacks: Vec::new(),
+            fusion_cache_hits: t.fusion_cache_hits, fusion_cache_misses: t.fusion_cache_misses,
+            bind_group_cache_hits: 0, bind_group_cache_misses: 0, bind_group_cache_by_layout: None, kernel_launches: Vec::new(),
+        }
+    }
+    fn reset_telemetry(&self) { unsafe { rm_reset_telemetry(self.raw) }; }
+}
+
+/// Registration, next to `register_wgpu_provider` (backend/wgpu/provider.rs:13):
+pub fn register_cuda_provider(cuda_ordinal: i32) -> Result<&'static CudaProvider> {
+    let id = runmat_accelerate_api::next_device_id();
+    let provider: &'static CudaProvider = Box::leak(Box::new(CudaProvider::new(cuda_ordinal, id)?));
+    unsafe { runmat_accelerate_api::register_provider(provider) };
+    Ok(provider)
+}

@@ -1,0 +1,71 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard ranges + the single final all-reduce."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_shard_ranges_tile_exactly():
+    from runmat_b200.sharding import shard_even_pairs, shard_range
+
+    for total in (0, 1, 7, 8, 100_000_000, 1_000_003):
+        for world in (1, 2, 3, 4, 8):
+            cuts = [shard_range(total, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+            ev = [shard_even_pairs(total, r, world) for r in range(world)]
+            assert ev[0][0] == 0 and ev[-1][1] == total and all(a[1] == b[0] for a, b in zip(ev, ev[1:]))
+            assert all(lo % 2 == 0 for lo, _ in ev)
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, M, T, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from oracle_binding import Oracle
+    from runmat_b200.sharding import allreduce_sum, shard_range
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = Oracle()
+    lo, hi = shard_range(M, rank, world)
+    partial = orc.mc_lcg_payoff_sum(M, T, lo, hi - lo)  # this rank's sum(max(S-K,0)) over its contiguous path range
+    t = torch.tensor([partial], dtype=torch.float64)
+    allreduce_sum(t, dist)                               # the path's ONLY collective: 1 f64
+    q.put((rank, float(t.item()), lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_monte_carlo_sum_matches_single_process(orc):
+    import torch.multiprocessing as mp
+
+    M, T, world = 4001, 16, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, M, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    whole = orc.mc_lcg_payoff_sum(M, T, 0, M)
+    for _, total, _, _ in results:
+        assert abs(total - whole) <= 1e-12 * abs(whole)  # only the order of the final two-term sum differs
+    ranges = sorted((lo, hi) for _, _, lo, hi in results)
+    assert ranges[0][0] == 0 and ranges[-1][1] == M and ranges[0][1] == ranges[1][0]
