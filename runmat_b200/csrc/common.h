@@ -198,5 +198,9 @@ rm_status compile_cuda_to_cubin(const std::string& src, const char* name, std::v
 
 // ---- other translation units ---------------------------------------------------------------------------------
 rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, const rm_matmul_epilogue* ep, rm_handle* out);
+// gemm_ozaki.cu: f64 GEMM on tcgen05 (int8 Ozaki split). *used=false => caller must run the DMMA engine.
+rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double* C, uint64_t m, uint64_t n, uint64_t k,
+                       const rm_matmul_epilogue* epd, const void* prow, const void* pcol, void* pdiag, bool ep_active, bool* used);
+int ozaki_default_slices();
 
 }  // namespace rm

@@ -273,6 +273,15 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
   if (m * n == 0) return RM_OK;
   rm_status st = RM_OK;
   if (p->precision == RM_F64) {
+    // engine selection: 1 = DMMA, 2 = Ozaki/tcgen05, 0 = auto (tcgen05 once the 128x256 tile grid can fill the SMs)
+    const uint64_t oz_tiles = ((m + 127) / 128) * ((n + 255) / 256);
+    const bool want_ozaki = p->matmul_engine == 2 || (p->matmul_engine == 0 && oz_tiles >= 96 && k >= 512 && !getenv("RUNMAT_B200_DISABLE_OZAKI"));
+    if (want_ozaki) {
+      bool used = false;
+      st = ozaki_matmul(p, (const double*)pa, (const double*)pb, (double*)pc, m, n, k, epd, prow, pcol, pdiag, active, &used);
+      if (st != RM_OK) { std::string msg = last_error(); rm_free(p, out); set_error("%s", msg.c_str()); return st; }
+      if (used) return RM_OK;
+    }
     Epilogue ep{};
     ep.alpha = 1.0;
     if (epd) {

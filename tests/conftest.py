@@ -1,5 +1,7 @@
 import os
 import sys
+
+os.environ.setdefault("RUNMAT_B200_OZAKI_CHECK", "1")  # surface pipeline-protocol errors of the tcgen05 kernel in tests
 from pathlib import Path
 
 import pytest

@@ -463,15 +463,64 @@ def test_matmul_kats(prov):
         prov.matmul(prov.upload(np.ones((2, 3))), prov.upload(np.ones((2, 3))))
 
 
+@pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("m,k,n", [(1, 1, 1), (3, 5, 2), (128, 128, 128), (129, 67, 131), (256, 1024, 64), (255, 33, 257), (512, 16, 512),
                                    (1000, 1000, 10), (2, 4096, 2), (640, 640, 640)])
-def test_matmul_vs_oracle(prov, orc, m, k, n):
+def test_matmul_vs_oracle(prov, orc, m, k, n, engine):
+    """engine 1 = FP64 DMMA (mma.sync), engine 2 = Ozaki int8 split on tcgen05/TMEM/TMA (gemm_ozaki.cu)."""
     rng = np.random.default_rng(m * 7 + n)
     a, b = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (k, n))
-    hc = prov.matmul(prov.upload(a), prov.upload(b))
-    got, want = prov.download(hc), orc.matmul(a, b)
+    prov.set_matmul_engine(engine)
+    try:
+        hc = prov.matmul(prov.upload(a), prov.upload(b))
+        got, want = prov.download(hc), orc.matmul(a, b)
+    finally:
+        prov.set_matmul_engine(0)
     assert got.shape == (m, n)
     matmul_close(got, a, b, want)
+
+
+def test_matmul_tcgen05_engine_details(prov, orc):
+    rng = np.random.default_rng(77)
+    prov.set_matmul_engine(2)
+    try:
+        # exact on small integers (every product and partial sum is representable)
+        a = rng.integers(-50, 50, (300, 200)).astype(np.float64)
+        b = rng.integers(-50, 50, (200, 260)).astype(np.float64)
+        assert np.array_equal(prov.download(prov.matmul(prov.upload(a), prov.upload(b))), a @ b)
+        # per-row / per-column exponents: rows and columns spanning 1e-150 .. 1e150
+        a = rng.uniform(-1, 1, (257, 384)) * (10.0 ** rng.integers(-150, 150, (257, 1)))
+        b = rng.uniform(-1, 1, (384, 300)) * (10.0 ** rng.integers(-150, 150, (1, 300)))
+        got, want = prov.download(prov.matmul(prov.upload(a), prov.upload(b))), orc.matmul(a, b)
+        matmul_close(got, a, b, want)
+        # zero rows / columns and an all-zero operand
+        a[5, :] = 0.0
+        b[:, 7] = 0.0
+        got = prov.download(prov.matmul(prov.upload(a), prov.upload(b)))
+        assert np.all(got[5, :] == 0.0) and np.all(got[:, 7] == 0.0)
+        assert np.all(prov.download(prov.matmul(prov.upload(np.zeros((130, 140))), prov.upload(b[:140, :]))) == 0.0)
+        # Inf / NaN inputs fall back to the native f64 engine: IEEE propagation like the host loop
+        a2 = rng.uniform(-1, 1, (64, 64))
+        b2 = rng.uniform(-1, 1, (64, 64))
+        a2[3, 4], b2[10, 20] = np.inf, np.nan
+        got, want = prov.download(prov.matmul(prov.upload(a2), prov.upload(b2))), orc.matmul(a2, b2)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+        # fused MatmulEpilogue on the tcgen05 engine
+        a3, b3 = rng.uniform(0, 1, (200, 150)), rng.uniform(0, 1, (150, 270))
+        rs, cs = rng.uniform(0.5, 2, (200, 1)), rng.uniform(0.5, 2, (1, 270))
+        diag = prov.zeros((200, 1))
+        ep = MatmulEpilogue(alpha=0.5, beta=-3.0, row_scale=prov.upload(rs), col_scale=prov.upload(cs), row_op="divide", clamp_min=0.25,
+                            clamp_max=4.0, pow_exponent=1.5, diag_output=diag)
+        got = prov.download(prov.matmul_epilogue(prov.upload(a3), prov.upload(b3), ep))
+        want, wdiag = orc.matmul_epilogue(orc.matmul(a3, b3), alpha=0.5, beta=-3.0, row_scale=rs, row_div=True, col_scale=cs, clamp_min=0.25,
+                                          clamp_max=4.0, pow_exponent=1.5, diag=np.zeros(200))
+        close(got, want, rtol=1e-9)
+        close(prov.download(diag)[:, 0], wdiag, rtol=1e-9)
+        # deterministic
+        h1, h2 = prov.upload(a3), prov.upload(b3)
+        assert np.array_equal(prov.download(prov.matmul(h1, h2)), prov.download(prov.matmul(h1, h2)))
+    finally:
+        prov.set_matmul_engine(0)
 
 
 def test_matmul_epilogue_kat_and_order(prov, orc):
@@ -513,8 +562,14 @@ def test_matmul_8192_properties(prov, orc):
     rng = np.random.default_rng(1)
     a, b = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
     ha, hb = prov.upload(a), prov.upload(b)
+    prov.set_matmul_engine(1)
+    c_dmma = prov.download(prov.matmul(ha, hb))
+    prov.set_matmul_engine(0)          # auto: the tcgen05 engine at this size
     hc = prov.matmul(ha, hb)
     c = prov.download(hc)
+    # the two engines agree far inside the tolerance (independent algorithms: DMMA vs exact-int8 split)
+    assert np.max(np.abs(c - c_dmma)) <= 1e-12 * n
+    del c_dmma
     x = rng.uniform(-1, 1, (n, 1))
     lhs = c @ x
     rhs = a @ (b @ x)
