@@ -382,7 +382,16 @@ def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
         for _ in range(reps):
             p.free(p.matmul(hA, hB))
         ms = p.timer_end_ms() / reps
-        out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "engine": "FP64 DMMA mma.sync.m8n8k4"}
+        out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9,
+                                  "engine": "auto -> tcgen05 (Ozaki int8 split, 7 slices = 28 exact int8 GEMMs, TMEM int32 accumulate, f64 recombine)"}
+        p.set_matmul_engine(1)
+        p.free(p.matmul(hA, hB))
+        p.synchronize()
+        p.timer_begin()
+        p.free(p.matmul(hA, hB))
+        ms1 = p.timer_end_ms()
+        p.set_matmul_engine(0)
+        out["matmul_8192_f64_dmma"] = {"ms": ms1, "gflops": 2.0 * n ** 3 / (ms1 * 1e-3) / 1e9, "engine": "FP64 DMMA mma.sync.m8n8k4"}
         p.free(hA)
         p.free(hB)
     return out
