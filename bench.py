@@ -185,18 +185,40 @@ def run_ours(args):
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
+    # The per-step all-reduce (1 f64) runs on a side stream so its latency overlaps the next step's kernels: the step's
+    # sum is copied into a 2-slot persistent buffer, the comm stream waits on that copy, reduces the slot in place, and
+    # the main stream only waits for a slot's previous reduction before overwriting it (two steps later).
+    if world > 1:
+        main_stream = torch.cuda.current_stream()
+        comm_stream = torch.cuda.Stream()
+        sum_slots = torch.zeros(2, dtype=torch.float64, device=f"cuda:{local_rank}")
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        reduced = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in reduced:
+            e.record(main_stream)
+    step_no = [0]
+
     def step():
         hC = p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS)
         hS = p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1)
         if world > 1:
+            slot = step_no[0] & 1
+            step_no[0] += 1
             ptr, n = p.device_ptr(hS)
             t = torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}")
-            dist.all_reduce(t)
+            main_stream.wait_event(reduced[slot])
+            sum_slots[slot:slot + 1].copy_(t)
+            copied[slot].record(main_stream)
+            comm_stream.wait_event(copied[slot])
+            with torch.cuda.stream(comm_stream):
+                dist.all_reduce(sum_slots[slot:slot + 1])
+                reduced[slot].record(comm_stream)
         return hC, hS
 
     def sync_all():
         p.synchronize()
         if world > 1:
+            torch.cuda.synchronize()
             dist.barrier()
             torch.cuda.synchronize()
 
@@ -220,12 +242,16 @@ def run_ours(args):
         if last_sum is not None:
             p.free(last_sum)
         last_sum = hS
+    if world > 1:
+        main_stream.wait_stream(comm_stream)  # the timed region ends when the last all-reduce has landed
     ms = p.timer_end_ms()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     launches = p.telemetry_snapshot().kernel_launches - t_before
     checksum = float(p.download(last_sum)[0, 0])
     p.free(last_sum)
+    if world > 1:
+        checksum = float(sum_slots[(step_no[0] - 1) & 1].item())  # the all-reduced sum of the last step
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -370,6 +396,36 @@ def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
     out["monte_carlo"] = {"paths": M, "steps": T, "ms": ms, "path_steps_per_s": M * T / (ms * 1e-3), "price": price, "scaling": "strong",
                           "collective": "one NCCL all-reduce of 1 f64" if world > 1 else None}
     if world == 1:
+        # configs[3] per-GPU share: [8,2160,3840] f32 normalise pipeline (image_normalize) + 5x5 imfilter on one 4K RGB frame
+        from runmat_b200 import B200Provider, ImageNormalizeDescriptor
+
+        with B200Provider(local_rank, device_id=rank + 1000, precision="f32") as p32:
+            Bi, H, W = 8, 2160, 3840
+            img = np.random.default_rng(3).random(Bi * H * W, dtype=np.float32)
+            hI = p32.upload(img, (Bi, H, W))
+            d = ImageNormalizeDescriptor(Bi, H, W, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+            for _ in range(2):
+                p32.free(p32.image_normalize(hI, d))
+            p32.synchronize()
+            p32.timer_begin()
+            for _ in range(5):
+                p32.free(p32.image_normalize(hI, d))
+            ms = p32.timer_end_ms() / 5
+            px = Bi * H * W
+            out["image_normalize_8x4k_f32"] = {"ms": ms, "gb_per_s_at_12B_per_px": 12 * px / (ms * 1e-3) / 1e9,
+                                               "gb_per_s_at_8B_per_px_algorithmic": 8 * px / (ms * 1e-3) / 1e9}
+            p32.free(hI)
+            frame = np.random.default_rng(4).random(H * W * 3, dtype=np.float32)
+            g = np.exp(-((np.arange(5) - 2)[:, None] ** 2 + (np.arange(5) - 2)[None, :] ** 2) / 2.0)
+            hF, hK = p32.upload(frame, (H, W, 3)), p32.upload((g / g.sum()).astype(np.float32))
+            for _ in range(2):
+                p32.free(p32.imfilter(hF, hK, padding="replicate"))
+            p32.synchronize()
+            p32.timer_begin()
+            for _ in range(5):
+                p32.free(p32.imfilter(hF, hK, padding="replicate"))
+            ms = p32.timer_end_ms() / 5
+            out["imfilter_5x5_4k_rgb_f32"] = {"ms": ms, "gb_per_s_at_8B_per_sample": 8 * H * W * 3 / (ms * 1e-3) / 1e9}
         n = 8192
         rng = np.random.default_rng(7)
         hA = p.upload(rng.uniform(-1, 1, n * n), (n, n))

@@ -13,6 +13,7 @@
 //   * reductions: per-thread accumulate -> warp shuffle -> shared -> deterministic last-block finish.
 // Arithmetic follows the CPU builtins' rounding: compiled with -fmad=false (Rust never fuses a*b+c).
 #include <cctype>
+#include <cstdlib>
 #include <sstream>
 
 #include "common.h"
@@ -322,6 +323,14 @@ __device__ __forceinline__ double rm_f64(double x) { return x; }
 __device__ __forceinline__ float rm_f32(double x) { return (float)x; }
 )CUDA";
 
+// tuning knobs (defaults chosen from the r01 sweep on B200; overridable for experiments)
+int env_int(const char* name, int dflt, int lo, int hi) {
+  if (const char* e = getenv(name)) { int v = atoi(e); if (v >= lo && v <= hi) return v; }
+  return dflt;
+}
+int red_unroll() { return env_int("RUNMAT_B200_RED_UNROLL", 2, 1, 8); }
+int red_minblocks() { return env_int("RUNMAT_B200_RED_MINB", 0, 0, 8); }
+
 std::string input_params(uint32_t n_inputs) {
   std::string s;
   for (uint32_t k = 0; k < n_inputs; ++k) s += "const T* __restrict__ in" + std::to_string(k) + ", ";
@@ -447,7 +456,10 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
 
   if (layout == RedLayout::Contig) {
     // slice s occupies [s*len, (s+1)*len). grid = (blocks_per_slice, num_slices).
-    o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(" << input_params(ni)
+    o << "#define RED_U " << red_unroll() << "\n";
+    if (red_minblocks() > 0) o << "extern \"C\" __global__ void __launch_bounds__(256, " << red_minblocks() << ") rm_fused_red(";
+    else o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(";
+    o << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner) {\n";
     o << "  __shared__ double smem[32];\n  __shared__ bool is_last;\n";
@@ -456,16 +468,17 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     o << "  const u64 tid = (u64)bidx * blockDim.x + threadIdx.x;\n  const u64 nthr = (u64)bps * blockDim.x;\n";
     o << "  double acc = IDENT; bool saw_nan = false;\n";
     o << "  u64 i = tid;\n";
-    // 2 vectors per input in flight per iteration
-    o << "  for (; i + nthr < nvec; i += 2 * nthr) {\n";
-    for (uint32_t k = 0; k < ni; ++k)
-      o << "    const vec_t a" << k << " = ldv(in" << k << " + base + i * VEC); const vec_t b" << k << " = ldv(in" << k << " + base + (i + nthr) * VEC);\n";
-    o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
-    for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = a" << k << ".x[l];\n";
-    o << "      accumulate(acc, saw_nan, " << prog.val_expr << ");\n    }\n";
-    o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
-    for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = b" << k << ".x[l];\n";
-    o << "      accumulate(acc, saw_nan, " << prog.val_expr << ");\n    }\n  }\n";
+    // U 256-bit vectors per input in flight per thread per iteration (all loads issued before any math)
+    o << "  for (; i + (u64)(RED_U - 1) * nthr < nvec; i += (u64)RED_U * nthr) {\n";
+    for (uint32_t k = 0; k < ni; ++k) {
+      o << "    vec_t a" << k << "[RED_U];\n";
+    }
+    o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "      a" << k << "[u] = ldv(in" << k << " + base + (i + (u64)u * nthr) * VEC);\n";
+    o << "    }\n";
+    o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n      #pragma unroll\n      for (int l = 0; l < VEC; ++l) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = a" << k << "[u].x[l];\n";
+    o << "        accumulate(acc, saw_nan, " << prog.val_expr << ");\n      }\n    }\n  }\n";
     o << "  for (; i < nvec; i += nthr) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "    const vec_t a" << k << " = ldv(in" << k << " + base + i * VEC);\n";
     o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
