@@ -351,7 +351,7 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       uint64_t threads = 256;
       while (threads > 32 && threads * vec / 2 >= reduce_len) threads >>= 1;
       if (num_slices < 2 * sms && num_slices <= FusedCache::kTicketCap) {
-        int bpsm = 8;
+        int bpsm = 4;  // r01 sweep: 4 CTAs/SM beats 8 and 16 (the kernel is ~50 us: per-block tail and finish costs dominate)
         if (const char* e = getenv("RUNMAT_B200_RED_BPSM")) { int v = atoi(e); if (v >= 1 && v <= 64) bpsm = v; }
         const uint64_t want = (sms * (uint64_t)bpsm + num_slices - 1) / num_slices;
         const uint64_t max_bps = std::max<uint64_t>(1, reduce_len / (threads * vec * 4));

@@ -12,6 +12,8 @@
 //   sweep 2  normalise + gain/bias/clamp/gamma, one read + one write.
 // HBM traffic: 2 reads + 1 write per pixel (12 B/px f32); a 4K batch is far larger than L2, so the second
 // read cannot be served on-chip with a batch-fastest layout (DESIGN.md "image_normalize").
+#include <type_traits>
+
 #include "common.h"
 
 namespace rm {
@@ -51,6 +53,49 @@ moments_partial_kernel(const T* __restrict__ x, uint64_t B, uint64_t P, double* 
   }
 }
 
+// Fast path (B %% VEC == 0 and the grid stride keeps each lane on a fixed image): 16-byte vector loads, 4 in flight per
+// thread, per-lane f64 accumulators, one shared-memory atomic per lane at the end.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+moments_partial_vec_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, double* __restrict__ partial /*[grid][2][B]*/) {
+  extern __shared__ double sh[];  // [2][B]
+  for (uint32_t i = threadIdx.x; i < 2 * B; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t b0 = (uint32_t)((v0 * VEC) % B);  // fixed for this thread: (nthr*VEC) %% B == 0
+  double K[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int l = 0; l < VEC; ++l) { K[l] = (double)x[b0 + l]; s1[l] = 0.0; s2[l] = 0.0; }
+  typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
+  const V* xv = reinterpret_cast<const V*>(x);
+  uint64_t v = v0;
+  for (; v + 3 * nthr < nvec; v += 4 * nthr) {
+    V a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const T* e = reinterpret_cast<const T*>(&a[u]);
+#pragma unroll
+      for (int l = 0; l < VEC; ++l) { const double d = (double)e[l] - K[l]; s1[l] += d; s2[l] += d * d; }
+    }
+  }
+  for (; v < nvec; v += nthr) {
+    const V a = __ldcs(xv + v);
+    const T* e = reinterpret_cast<const T*>(&a);
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) { const double d = (double)e[l] - K[l]; s1[l] += d; s2[l] += d * d; }
+  }
+#pragma unroll
+  for (int l = 0; l < VEC; ++l) { atomicAdd(&sh[b0 + l], s1[l]); atomicAdd(&sh[B + b0 + l], s2[l]); }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) {
+    partial[((uint64_t)blockIdx.x * 2 + 0) * B + i] = sh[i];
+    partial[((uint64_t)blockIdx.x * 2 + 1) * B + i] = sh[B + i];
+  }
+}
+
 // stats[b] = {mean, inv_sigma}
 template <typename T>
 __global__ void moments_finalize_kernel(const T* __restrict__ x, const double* __restrict__ partial, uint32_t nblocks, uint64_t B, uint64_t P,
@@ -73,6 +118,47 @@ struct NormParams {
   int has_gain, has_bias, has_gamma, clamp_zero;
   double gain, bias, gamma;
 };
+
+__device__ __forceinline__ float rm_powT(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double rm_powT(double a, double b) { return pow(a, b); }
+
+// Fixed-lane variant: (gridDim*blockDim*VEC) %% B == 0, so each thread's lane l always belongs to image (b0+l): the
+// per-image mean / 1/sigma live in registers and the inner loop is load -> 4 FLOPs (+pow) -> store.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_fixed_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
+                       const __grid_constant__ NormParams np) {
+  typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
+  const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t b0 = (uint32_t)((v0 * VEC) % B);
+  T mean[VEC], inv[VEC];
+#pragma unroll
+  for (int l = 0; l < VEC; ++l) { mean[l] = (T)stats[2 * (b0 + l)]; inv[l] = (T)stats[2 * (b0 + l) + 1]; }
+  const T gain = (T)np.gain, bias = (T)np.bias, gamma = (T)np.gamma;
+  const V* xv = reinterpret_cast<const V*>(x);
+  V* yv = reinterpret_cast<V*>(y);
+  auto body = [&](V a) {
+    T* e = reinterpret_cast<T*>(&a);
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) {
+      T val = (e[l] - mean[l]) * inv[l];
+      if (np.has_gain) val *= gain;
+      if (np.has_bias) val += bias;
+      if (np.clamp_zero) val = val > (T)0 ? val : (T)0;
+      if (np.has_gamma) val = rm_powT(val, gamma);
+      e[l] = val;
+    }
+    return a;
+  };
+  uint64_t v = v0;
+  for (; v + nthr < nvec; v += 2 * nthr) {
+    const V a = __ldcs(xv + v), b = __ldcs(xv + v + nthr);
+    __stcs(yv + v, body(a));
+    __stcs(yv + v + nthr, body(b));
+  }
+  for (; v < nvec; v += nthr) __stcs(yv + v, body(__ldcs(xv + v)));
+}
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
@@ -166,6 +252,62 @@ imfilter_kernel(const T* __restrict__ img, const T* __restrict__ ker, T* __restr
   }
 }
 
+// Tiled variant for 2-D kernels (the common case: fspecial-style filters on H x W x C images). One CTA produces a
+// 64 x 16 output tile of one plane: the input tile + halo is staged ONCE in shared memory with the padding rule resolved
+// per row/column (separable index maps), then each thread accumulates its 4 outputs from shared memory, visiting the
+// kernel points in the host's column-major order with separate multiply and add (-fmad=false): bit-identical to
+// imfilter.rs:731-745. HBM traffic ~ (1 + halo) read + 1 write per sample instead of taps x (index math + load).
+constexpr int IMF_TX = 64, IMF_TY = 16, IMF_MAXK = 15;
+template <typename T>
+__global__ void __launch_bounds__(256)
+imfilter_tiled_kernel(const T* __restrict__ img, const T* __restrict__ ker, T* __restrict__ out, const __grid_constant__ FilterParams fp) {
+  extern __shared__ __align__(16) unsigned char imf_smem[];
+  const int K0 = (int)fp.ke[0], K1 = (int)fp.ke[1];
+  const int SX = IMF_TX + K0 - 1, SY = IMF_TY + K1 - 1;
+  T* tile = reinterpret_cast<T*>(imf_smem);                   // [SY][SX]
+  T* w = tile + SX * SY;                                      // [K1][K0] in application order
+  int* map0 = reinterpret_cast<int*>(w + K0 * K1);            // [SX] source row (dim 0) or -1
+  int* map1 = map0 + SX;                                      // [SY] source col (dim 1) or -1
+  const int64_t t0 = (int64_t)blockIdx.x * IMF_TX, t1 = (int64_t)blockIdx.y * IMF_TY;
+  const uint64_t plane = blockIdx.z;
+  const int tid = threadIdx.x;
+  auto remap = [&](int64_t c, int64_t len) -> int {
+    if (c >= 0 && c < len) return (int)c;
+    if (fp.padding == 0) return -1;
+    return (int)(fp.padding == 1 ? clamp_index(c, len) : (fp.padding == 3 ? wrap_index(c, len) : reflect_index(c, len)));
+  };
+  for (int i = tid; i < SX; i += 256) map0[i] = remap(t0 + i + fp.base[0] - fp.origin[0], (int64_t)fp.ie[0]);
+  for (int i = tid; i < SY; i += 256) map1[i] = remap(t1 + i + fp.base[1] - fp.origin[1], (int64_t)fp.ie[1]);
+  for (int i = tid; i < K0 * K1; i += 256) {
+    const int k0 = i % K0, k1 = i / K0;
+    w[i] = fp.mode == 0 ? ker[k0 + k1 * K0] : ker[(K0 - 1 - k0) + (K1 - 1 - k1) * K0];
+  }
+  __syncthreads();
+  const T* src = img + plane * fp.ie[0] * fp.ie[1];
+  for (int i = tid; i < SX * SY; i += 256) {
+    const int sx = i % SX, sy = i / SX;
+    const int r = map0[sx], c = map1[sy];
+    tile[i] = (r < 0 || c < 0) ? (T)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+  }
+  __syncthreads();
+  const int lx = tid & 63, ly = tid >> 6;  // 4 thread rows; each thread produces outputs ly, ly+4, ly+8, ly+12
+  T acc[4] = {(T)0, (T)0, (T)0, (T)0};
+  for (int k1 = 0; k1 < K1; ++k1)
+    for (int k0 = 0; k0 < K0; ++k0) {
+      const T kv = w[k0 + k1 * K0];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += kv * tile[(ly + 4 * j + k1) * SX + lx + k0];
+    }
+  const uint64_t o0 = (uint64_t)t0 + lx;
+  if (o0 < fp.oe[0]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t o1 = (uint64_t)t1 + ly + 4 * j;
+      if (o1 < fp.oe[1]) out[o0 + o1 * fp.oe[0] + plane * fp.oe[0] * fp.oe[1]] = acc[j];
+    }
+  }
+}
+
 // ---- value + index reductions along one dim of [pre, n, post] (simple_provider.rs:7387-7445) ---------------------------
 template <typename T, bool IS_MIN>
 __global__ void minmax_dim_kernel(const T* __restrict__ a, T* __restrict__ vals, T* __restrict__ idx, uint64_t pre, uint64_t n, uint64_t post) {
@@ -216,28 +358,48 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   if (total == 0) return RM_OK;
   RM_REQUIRE(B <= 1024, RM_UNSUPPORTED, "image_normalize: batch %llu > 1024 not supported by provider", (unsigned long long)B);
 
-  const uint32_t threads = 1024 - (1024 % (uint32_t)B);  // whole number of pixel lanes
+  const int VEC = p->precision == RM_F64 ? 2 : 4;
+  const uint32_t sms = (uint32_t)p->prop.multiProcessorCount;
+  // fast path: lanes stay on a fixed image when the grid stride (in elements) is a multiple of B
+  uint32_t fast_blocks = 0;
+  if (B % VEC == 0 && total % VEC == 0) {
+    for (uint32_t mult = 8; mult >= 1 && !fast_blocks; --mult) {
+      const uint64_t blocks = (uint64_t)sms * mult;
+      if ((blocks * 256ull * VEC) % B == 0 && blocks * 256ull * 2 <= total / VEC + blocks * 256ull) fast_blocks = (uint32_t)blocks;
+    }
+  }
+  const uint32_t threads = 1024 - (1024 % (uint32_t)B);  // (generic path) whole number of pixel lanes
   const uint32_t lanes = threads / (uint32_t)B;
-  uint32_t nblocks = (uint32_t)std::min<uint64_t>((uint64_t)p->prop.multiProcessorCount * 2, std::max<uint64_t>(1, P / (lanes * 4ull)));
+  uint32_t nblocks = fast_blocks ? fast_blocks : (uint32_t)std::min<uint64_t>((uint64_t)sms * 2, std::max<uint64_t>(1, P / (lanes * 4ull)));
   const size_t partial_bytes = (size_t)nblocks * 2 * B * sizeof(double);
   const size_t stats_off = ((partial_bytes + 255) / 256) * 256;
   rm_status st = ensure_scratch(p, stats_off + 2 * B * sizeof(double));
   if (st != RM_OK) { rm_free(p, out); return st; }
   double* partial = (double*)p->reduce_scratch;
   double* stats = (double*)((char*)p->reduce_scratch + stats_off);
-  const size_t sh = (size_t)lanes * 2 * B * sizeof(double);
+  const size_t sh = fast_blocks ? (size_t)2 * B * sizeof(double) : (size_t)lanes * 2 * B * sizeof(double);
   NormParams np{d->has_gain, d->has_bias, d->has_gamma, d->clamp_zero, d->gain, d->bias, d->gamma};
-  const unsigned ngrid = (unsigned)std::min<uint64_t>((total / 4 + 255) / 256 + 1, (uint64_t)p->prop.multiProcessorCount * 16);
+  const unsigned ngrid = (unsigned)std::min<uint64_t>((total / 4 + 255) / 256 + 1, (uint64_t)sms * 16);
   if (p->precision == RM_F64) {
-    cudaFuncSetAttribute(moments_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    moments_partial_kernel<double><<<nblocks, threads, sh, p->stream>>>((const double*)src, B, P, partial);
+    if (fast_blocks) {
+      moments_partial_vec_kernel<double, 2><<<nblocks, 256, sh, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
+    } else {
+      cudaFuncSetAttribute(moments_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+      moments_partial_kernel<double><<<nblocks, threads, sh, p->stream>>>((const double*)src, B, P, partial);
+    }
     moments_finalize_kernel<double><<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>((const double*)src, partial, nblocks, B, P, d->epsilon, stats);
-    normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
+    if (fast_blocks) normalize_fixed_kernel<double, 2><<<fast_blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, (uint32_t)B, total, stats, np);
+    else normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
   } else {
-    cudaFuncSetAttribute(moments_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
+    if (fast_blocks) {
+      moments_partial_vec_kernel<float, 4><<<nblocks, 256, sh, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
+    } else {
+      cudaFuncSetAttribute(moments_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+      moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
+    }
     moments_finalize_kernel<float><<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
-    normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
+    if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+    else normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "image_normalize launch failed: %s", cudaGetErrorString(e)); }
@@ -278,9 +440,19 @@ RM_EXPORT rm_status rm_imfilter(rm_provider* p, const rm_handle* image, const rm
   RM_TRY(alloc_tensor(p, oshape, orank, out, &po));
   const uint64_t total = fp.oe[0] * fp.oe[1] * fp.oe[2];
   if (total == 0) return RM_OK;
-  const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 32);
-  if (p->precision == RM_F64) imfilter_kernel<double><<<grid, 256, 0, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, total, fp);
-  else imfilter_kernel<float><<<grid, 256, 0, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, total, fp);
+  const bool tiled = fp.ke[2] == 1 && fp.ke[0] <= IMF_MAXK && fp.ke[1] <= IMF_MAXK && fp.oe[2] <= 65535 && (fp.oe[1] + IMF_TY - 1) / IMF_TY <= 65535 &&
+                     fp.ie[0] < (1ull << 31) && fp.ie[1] < (1ull << 31);
+  if (tiled) {
+    const int SX = IMF_TX + (int)fp.ke[0] - 1, SY = IMF_TY + (int)fp.ke[1] - 1;
+    const size_t sh = (size_t)(SX * SY + (int)(fp.ke[0] * fp.ke[1])) * p->elem_size() + (size_t)(SX + SY) * sizeof(int) + 16;
+    dim3 grid((unsigned)((fp.oe[0] + IMF_TX - 1) / IMF_TX), (unsigned)((fp.oe[1] + IMF_TY - 1) / IMF_TY), (unsigned)fp.oe[2]);
+    if (p->precision == RM_F64) imfilter_tiled_kernel<double><<<grid, 256, sh, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, fp);
+    else imfilter_tiled_kernel<float><<<grid, 256, sh, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, fp);
+  } else {
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 32);
+    if (p->precision == RM_F64) imfilter_kernel<double><<<grid, 256, 0, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, total, fp);
+    else imfilter_kernel<float><<<grid, 256, 0, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, total, fp);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "imfilter launch failed: %s", cudaGetErrorString(e)); }
   count_launch(p);

@@ -744,6 +744,19 @@ def test_imfilter_kats_and_modes(prov, orc):
                 got = prov.download(prov.imfilter(hi, hk, padding=padding, constant_value=0.5, shape=shape, mode=mode))
                 want = orc.imfilter(img, ker, padding=padding, cval=0.5, shape=shape, mode=mode)
                 assert_same(got, want)  # only mul/add in the host's order, no FMA: bit-exact
+    # even-sized and rectangular kernels, kernels larger than the image, and a 3-D kernel (generic, non-tiled path)
+    for kshape in [(2, 2), (4, 3), (1, 7), (15, 15), (3, 3, 2)]:
+        kk = rng.uniform(-1, 1, kshape)
+        for padding in ("constant", "symmetric", "circular", "replicate"):
+            for shape in ("same", "full", "valid"):
+                got = prov.download(prov.imfilter(hi, prov.upload(kk), padding=padding, shape=shape))
+                assert_same(got, orc.imfilter(img, kk, padding=padding, shape=shape))
+    small = rng.uniform(0, 1, (3, 4))
+    got = prov.download(prov.imfilter(prov.upload(small), prov.upload(np.ones((7, 9))), padding="symmetric"))
+    assert_same(got, orc.imfilter(small, np.ones((7, 9)), padding="symmetric"))
+    big = rng.uniform(0, 1, (300, 200))
+    got = prov.download(prov.imfilter(prov.upload(big), hk, padding="replicate"))
+    assert_same(got, orc.imfilter(big, ker, padding="replicate"))
 
 
 # ---------------------------------------------------------------------------------------------------------------
