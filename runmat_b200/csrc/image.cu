@@ -96,22 +96,35 @@ moments_partial_vec_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, 
   }
 }
 
-// stats[b] = {mean, inv_sigma}
+// stats[b] = {mean, inv_sigma}. One CTA per image: threads stride over the per-block partials, fixed-order tree in
+// shared memory (deterministic).
 template <typename T>
-__global__ void moments_finalize_kernel(const T* __restrict__ x, const double* __restrict__ partial, uint32_t nblocks, uint64_t B, uint64_t P,
-                                        double eps, double* __restrict__ stats) {
-  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__global__ void __launch_bounds__(128)
+moments_finalize_kernel(const T* __restrict__ x, const double* __restrict__ partial, uint32_t nblocks, uint64_t B, uint64_t P,
+                        double eps, double* __restrict__ stats) {
+  __shared__ double r1[128], r2[128];
+  const uint64_t b = blockIdx.x;
   double s1 = 0.0, s2 = 0.0;
-  for (uint32_t i = 0; i < nblocks; ++i) { s1 += partial[((uint64_t)i * 2 + 0) * B + b]; s2 += partial[((uint64_t)i * 2 + 1) * B + b]; }
-  const double K = (double)x[b];
-  const double n = (double)P;
-  const double dm = s1 / n;                       // mean of (x-K)
-  double var = (s2 - s1 * dm) / n;                // sum((x-mean)^2)/P
-  if (var < 0.0) var = 0.0;
-  const double sigma = sqrt(var + eps);
-  stats[2 * b] = K + dm;
-  stats[2 * b + 1] = sigma > 0.0 ? 1.0 / sigma : 0.0;  // simple_provider.rs:7962
+  for (uint32_t i = threadIdx.x; i < nblocks; i += 128) { s1 += partial[((uint64_t)i * 2 + 0) * B + b]; s2 += partial[((uint64_t)i * 2 + 1) * B + b]; }
+  r1[threadIdx.x] = s1;
+  r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) { r1[threadIdx.x] += r1[threadIdx.x + off]; r2[threadIdx.x] += r2[threadIdx.x + off]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    s1 = r1[0];
+    s2 = r2[0];
+    const double K = (double)x[b];
+    const double n = (double)P;
+    const double dm = s1 / n;                       // mean of (x-K)
+    double var = (s2 - s1 * dm) / n;                // sum((x-mean)^2)/P
+    if (var < 0.0) var = 0.0;
+    const double sigma = sqrt(var + eps);
+    stats[2 * b] = K + dm;
+    stats[2 * b + 1] = sigma > 0.0 ? 1.0 / sigma : 0.0;  // simple_provider.rs:7962
+  }
 }
 
 struct NormParams {
@@ -387,7 +400,7 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
       cudaFuncSetAttribute(moments_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
       moments_partial_kernel<double><<<nblocks, threads, sh, p->stream>>>((const double*)src, B, P, partial);
     }
-    moments_finalize_kernel<double><<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>((const double*)src, partial, nblocks, B, P, d->epsilon, stats);
+    moments_finalize_kernel<double><<<(unsigned)B, 128, 0, p->stream>>>((const double*)src, partial, nblocks, B, P, d->epsilon, stats);
     if (fast_blocks) normalize_fixed_kernel<double, 2><<<fast_blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, (uint32_t)B, total, stats, np);
     else normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
   } else {
@@ -397,7 +410,7 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
       cudaFuncSetAttribute(moments_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
       moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
     }
-    moments_finalize_kernel<float><<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
+    moments_finalize_kernel<float><<<(unsigned)B, 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
     if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
     else normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
   }
