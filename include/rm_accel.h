@@ -261,7 +261,8 @@ rm_status rm_syrk(rm_provider* p, const rm_handle* a, rm_handle* out); /* A' * A
 /* selects the GEMM engine: 0 = auto, 1 = FP64 DMMA (mma.sync m8n8k4), 2 = Ozaki split on tcgen05 i8 */
 rm_status rm_set_matmul_engine(rm_provider* p, int engine);
 
-/* ---- a9: mldivide core (lib.rs:2477-2489) -------------------------------------------------------- */
+/* ---- a9: mldivide core (lib.rs:2477-2489): square systems by device LU with partial pivoting; non-square,
+ *      singular or badly conditioned inputs return RM_UNSUPPORTED (host SVD fallback, as with wgpu today) ---- */
 rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_handle* b, rm_handle* out);
 
 /* ---- a10/a11: Monte-Carlo evolution + RNG (lib.rs:1713-1775) -------------------------------------- */

@@ -202,5 +202,7 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
 rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double* C, uint64_t m, uint64_t n, uint64_t k,
                        const rm_matmul_epilogue* epd, const void* prow, const void* pcol, void* pdiag, bool ep_active, bool* used);
 int ozaki_default_slices();
+rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const double* B, uint64_t ldb, double* C, uint64_t ldc,
+                            uint64_t m, uint64_t n, uint64_t k);
 
 }  // namespace rm

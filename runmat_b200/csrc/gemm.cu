@@ -70,7 +70,8 @@ __device__ __forceinline__ double apply_epilogue(double v, const Epilogue& ep, u
 template <bool ALIGNED2>
 __global__ void __launch_bounds__(256, 1)
 dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
-                  uint64_t m, uint64_t n, uint64_t k, const __grid_constant__ Epilogue ep) {
+                  uint64_t m, uint64_t n, uint64_t k, uint64_t lda, uint64_t ldb, uint64_t ldc, int subtract,
+                  const __grid_constant__ Epilogue ep) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                              // [STAGES][BK][LDA_S]
   double* Bs = smem + (size_t)STAGES * A_STAGE;   // [STAGES][BN][LDB_S]
@@ -94,7 +95,7 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
         const int kc = c / (BM / 2), mr = (c % (BM / 2)) * 2;
         const uint64_t gi = m0 + mr, gk = k0 + kc;
         const bool ok = gi < m && gk < k;
-        cp_async16(as + kc * LDA_S + mr, A + (ok ? gk * m + gi : 0), ok);
+        cp_async16(as + kc * LDA_S + mr, A + (ok ? gk * lda + gi : 0), ok);
       }
       // B tile: BN columns of BK rows; 8 chunks per column
 #pragma unroll
@@ -102,7 +103,7 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
         const int nc = c / (BK / 2), kr = (c % (BK / 2)) * 2;
         const uint64_t gj = n0 + nc, gk = k0 + kr;
         const bool ok = gj < n && gk < k;
-        cp_async16(bs + nc * LDB_S + kr, B + (ok ? gj * k + gk : 0), ok);
+        cp_async16(bs + nc * LDB_S + kr, B + (ok ? gj * ldb + gk : 0), ok);
       }
     } else {
 #pragma unroll 4
@@ -110,14 +111,14 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
         const int kc = c / BM, mr = c % BM;
         const uint64_t gi = m0 + mr, gk = k0 + kc;
         const bool ok = gi < m && gk < k;
-        cp_async8(as + kc * LDA_S + mr, A + (ok ? gk * m + gi : 0), ok);
+        cp_async8(as + kc * LDA_S + mr, A + (ok ? gk * lda + gi : 0), ok);
       }
 #pragma unroll 4
       for (int c = tid; c < BN * BK; c += 256) {
         const int nc = c / BK, kr = c % BK;
         const uint64_t gj = n0 + nc, gk = k0 + kr;
         const bool ok = gj < n && gk < k;
-        cp_async8(bs + nc * LDB_S + kr, B + (ok ? gj * k + gk : 0), ok);
+        cp_async8(bs + nc * LDB_S + kr, B + (ok ? gj * ldb + gk : 0), ok);
       }
     }
   };
@@ -172,8 +173,9 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
         const uint64_t col = n0 + wn + j * 8 + 2 * t + e;
         if (col < n) {
           double v = acc[i][j][e];
-          if (ep.active) v = apply_epilogue(v, ep, row, col);
-          C[row + col * m] = v;
+          if (subtract) v = C[row + col * ldc] - v;  // trailing-matrix update of the blocked LU (solve.cu)
+          else if (ep.active) v = apply_epilogue(v, ep, row, col);
+          C[row + col * ldc] = v;
         }
       }
     }
@@ -293,10 +295,10 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
     const bool aligned = (m % 2 == 0) && (k % 2 == 0);
     if (aligned) {
       cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-      dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, ep);
+      dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, m, k, m, 0, ep);
     } else {
       cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-      dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, ep);
+      dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, m, k, m, 0, ep);
     }
   } else {
     EpilogueF ep{};
@@ -312,6 +314,27 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
   if (e != cudaSuccess) { st = fail(RM_ERROR, "matmul launch failed: %s", cudaGetErrorString(e)); rm_free(p, out); }
   else count_launch(p);
   return st;
+}
+
+// C (ldc) -= A (lda) * B (ldb) on sub-matrices of column-major storage: the GEMM core of mldivide's blocked LU / solves.
+rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const double* B, uint64_t ldb, double* C, uint64_t ldc,
+                            uint64_t m, uint64_t n, uint64_t k) {
+  if (m == 0 || n == 0 || k == 0) return RM_OK;
+  Epilogue ep{};
+  ep.alpha = 1.0;
+  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN));
+  RM_REQUIRE(grid.y <= 65535, RM_UNSUPPORTED, "gemm update: n too large");
+  const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A) % 16 == 0) && (((uintptr_t)B) % 16 == 0);
+  if (aligned) {
+    cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep);
+  } else {
+    cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep);
+  }
+  RM_LAUNCH_CHECK();
+  count_launch(p);
+  return RM_OK;
 }
 
 }  // namespace rm

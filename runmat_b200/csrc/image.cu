@@ -506,12 +506,6 @@ static rm_status minmax_dim(rm_provider* p, const rm_handle* a, uint32_t dim, bo
 RM_EXPORT rm_status rm_reduce_max_dim(rm_provider* p, const rm_handle* a, uint32_t dim, rm_handle* values, rm_handle* indices) { return minmax_dim(p, a, dim, false, values, indices); }
 RM_EXPORT rm_status rm_reduce_min_dim(rm_provider* p, const rm_handle* a, uint32_t dim, rm_handle* values, rm_handle* indices) { return minmax_dim(p, a, dim, true, values, indices); }
 
-// a9 (mldivide) is a "next" row: not yet provided; callers fall back to host exactly as the
-// wgpu provider's own implementation does today (download -> host solve -> upload, provider/ops/solve.rs:131-205).
-RM_EXPORT rm_status rm_mldivide(rm_provider*, const rm_handle*, const rm_handle*, rm_handle*) {
-  return fail(RM_UNSUPPORTED, "mldivide not supported by provider");
-}
-
 RM_EXPORT rm_status rm_warmup(rm_provider* p) {
   RM_REQUIRE(p, RM_INVALID_ARG, "null provider");
   DeviceGuard g(p->ordinal);

@@ -587,6 +587,57 @@ def test_matmul_8192_properties(prov, orc):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# a9: mldivide (device LU; the reference pins this path by residual only: mldivide.rs:662-676)
+# ---------------------------------------------------------------------------------------------------------------
+def test_mldivide_kat_and_scalar(prov):
+    from svd_solve import mldivide as oracle_mldivide
+
+    a = np.array([1.0, 3.0, 2.0, 4.0]).reshape((2, 2), order="F")  # mldivide.rs:667-668 solves_square_system
+    b = np.array([[5.0], [6.0]])
+    x = prov.download(prov.mldivide(prov.upload(a), prov.upload(b)))
+    assert x.shape == (2, 1) and np.linalg.norm(a @ x - b) < 1e-12
+    assert np.allclose(x, oracle_mldivide(a, b), rtol=1e-12, atol=1e-12)
+    s = prov.download(prov.mldivide(prov.upload(np.array([[4.0]])), prov.upload(np.array([[2.0, 6.0], [8.0, 1.0]]))))
+    assert np.array_equal(s, np.array([[2.0, 6.0], [8.0, 1.0]]) * 0.25)
+
+
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (3, 2), (64, 1), (65, 7), (130, 33), (257, 5), (1000, 64), (2048, 3)])
+def test_mldivide_vs_svd_oracle(prov, n, nrhs):
+    from svd_solve import mldivide as oracle_mldivide
+
+    rng = np.random.default_rng(n + nrhs)
+    a = rng.uniform(-1, 1, (n, n)) + np.eye(n) * 2.0
+    b = rng.uniform(-1, 1, (n, nrhs))
+    x = prov.download(prov.mldivide(prov.upload(a), prov.upload(b)))
+    want = oracle_mldivide(a, b)
+    cond = np.linalg.cond(a)
+    assert x.shape == (n, nrhs)
+    assert np.linalg.norm(a @ x - b) <= 1e-12 * n * (np.linalg.norm(a) * np.linalg.norm(x) + np.linalg.norm(b))   # backward stable
+    assert np.linalg.norm(x - want) <= 1e-13 * cond * n * np.linalg.norm(want) + 1e-300                           # agrees with the SVD solve
+
+
+def test_mldivide_pivoting_and_fallbacks(prov):
+    rng = np.random.default_rng(99)
+    n = 200
+    a = rng.uniform(-1, 1, (n, n))
+    a[np.arange(n), np.arange(n)] = 0.0           # zero diagonal: unusable without row interchanges
+    b = rng.uniform(-1, 1, (n, 4))
+    x = prov.download(prov.mldivide(prov.upload(a), prov.upload(b)))
+    assert np.linalg.norm(a @ x - b) <= 1e-10 * np.linalg.norm(b)
+    perm = np.eye(n)[rng.permutation(n)]          # a permutation matrix: every pivot needs a swap, solution is exact
+    xp = prov.download(prov.mldivide(prov.upload(perm), prov.upload(b)))
+    assert np.array_equal(xp, perm.T @ b)
+    with pytest.raises(ProviderError, match="not supported by provider"):   # singular -> host SVD fallback
+        prov.mldivide(prov.upload(np.ones((50, 50))), prov.upload(np.ones((50, 1))))
+    with pytest.raises(ProviderError, match="not supported by provider"):   # least squares -> host fallback
+        prov.mldivide(prov.upload(np.ones((6, 3))), prov.upload(np.ones((6, 1))))
+    with pytest.raises(ProviderError, match="same number of rows"):
+        prov.mldivide(prov.upload(np.eye(4)), prov.upload(np.ones((5, 1))))
+    t = prov.telemetry_snapshot()
+    assert t.mldivide.count >= 3
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # a10 / a11: RNG + Monte-Carlo evolution
 # ---------------------------------------------------------------------------------------------------------------
 def test_random_uniform_stream_is_bit_exact(prov, orc):
