@@ -185,6 +185,35 @@ def test_named_wrappers_match_generic(prov, orc):
     assert_same(prov.download(prov.scalar_add(h, 1.0)), x + 1.0)
 
 
+def test_f32_provider_surface(prov32, orc):
+    """precision F32 (what the wgpu provider defaults to, init.rs:145-172): storage and arithmetic in f32. Checked against the
+    f64 oracle evaluated on the f32-rounded inputs with the reference's f32 tolerance 5e-4*max(|x|,1) (matmul_small_k.rs:207)."""
+    rng = np.random.default_rng(21)
+    a = rng.uniform(0.1, 3, (70, 33)).astype(np.float32).astype(np.float64)
+    b = rng.uniform(0.1, 3, (70, 33)).astype(np.float32).astype(np.float64)
+    ha, hb = prov32.upload(a), prov32.upload(b)
+
+    def f32close(got, want):
+        assert np.all(np.abs(got - want) <= 5e-4 * np.maximum(np.abs(want), 1.0))
+
+    for op in ("add", "sub", "mul", "div", "pow", "max", "hypot"):
+        f32close(prov32.download(prov32.elem_binary(op, ha, hb)), orc.elem_binary(op, a, b))
+    for op in ("sin", "exp", "log", "sqrt", "tanh", "floor", "abs"):
+        f32close(prov32.download(prov32.unary(op, ha)), orc.unary(op, a))
+    f32close(prov32.download(prov32.scalar_op("rdiv", ha, 2.5)), orc.scalar_op("rdiv", a, 2.5))
+    assert abs(prov32.download(prov32.reduce_sum(ha))[0, 0] - a.sum()) <= 1e-5 * a.sum()   # f64 accumulation of f32 data
+    f32close(prov32.download(prov32.reduce_sum_dim(ha, 1)), orc.sum_dims(a, [1]))
+    f32close(prov32.download(prov32.matmul(ha, prov32.upload(np.ascontiguousarray(b.T)))), a @ b.T)
+    sh = ft.sin_mul_add_wgsl("f32")
+    h1 = prov32.upload(np.array([[1.0]]))
+    f32close(prov32.download(prov32.fused_elementwise(sh, [ha, hb, h1], (70, 33), 70 * 33)), orc.sin_mul_add(a, b, 1.0))
+    assert_same(prov32.download(prov32.transpose(ha)), a.T)   # layout ops stay exact
+    prov32.set_rng_state(0)
+    u = prov32.download(prov32.random_uniform((1000, 1)))[:, 0]
+    want, _ = orc.generate_uniform(orc.default_seed(), 1000)
+    assert np.array_equal(u, want.astype(np.float32).astype(np.float64))   # same stream, narrowed to f32
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # a3: fused elementwise (the WGSL the reference planner emits)
 # ---------------------------------------------------------------------------------------------------------------
