@@ -132,7 +132,13 @@ struct NormParams {
   double gain, bias, gamma;
 };
 
-__device__ __forceinline__ float rm_powT(float a, float b) { return powf(a, b); }
+// f32 storage: pow as WGSL defines it, exp2(y * log2(x)) with the full-precision (non-approximate) log2f/exp2f — the
+// accuracy class of the reference's own f32 shader (shaders/image_normalize.rs) at a fraction of powf's cost
+// (powf carries double-float internals; ncu r02: the normalise sweep was compute-bound on it, SM throughput 81 %).
+__device__ __forceinline__ float rm_powT(float a, float b) {
+  if (b == 0.0f) return 1.0f;
+  return exp2f(b * log2f(a));
+}
 __device__ __forceinline__ double rm_powT(double a, double b) { return pow(a, b); }
 
 // Fixed-lane variant: (gridDim*blockDim*VEC) %% B == 0, so each thread's lane l always belongs to image (b0+l): the
