@@ -277,7 +277,8 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": ew_ms * 1e3,
                 "reduction_kernel": {"kernel": "rm_fused_red (sum(sin(A).*B+1), 16 B/elem)", "achieved": BYTES_RED / (red_ms * 1e-3) / 1e9,
                                      "frac": BYTES_RED / (red_ms * 1e-3) / 1e9 / peak, "us_per_launch": red_ms * 1e3}}
-    prof = ROOT / "profiles" / "r01_traffic.json"
+    profs = sorted((ROOT / "profiles").glob("r*_traffic.json"))
+    prof = profs[-1] if profs else ROOT / "profiles" / "none"
     if prof.exists():
         try:
             roofline["traffic"] = json.loads(prof.read_text()).get("rm_fused_ew_dram_bytes_per_launch")

@@ -87,6 +87,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Grouped tile rasterisation: consecutive tile ids walk GROUP_M m-tiles before advancing n, so the ~148 tiles in flight
+// form a roughly square patch of the output and share both A row-panels and B row-panels through L2 (r02 ncu: with
+// m-fastest order the kernel re-read 32 GB of slices from DRAM per 8192^3 product).
+constexpr int GROUP_M = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int* m0, int* n0) {
+  const int per_group = GROUP_M * tiles_n;
+  const int group = tile / per_group;
+  const int first_m = group * GROUP_M;
+  const int gsz = min(tiles_m - first_m, GROUP_M);
+  const int r = tile % per_group;
+  *m0 = (first_m + r % gsz) * BM;
+  *n0 = (r / gsz) * BN;
+}
+
 struct OzEpilogue {
   double alpha, beta;
   const double* row_scale;
@@ -213,7 +227,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t it = 0;  // global k-block counter -> stage / phase
       bool ok = true;
       for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;  // m fastest: a wave shares B panels in L2
+        int m0, n0;
+        tile_coords(tile, tiles_m, tiles_n, &m0, &n0);
         for (int d = S - 1; d >= 0 && ok; --d)
           for (int s = 0; s <= d && ok; ++s) {
             const int t = d - s;
@@ -259,7 +274,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t g = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      int m0, n0;
+      tile_coords(tile, tiles_m, tiles_n, &m0, &n0);
       const uint64_t row = (uint64_t)m0 + q * 32 + lane;
       const bool row_ok = row < M;
       const int ea = row_ok ? scale_exponent(amax[row]) : 0;
