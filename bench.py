@@ -451,6 +451,19 @@ def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
         out["matmul_8192_f64_dmma"] = {"ms": ms1, "gflops": 2.0 * n ** 3 / (ms1 * 1e-3) / 1e9, "engine": "FP64 DMMA mma.sync.m8n8k4"}
         p.free(hA)
         p.free(hB)
+        # mldivide: 4096 x 4096 system, 64 right-hand sides (device LU with partial pivoting)
+        ns = 4096
+        hM = p.upload(rng.uniform(-1, 1, ns * ns) + np.eye(ns).reshape(-1) * 4.0, (ns, ns))
+        hR = p.upload(rng.uniform(-1, 1, ns * 64), (ns, 64))
+        p.free(p.mldivide(hM, hR))
+        p.synchronize()
+        t0 = time.perf_counter()
+        hX = p.mldivide(hM, hR)
+        p.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        out["mldivide_4096_x64"] = {"ms": ms, "gflops_lu": (2.0 / 3.0) * ns ** 3 / (ms * 1e-3) / 1e9}
+        for h in (hM, hR, hX):
+            p.free(h)
     return out
 
 
