@@ -167,14 +167,6 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     p = B200Provider(local_rank, device_id=rank)
-    if world > 1:
-        # share ONE stream with torch so the NCCL all-reduce is ordered with the provider's kernels
-        p_stream = torch.cuda.current_stream().cuda_stream
-        from runmat_b200._capi import lib
-        import ctypes as C
-
-        lib.rm_set_stream(p._p, C.c_void_p(p_stream))
-
     ew_shader, red_shader = ft.sin_mul_add_wgsl(), ft.sum_sin_mul_add_wgsl()
     A, B = synth_inputs(rank)
     shape = (N_SIDE, N_SIDE)
@@ -185,17 +177,20 @@ def run_ours(args):
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
-    # The per-step all-reduce (1 f64) runs on a side stream so its latency overlaps the next step's kernels: the step's
-    # sum is copied into a 2-slot persistent buffer, the comm stream waits on that copy, reduces the slot in place, and
-    # the main stream only waits for a slot's previous reduction before overwriting it (two steps later).
+    # Multi-GPU: the provider keeps its own stream; torch's current stream is the communication stream. Per step the 8-byte
+    # sum is copied (one C call, stream-ordered) into a 2-slot persistent buffer, the comm stream waits on that copy and
+    # all-reduces the slot in place, so the collective's latency overlaps the next step's kernels. A slot is reused two
+    # steps later, after the provider stream has waited for its previous reduction.
     if world > 1:
-        main_stream = torch.cuda.current_stream()
-        comm_stream = torch.cuda.Stream()
+        prov_stream = torch.cuda.ExternalStream(p.stream(), device=f"cuda:{local_rank}")
+        comm_stream = torch.cuda.current_stream()
         sum_slots = torch.zeros(2, dtype=torch.float64, device=f"cuda:{local_rank}")
+        slot_ptr = [sum_slots[i:i + 1].data_ptr() for i in range(2)]
+        slot_view = [sum_slots[i:i + 1] for i in range(2)]
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         reduced = [torch.cuda.Event(), torch.cuda.Event()]
         for e in reduced:
-            e.record(main_stream)
+            e.record(comm_stream)
     step_no = [0]
 
     def step():
@@ -204,15 +199,12 @@ def run_ours(args):
         if world > 1:
             slot = step_no[0] & 1
             step_no[0] += 1
-            ptr, n = p.device_ptr(hS)
-            t = torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}")
-            main_stream.wait_event(reduced[slot])
-            sum_slots[slot:slot + 1].copy_(t)
-            copied[slot].record(main_stream)
+            prov_stream.wait_event(reduced[slot])
+            p.copy_to_device(hS, slot_ptr[slot], 1)
+            copied[slot].record(prov_stream)
             comm_stream.wait_event(copied[slot])
-            with torch.cuda.stream(comm_stream):
-                dist.all_reduce(sum_slots[slot:slot + 1])
-                reduced[slot].record(comm_stream)
+            dist.all_reduce(slot_view[slot])
+            reduced[slot].record(comm_stream)
         return hC, hS
 
     def sync_all():
@@ -243,7 +235,7 @@ def run_ours(args):
             p.free(last_sum)
         last_sum = hS
     if world > 1:
-        main_stream.wait_stream(comm_stream)  # the timed region ends when the last all-reduce has landed
+        prov_stream.wait_stream(comm_stream)  # the timed region ends when the last all-reduce has landed
     ms = p.timer_end_ms()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
@@ -295,11 +287,12 @@ def run_ours(args):
         b = p.upload_ptr(hostB.ctypes.data, shape)
         c = p.fused_elementwise(ew_shader, [a, b, hOne], shape, ELEMS)
         s = p.fused_reduction(red_shader, [a, b], (1, 1), ELEMS, 1)
-        if world > 1:
-            ptr, n = p.device_ptr(s)
-            dist.all_reduce(torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}"))
         p.download_into_ptr(c, hostC.ctypes.data, ELEMS)   # C back to the host (synchronises)
         val = p.read_scalar(s, 0)
+        if world > 1:
+            tv = torch.tensor([val], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(tv)
+            val = float(tv.item())
         for h in (a, b, c, s):
             p.free(h)
         return val
@@ -383,8 +376,10 @@ def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
         hS = p.stochastic_evolution_sharded(hS0, drift, scale, T, lo, M)
         hP = p.payoff_partial_sum(hS, 100.0)
         if world > 1:
+            p.synchronize()
             ptr, n = p.device_ptr(hP)
             dist.all_reduce(torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}"))
+            torch.cuda.synchronize()
         ms = p.timer_end_ms()
         price = p.read_scalar(hP, 0) / M * math.exp(-0.05 * T / 252.0)
         p.free(hS)

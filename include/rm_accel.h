@@ -112,6 +112,8 @@ rm_status rm_get_stream(rm_provider* p, void** cuda_stream_out);
 rm_status rm_set_stream(rm_provider* p, void* cuda_stream);
 rm_status rm_device_ptr(rm_provider* p, const rm_handle* h, void** dptr_out, uint64_t* elems_out);
 rm_status rm_warmup(rm_provider* p);                                       /* warmup() :3010 */
+/* stream-ordered D2D copy of a tensor into caller-owned device memory (feeds the final NCCL all-reduce without a host hop) */
+rm_status rm_copy_to_device(rm_provider* p, const rm_handle* h, void* dst_device_ptr, uint64_t dst_elems);
 
 /* ---- a2: upload / download / free (lib.rs:1387-1389) -------------------------------------------- */
 rm_status rm_upload(rm_provider* p, const double* data, const uint64_t* shape, uint32_t rank,

@@ -283,6 +283,16 @@ RM_EXPORT rm_status rm_device_ptr(rm_provider* p, const rm_handle* h, void** dpt
   RM_REQUIRE(p && dptr, RM_INVALID_ARG, "rm_device_ptr: bad arguments");
   return resolve(p, h, dptr, elems);
 }
+RM_EXPORT rm_status rm_copy_to_device(rm_provider* p, const rm_handle* h, void* dst, uint64_t dst_elems) {
+  RM_REQUIRE(p && h && dst, RM_INVALID_ARG, "copy_to_device: bad arguments");
+  DeviceGuard g(p->ordinal);
+  void* src;
+  uint64_t n;
+  RM_TRY(resolve(p, h, &src, &n));
+  RM_REQUIRE(dst_elems >= n, RM_INVALID_ARG, "copy_to_device: destination holds %llu elements, tensor has %llu", (unsigned long long)dst_elems, (unsigned long long)n);
+  RM_CUDA(cudaMemcpyAsync(dst, src, n * p->elem_size(), cudaMemcpyDeviceToDevice, p->stream));
+  return RM_OK;
+}
 RM_EXPORT uint64_t rm_live_buffers(rm_provider* p) { std::lock_guard<std::mutex> lk(p->mu); return p->buffers.size(); }
 RM_EXPORT uint64_t rm_live_bytes(rm_provider* p) { return p->live_bytes.load(); }
 

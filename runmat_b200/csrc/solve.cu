@@ -104,11 +104,22 @@ lu_panel_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, i
       for (uint64_t r = (uint64_t)c + 1 + tid; r < m; r += nthr) {
         const double l = P[r + (uint64_t)c * lda] / pivot;
         P[r + (uint64_t)c * lda] = l;
-        for (int cc = c + 1; cc < jb; ++cc) {
+        int cc = c + 1;
+        if (cc < jb) {  // next column: also the pivot candidate for step c+1
           const double v = P[r + (uint64_t)cc * lda] - l * s_row[cc];
           P[r + (uint64_t)cc * lda] = v;
-          if (cc == c + 1) { const double av = fabs(v); if (av > best) { best = av; best_i = r; } }
+          const double av = fabs(v);
+          if (av > best) { best = av; best_i = r; }
+          ++cc;
         }
+        for (; cc + 7 < jb; cc += 8) {  // 8 independent loads in flight before the stores (the loop is L2-latency bound)
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = P[r + (uint64_t)(cc + u) * lda];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) P[r + (uint64_t)(cc + u) * lda] = v[u] - l * s_row[cc + u];
+        }
+        for (; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = P[r + (uint64_t)cc * lda] - l * s_row[cc];
       }
     } else {
       for (uint64_t r = (uint64_t)c + 1 + tid; r < m; r += nthr)

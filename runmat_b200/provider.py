@@ -121,6 +121,9 @@ class B200Provider:
         _check(lib.rm_device_ptr(self._p, C.byref(h), C.byref(ptr), C.byref(n)))
         return ptr.value or 0, n.value
 
+    def copy_to_device(self, h: Handle, dst_ptr: int, dst_elems: int) -> None:
+        _check(lib.rm_copy_to_device(self._p, C.byref(h), C.c_void_p(dst_ptr), C.c_uint64(dst_elems)))
+
     def warmup(self) -> None:
         _check(lib.rm_warmup(self._p))
 
