@@ -147,6 +147,8 @@ rm_status rm_scatter_linear(rm_provider* p, const rm_handle* target, const uint3
                             uint64_t n_indices, const rm_handle* values);
 rm_status rm_repmat(rm_provider* p, const rm_handle* a, const uint64_t* reps, uint32_t n_reps,
                     rm_handle* out);                                                        /* :2689 */
+/* cat (lib.rs:2686): concatenate along the 1-based dimension `dim` */
+rm_status rm_cat(rm_provider* p, uint32_t dim_one_based, const rm_handle* inputs, uint32_t n_inputs, rm_handle* out);
 
 /* ---- a5: unfused operator surface (lib.rs:1890-2357) --------------------------------------------- */
 typedef enum rm_binary_op {
@@ -163,6 +165,7 @@ typedef enum rm_unary_op {
   RM_UN_ABS, RM_UN_SIGN, RM_UN_FLOOR, RM_UN_CEIL, RM_UN_ROUND, RM_UN_FIX, RM_UN_NEG,
   RM_UN_POW2, RM_UN_HEAVISIDE, RM_UN_SINGLE, RM_UN_DOUBLE,
   RM_UN_ISNAN, RM_UN_ISINF, RM_UN_ISFINITE, RM_UN_NAN_TO_ZERO, RM_UN_NOT_NAN_MASK,
+  RM_UN_ERF, RM_UN_GAMMA, RM_UN_GAMMALN,   /* unary_erf :2101, unary_gamma :2089, unary_gammaln :2095 */
   RM_UN__COUNT
 } rm_unary_op;
 
@@ -266,6 +269,7 @@ rm_status rm_set_matmul_engine(rm_provider* p, int engine);
 /* ---- a9: mldivide core (lib.rs:2477-2489): square systems by device LU with partial pivoting; non-square,
  *      singular or badly conditioned inputs return RM_UNSUPPORTED (host SVD fallback, as with wgpu today) ---- */
 rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_handle* b, rm_handle* out);
+rm_status rm_mrdivide(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, rm_handle* out); /* lhs / rhs, lib.rs:2484 */
 
 /* ---- a10/a11: Monte-Carlo evolution + RNG (lib.rs:1713-1775) -------------------------------------- */
 rm_status rm_set_rng_state(rm_provider* p, uint64_t state);                                     /* :1772 */
@@ -306,6 +310,10 @@ typedef struct rm_imfilter_options {
 } rm_imfilter_options;
 rm_status rm_imfilter(rm_provider* p, const rm_handle* image, const rm_handle* kernel,
                       const rm_imfilter_options* opt, rm_handle* out);
+/* conv2d (lib.rs:2543): ProviderConvMode Full=0 / Same=1 / Valid=2; full convolution then MATLAB conv2 slicing
+ * (simple_provider.rs:1845-1956, 6065-6155) */
+typedef enum rm_conv_mode { RM_CONV_FULL = 0, RM_CONV_SAME = 1, RM_CONV_VALID = 2 } rm_conv_mode;
+rm_status rm_conv2d(rm_provider* p, const rm_handle* signal, const rm_handle* kernel, rm_conv_mode mode, rm_handle* out);
 
 /* ---- a15: telemetry / tuning hints (lib.rs:3010-3060) -------------------------------------------- */
 rm_status rm_telemetry_snapshot(rm_provider* p, rm_telemetry* out);

@@ -154,7 +154,7 @@ double apply_binary(int op, double a, double b) {
 enum UnOp { U_SIN, U_COS, U_TAN, U_ASIN, U_ACOS, U_ATAN, U_SINH, U_COSH, U_TANH, U_ASINH, U_ACOSH,
             U_ATANH, U_EXP, U_EXPM1, U_LOG, U_LOG2, U_LOG10, U_LOG1P, U_SQRT, U_ABS, U_SIGN, U_FLOOR,
             U_CEIL, U_ROUND, U_FIX, U_NEG, U_POW2, U_HEAVISIDE, U_SINGLE, U_DOUBLE, U_ISNAN, U_ISINF,
-            U_ISFINITE, U_NAN_TO_ZERO, U_NOT_NAN_MASK };
+            U_ISFINITE, U_NAN_TO_ZERO, U_NOT_NAN_MASK, U_ERF, U_GAMMA, U_GAMMALN };
 
 double apply_unary(int op, double x) {
   switch (op) {
@@ -193,6 +193,9 @@ double apply_unary(int op, double x) {
     case U_ISFINITE: return std::isfinite(x) ? 1.0 : 0.0;
     case U_NAN_TO_ZERO: return std::isnan(x) ? 0.0 : x;     // accelerate-api lib.rs:2980
     case U_NOT_NAN_MASK: return std::isnan(x) ? 0.0 : 1.0;  // lib.rs:2985
+    case U_ERF: return std::erf(x);       // simple_provider.rs:134-136 (libm crate 0.2.16 erf; glibc erf agrees to <= 1 ulp)
+    case U_GAMMA: return std::tgamma(x);
+    case U_GAMMALN: return std::lgamma(x);
   }
   return NAN;
 }
@@ -504,6 +507,32 @@ ORC_API int orc_imfilter(const double* img, const uint64_t* ishape, int irank, c
         out[oi] = sum;
       }
   return rank;
+}
+
+// conv2d: simple_provider.rs:1845-1876 (conv2d_full_real: scatter over the signal in column-major order, zero
+// signal entries skipped, kernel rotated 180 deg) + :1908-1956 (apply_conv2_mode_real_2d). mode: 0 full, 1 same, 2 valid.
+ORC_API void orc_conv2d(const double* sig, uint64_t sr, uint64_t sc, const double* ker, uint64_t kr, uint64_t kc, int mode, double* out, uint64_t* out_dims) {
+  const uint64_t fr = sr + kr - 1, fc = sc + kc - 1;
+  uint64_t r0 = 0, c0 = 0, orows = fr, ocols = fc;
+  if (mode == 1) { r0 = (kr - 1) / 2; c0 = (kc - 1) / 2; orows = sr; ocols = sc; }
+  else if (mode == 2) { if (sr < kr || sc < kc) { orows = ocols = 0; } else { r0 = kr - 1; c0 = kc - 1; orows = sr - kr + 1; ocols = sc - kc + 1; } }
+  out_dims[0] = orows; out_dims[1] = ocols;
+  if (!out) return;
+  std::vector<double> full(fr * fc, 0.0);
+  for (uint64_t c = 0; c < sc; ++c)
+    for (uint64_t r = 0; r < sr; ++r) {
+      const double aval = sig[c * sr + r];
+      if (aval == 0.0) continue;
+      for (uint64_t j = 0; j < kc; ++j) {
+        const uint64_t oc = c + j, kcol = kc - 1 - j;
+        for (uint64_t i = 0; i < kr; ++i) {
+          const uint64_t orr = r + i, krow = kr - 1 - i;
+          full[oc * fr + orr] += aval * ker[kcol * kr + krow];
+        }
+      }
+    }
+  for (uint64_t c = 0; c < ocols; ++c)
+    for (uint64_t r = 0; r < orows; ++r) out[c * orows + r] = full[(c0 + c) * fr + r0 + r];
 }
 
 // ---- RNG: common/random.rs ---------------------------------------------------------------------------------

@@ -94,7 +94,7 @@ BINARY_OPS = ["add", "sub", "mul", "div", "pow", "max", "min", "hypot", "atan2",
 UNARY_OPS = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh",
              "exp", "expm1", "log", "log2", "log10", "log1p", "sqrt", "abs", "sign", "floor", "ceil", "round",
              "fix", "neg", "pow2", "heaviside", "single", "double", "isnan", "isinf", "isfinite",
-             "nan_to_zero", "not_nan_mask"]
+             "nan_to_zero", "not_nan_mask", "erf", "gamma", "gammaln"]
 SCALAR_OPS = ["add", "sub", "mul", "div", "rsub", "rdiv", "max", "min", "pow"]
 
 lib.rm_last_error.restype = C.c_char_p

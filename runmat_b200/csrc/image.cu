@@ -426,6 +426,23 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   return RM_OK;
 }
 
+// Launches the tiled (2-D kernel) or generic (N-D kernel) filter kernel for a prepared FilterParams.
+static void launch_filter(rm_provider* p, const void* pi, const void* pk, void* po, uint64_t total, const FilterParams& fp) {
+  const bool tiled = fp.ke[2] == 1 && fp.ke[0] <= IMF_MAXK && fp.ke[1] <= IMF_MAXK && fp.oe[2] <= 65535 && (fp.oe[1] + IMF_TY - 1) / IMF_TY <= 65535 &&
+                     fp.ie[0] < (1ull << 31) && fp.ie[1] < (1ull << 31);
+  if (tiled) {
+    const int SX = IMF_TX + (int)fp.ke[0] - 1, SY = IMF_TY + (int)fp.ke[1] - 1;
+    const size_t sh = (size_t)(SX * SY + (int)(fp.ke[0] * fp.ke[1])) * p->elem_size() + (size_t)(SX + SY) * sizeof(int) + 16;
+    dim3 grid((unsigned)((fp.oe[0] + IMF_TX - 1) / IMF_TX), (unsigned)((fp.oe[1] + IMF_TY - 1) / IMF_TY), (unsigned)fp.oe[2]);
+    if (p->precision == RM_F64) imfilter_tiled_kernel<double><<<grid, 256, sh, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, fp);
+    else imfilter_tiled_kernel<float><<<grid, 256, sh, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, fp);
+  } else {
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 32);
+    if (p->precision == RM_F64) imfilter_kernel<double><<<grid, 256, 0, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, total, fp);
+    else imfilter_kernel<float><<<grid, 256, 0, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, total, fp);
+  }
+}
+
 RM_EXPORT rm_status rm_imfilter(rm_provider* p, const rm_handle* image, const rm_handle* kernel, const rm_imfilter_options* opt, rm_handle* out) {
   RM_REQUIRE(p && image && kernel && opt && out, RM_INVALID_ARG, "imfilter: bad arguments");
   DeviceGuard g(p->ordinal);
@@ -459,21 +476,51 @@ RM_EXPORT rm_status rm_imfilter(rm_provider* p, const rm_handle* image, const rm
   RM_TRY(alloc_tensor(p, oshape, orank, out, &po));
   const uint64_t total = fp.oe[0] * fp.oe[1] * fp.oe[2];
   if (total == 0) return RM_OK;
-  const bool tiled = fp.ke[2] == 1 && fp.ke[0] <= IMF_MAXK && fp.ke[1] <= IMF_MAXK && fp.oe[2] <= 65535 && (fp.oe[1] + IMF_TY - 1) / IMF_TY <= 65535 &&
-                     fp.ie[0] < (1ull << 31) && fp.ie[1] < (1ull << 31);
-  if (tiled) {
-    const int SX = IMF_TX + (int)fp.ke[0] - 1, SY = IMF_TY + (int)fp.ke[1] - 1;
-    const size_t sh = (size_t)(SX * SY + (int)(fp.ke[0] * fp.ke[1])) * p->elem_size() + (size_t)(SX + SY) * sizeof(int) + 16;
-    dim3 grid((unsigned)((fp.oe[0] + IMF_TX - 1) / IMF_TX), (unsigned)((fp.oe[1] + IMF_TY - 1) / IMF_TY), (unsigned)fp.oe[2]);
-    if (p->precision == RM_F64) imfilter_tiled_kernel<double><<<grid, 256, sh, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, fp);
-    else imfilter_tiled_kernel<float><<<grid, 256, sh, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, fp);
-  } else {
-    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 32);
-    if (p->precision == RM_F64) imfilter_kernel<double><<<grid, 256, 0, p->stream>>>((const double*)pi, (const double*)pk, (double*)po, total, fp);
-    else imfilter_kernel<float><<<grid, 256, 0, p->stream>>>((const float*)pi, (const float*)pk, (float*)po, total, fp);
-  }
+  launch_filter(p, pi, pk, po, total, fp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "imfilter launch failed: %s", cudaGetErrorString(e)); }
+  count_launch(p);
+  return RM_OK;
+}
+
+RM_EXPORT rm_status rm_conv2d(rm_provider* p, const rm_handle* signal, const rm_handle* kernel, rm_conv_mode mode, rm_handle* out) {
+  RM_REQUIRE(p && signal && kernel && out, RM_INVALID_ARG, "conv2d: bad arguments");
+  RM_REQUIRE(signal->rank <= 2 && kernel->rank <= 2, RM_ERROR, "conv2d: inputs must be 2-D matrices");
+  DeviceGuard g(p->ordinal);
+  void *pi, *pk;
+  uint64_t ni, nk;
+  RM_TRY(resolve(p, signal, &pi, &ni));
+  RM_TRY(resolve(p, kernel, &pk, &nk));
+  const uint64_t sr = signal->rank >= 1 ? signal->shape[0] : 1, sc = signal->rank >= 2 ? signal->shape[1] : 1;
+  const uint64_t kr = kernel->rank >= 1 ? kernel->shape[0] : 1, kc = kernel->rank >= 2 ? kernel->shape[1] : 1;
+  if (ni == 0 || nk == 0) {  // simple_provider.rs:6079-6093
+    uint64_t es[2] = {mode == RM_CONV_SAME ? sr : 0, mode == RM_CONV_SAME ? sc : 0};
+    return rm_zeros(p, es, 2, out);
+  }
+  // out(o) = sum_k flipped_ker(k) * sig(o + start - (K-1) + k), zero outside: the host's full convolution followed by its
+  // MATLAB conv2 slicing (simple_provider.rs:1908-1956); the tap order equals the host's scatter order (signal index ascending).
+  FilterParams fp{};
+  const uint64_t se[2] = {sr, sc}, ke[2] = {kr, kc};
+  for (int d = 0; d < 3; ++d) { fp.ie[d] = d < 2 ? se[d] : 1; fp.ke[d] = d < 2 ? ke[d] : 1; fp.oe[d] = 1; fp.origin[d] = 0; fp.base[d] = 0; }
+  for (int d = 0; d < 2; ++d) {
+    int64_t start = 0;
+    if (mode == RM_CONV_FULL) fp.oe[d] = se[d] + ke[d] - 1;
+    else if (mode == RM_CONV_SAME) { fp.oe[d] = se[d]; start = (int64_t)((ke[d] - 1) / 2); }
+    else { fp.oe[d] = se[d] >= ke[d] ? se[d] - ke[d] + 1 : 0; start = (int64_t)ke[d] - 1; }
+    fp.base[d] = start - ((int64_t)ke[d] - 1);
+  }
+  if (mode == RM_CONV_VALID && (fp.oe[0] == 0 || fp.oe[1] == 0)) { uint64_t es[2] = {0, 0}; return rm_zeros(p, es, 2, out); }
+  fp.padding = 0;
+  fp.mode = 1;
+  fp.cval = 0.0;
+  uint64_t oshape[2] = {fp.oe[0], fp.oe[1]};
+  void* po;
+  RM_TRY(alloc_tensor(p, oshape, 2, out, &po));
+  const uint64_t total = fp.oe[0] * fp.oe[1];
+  if (total == 0) return RM_OK;
+  launch_filter(p, pi, pk, po, total, fp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "conv2d launch failed: %s", cudaGetErrorString(e)); }
   count_launch(p);
   return RM_OK;
 }

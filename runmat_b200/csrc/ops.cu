@@ -75,6 +75,9 @@ const char* unary_expr(rm_unary_op op) {
     case RM_UN_ISFINITE: return "(rm_isfinite(v0) ? (T)1 : (T)0)";
     case RM_UN_NAN_TO_ZERO: return "(rm_isnan(v0) ? (T)0 : v0)";
     case RM_UN_NOT_NAN_MASK: return "(rm_isnan(v0) ? (T)0 : (T)1)";
+    case RM_UN_ERF: return "erf(v0)";
+    case RM_UN_GAMMA: return "tgamma(v0)";
+    case RM_UN_GAMMALN: return "lgamma(v0)";
     default: return nullptr;
   }
 }

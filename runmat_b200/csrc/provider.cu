@@ -541,6 +541,44 @@ RM_EXPORT rm_status rm_repmat(rm_provider* p, const rm_handle* a, const uint64_t
   return gather_nd(p, src, gd, oshape, rank, out);
 }
 
+RM_EXPORT rm_status rm_cat(rm_provider* p, uint32_t dim_one_based, const rm_handle* inputs, uint32_t n_inputs, rm_handle* out) {
+  RM_REQUIRE(p && inputs && out && n_inputs > 0, RM_INVALID_ARG, "cat: bad arguments");
+  RM_REQUIRE(dim_one_based >= 1 && dim_one_based <= RM_MAX_RANK, RM_ERROR, "cat: dimension must be >= 1");
+  DeviceGuard g(p->ordinal);
+  const uint32_t d = dim_one_based - 1;
+  uint32_t rank = std::max<uint32_t>(d + 1, 2);
+  for (uint32_t i = 0; i < n_inputs; ++i) rank = std::max(rank, inputs[i].rank);
+  auto ext = [&](const rm_handle& h, uint32_t k) -> uint64_t { return k < h.rank ? h.shape[k] : 1; };
+  uint64_t oshape[RM_MAX_RANK], along = 0;
+  for (uint32_t k = 0; k < rank; ++k) oshape[k] = ext(inputs[0], k);
+  for (uint32_t i = 0; i < n_inputs; ++i) {
+    for (uint32_t k = 0; k < rank; ++k)
+      RM_REQUIRE(k == d || ext(inputs[i], k) == oshape[k], RM_ERROR, "cat: dimension mismatch on input %u (dim %u: %llu vs %llu)", i + 1, k + 1,
+                 (unsigned long long)ext(inputs[i], k), (unsigned long long)oshape[k]);
+    along += ext(inputs[i], d);
+  }
+  oshape[d] = along;
+  void* dst;
+  RM_TRY(alloc_tensor(p, oshape, rank, out, &dst));
+  uint64_t pre = 1, post = 1;
+  for (uint32_t k = 0; k < d; ++k) pre *= oshape[k];
+  for (uint32_t k = d + 1; k < rank; ++k) post *= oshape[k];
+  const size_t es = p->elem_size();
+  uint64_t off = 0;
+  for (uint32_t i = 0; i < n_inputs; ++i) {
+    void* src;
+    rm_status st = resolve(p, &inputs[i], &src, nullptr);
+    if (st != RM_OK) { std::string m = last_error(); rm_free(p, out); set_error("%s", m.c_str()); return st; }
+    const uint64_t ni = ext(inputs[i], d);
+    if (pre * ni * post == 0) continue;
+    // each input is `post` slabs of pre*ni contiguous elements; in the output the slabs are pre*along apart
+    cudaError_t e = cudaMemcpy2DAsync((char*)dst + off * pre * es, pre * along * es, src, pre * ni * es, pre * ni * es, post, cudaMemcpyDeviceToDevice, p->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); rm_free(p, out); return fail(RM_ERROR, "cat: copy failed: %s", cudaGetErrorString(e)); }
+    off += ni;
+  }
+  return RM_OK;
+}
+
 static rm_status upload_indices(rm_provider* p, const uint32_t* idx, uint64_t n, uint64_t bound, const char* what, uint32_t** dptr) {
   for (uint64_t i = 0; i < n; ++i)  // bounds are checked on the host, as the reference does (simple_provider.rs:2636-2646)
     RM_REQUIRE(idx[i] < bound, RM_INVALID_ARG, "%s: index %u (position %llu) out of bounds (logical_len=%llu)", what, idx[i], (unsigned long long)i, (unsigned long long)bound);

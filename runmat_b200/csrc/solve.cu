@@ -327,3 +327,32 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
 #undef SV_TRY
   return RM_OK;
 }
+
+// mrdivide (lib.rs:2484): lhs / rhs = (rhs' \ lhs')'
+RM_EXPORT rm_status rm_mrdivide(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, rm_handle* out) {
+  RM_REQUIRE(p && lhs && rhs && out, RM_INVALID_ARG, "mrdivide: bad arguments");
+  RM_REQUIRE(lhs->rank == 2 && rhs->rank == 2, RM_ERROR, "mrdivide: inputs must be 2-D matrices");
+  DeviceGuard g(p->ordinal);
+  ScopedWall wall(p->t_mrdivide);
+  if (rhs->shape[0] == 1 && rhs->shape[1] == 1) {
+    double rv;
+    RM_TRY(rm_read_scalar(p, rhs, 0, &rv));
+    return rm_scalar_op_apply(p, RM_SC_MUL, lhs, 1.0 / rv, out);
+  }
+  RM_REQUIRE(lhs->shape[1] == rhs->shape[1], RM_ERROR, "mrdivide: left and right operands must have the same number of columns (%llu vs %llu)",
+             (unsigned long long)lhs->shape[1], (unsigned long long)rhs->shape[1]);
+  rm_handle lt, rt, xt;
+  RM_TRY(rm_transpose(p, lhs, &lt));
+  rm_status st = rm_transpose(p, rhs, &rt);
+  if (st != RM_OK) { std::string m = last_error(); rm_free(p, &lt); set_error("%s", m.c_str()); return st; }
+  st = rm_mldivide(p, &rt, &lt, &xt);
+  std::string msg = st == RM_OK ? "" : last_error();
+  rm_free(p, &lt);
+  rm_free(p, &rt);
+  if (st != RM_OK) { set_error("%s", msg.c_str()); return st; }
+  st = rm_transpose(p, &xt, out);
+  msg = st == RM_OK ? "" : last_error();
+  rm_free(p, &xt);
+  if (st != RM_OK) set_error("%s", msg.c_str());
+  return st;
+}

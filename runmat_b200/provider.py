@@ -366,6 +366,19 @@ class B200Provider:
     def syrk(self, a): return self._named1(lib.rm_syrk, a)
     def mldivide(self, a, b): return self._named2(lib.rm_mldivide, a, b)
 
+    def mrdivide(self, lhs, rhs): return self._named2(lib.rm_mrdivide, lhs, rhs)
+
+    def conv2d(self, signal: Handle, kernel: Handle, mode: str = "full") -> Handle:
+        h = Handle()
+        _check(lib.rm_conv2d(self._p, C.byref(signal), C.byref(kernel), ["full", "same", "valid"].index(mode), C.byref(h)))
+        return h
+
+    def cat(self, dim_one_based: int, inputs: Sequence[Handle]) -> Handle:
+        arr = (Handle * len(inputs))(*inputs)
+        h = Handle()
+        _check(lib.rm_cat(self._p, C.c_uint32(dim_one_based), arr, len(inputs), C.byref(h)))
+        return h
+
     def set_matmul_engine(self, engine: int) -> None:
         _check(lib.rm_set_matmul_engine(self._p, int(engine)))
 

@@ -12,7 +12,7 @@ LIB = ROOT / "oracle" / "librm_oracle.so"
 BINARY_OPS = ["add", "sub", "mul", "div", "pow", "max", "min", "hypot", "atan2", "mod", "rem", "ge", "le", "lt", "gt", "eq", "ne"]
 UNARY_OPS = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "expm1", "log",
              "log2", "log10", "log1p", "sqrt", "abs", "sign", "floor", "ceil", "round", "fix", "neg", "pow2", "heaviside", "single",
-             "double", "isnan", "isinf", "isfinite", "nan_to_zero", "not_nan_mask"]
+             "double", "isnan", "isinf", "isfinite", "nan_to_zero", "not_nan_mask", "erf", "gamma", "gammaln"]
 SCALAR_OPS = ["add", "sub", "mul", "div", "rsub", "rdiv", "max", "min", "pow"]
 
 _d = C.POINTER(C.c_double)
@@ -193,6 +193,16 @@ class Oracle:
         d = f64(data).copy()
         new = self.lib.orc_stochastic_evolution(C.c_uint64(rng_state), _dp(d), C.c_uint64(d.size), C.c_double(drift), C.c_double(scale), C.c_uint32(steps))
         return d.reshape(np.asarray(data).shape, order="F"), new
+
+    def conv2d(self, sig, ker, mode):
+        sig, ker = np.asarray(sig, dtype=np.float64), np.asarray(ker, dtype=np.float64)
+        m = ["full", "same", "valid"].index(mode)
+        dims = (C.c_uint64 * 2)()
+        fs, fk = f64(sig), f64(ker)
+        self.lib.orc_conv2d(_dp(fs), C.c_uint64(sig.shape[0]), C.c_uint64(sig.shape[1]), _dp(fk), C.c_uint64(ker.shape[0]), C.c_uint64(ker.shape[1]), m, None, dims)
+        out = np.empty(int(dims[0] * dims[1]))
+        self.lib.orc_conv2d(_dp(fs), C.c_uint64(sig.shape[0]), C.c_uint64(sig.shape[1]), _dp(fk), C.c_uint64(ker.shape[0]), C.c_uint64(ker.shape[1]), m, _dp(out), dims)
+        return out.reshape((dims[0], dims[1]), order="F")
 
     def linspace(self, start, stop, count):
         out = np.empty(count)

@@ -22,7 +22,7 @@ EXACT_BIN = ["add", "sub", "mul", "div", "max", "min", "mod", "rem", "ge", "le",
 LIBM_BIN = ["pow", "hypot", "atan2"]
 EXACT_UN = ["sqrt", "abs", "sign", "floor", "ceil", "round", "fix", "neg", "heaviside", "single", "double", "isnan", "isinf", "isfinite",
             "nan_to_zero", "not_nan_mask"]
-LIBM_UN = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "expm1", "log", "log2",
+LIBM_UN = ["erf", "gamma", "gammaln", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "expm1", "log", "log2",
            "log10", "log1p", "pow2"]
 
 
@@ -153,6 +153,8 @@ def test_unary(prov, orc, op):
         x = np.abs(x) + 1.0
     if op == "log1p":
         x = np.abs(x)
+    if op in ("gamma", "gammaln"):
+        x = np.abs(x) + 0.1
     x.flat[: special_values().size] = special_values() if op in EXACT_UN else x.flat[: special_values().size]
     h = prov.upload(x)
     hr = prov.unary(op, h)
@@ -837,6 +839,36 @@ def test_imfilter_kats_and_modes(prov, orc):
     big = rng.uniform(0, 1, (300, 200))
     got = prov.download(prov.imfilter(prov.upload(big), hk, padding="replicate"))
     assert_same(got, orc.imfilter(big, ker, padding="replicate"))
+
+
+def test_conv2d_matches_host_order(prov, orc):
+    rng = np.random.default_rng(23)
+    for sshape, kshape in [((7, 9), (3, 3)), ((40, 33), (5, 4)), ((2, 2), (3, 5)), ((130, 70), (1, 7)), ((64, 64), (2, 2))]:
+        sig, ker = rng.uniform(-1, 1, sshape), rng.uniform(-1, 1, kshape)
+        sig[sig > 0.8] = 0.0  # the host skips zero signal entries
+        for mode in ("full", "same", "valid"):
+            got = prov.download(prov.conv2d(prov.upload(sig), prov.upload(ker), mode))
+            want = orc.conv2d(sig, ker, mode)
+            assert got.shape == want.shape, (sshape, kshape, mode)
+            assert_same(got, want)  # same tap order as the host's scatter loop: bit-exact
+
+
+def test_cat_and_mrdivide(prov):
+    rng = np.random.default_rng(24)
+    a, b, c = rng.uniform(-1, 1, (3, 4)), rng.uniform(-1, 1, (2, 4)), rng.uniform(-1, 1, (3, 5))
+    ha, hb, hc = prov.upload(a), prov.upload(b), prov.upload(c)
+    assert np.array_equal(prov.download(prov.cat(1, [ha, hb, ha])), np.concatenate([a, b, a], axis=0))
+    assert np.array_equal(prov.download(prov.cat(2, [ha, hc])), np.concatenate([a, c], axis=1))
+    assert np.array_equal(prov.download(prov.cat(3, [ha, ha])), np.stack([a, a], axis=2))
+    t = rng.uniform(-1, 1, (2, 3, 4))
+    assert np.array_equal(prov.download(prov.cat(2, [prov.upload(t), prov.upload(t[:, :1, :])])), np.concatenate([t, t[:, :1, :]], axis=1))
+    with pytest.raises(ProviderError, match="dimension mismatch"):
+        prov.cat(1, [ha, hc])
+    n = 150
+    A = rng.uniform(-1, 1, (n, n)) + 3 * np.eye(n)
+    Bm = rng.uniform(-1, 1, (7, n))
+    X = prov.download(prov.mrdivide(prov.upload(Bm), prov.upload(A)))   # X = Bm / A
+    assert X.shape == (7, n) and np.linalg.norm(X @ A - Bm) <= 1e-11 * np.linalg.norm(Bm) * n
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -158,3 +158,19 @@ def test_image_normalize_matches_test_restatement(orc):
     sig = np.sqrt(((x - mu) ** 2).mean(axis=(1, 2), keepdims=True) + 1e-6)
     want = np.maximum((x - mu) / sig * 1.0123 - 0.02, 0.0) ** 1.8
     assert_same(got, want, tol=1e-12)
+
+
+def test_conv2d_oracle_matches_scipy(orc):
+    # simple_provider.rs:1845-1956 restated; cross-checked against scipy's direct convolution (same maths, any order)
+    from scipy.signal import convolve2d
+
+    rng = np.random.default_rng(5)
+    for sshape, kshape in [((5, 6), (3, 3)), ((4, 4), (2, 5)), ((2, 2), (3, 3))]:
+        sig, ker = rng.uniform(-1, 1, sshape), rng.uniform(-1, 1, kshape)
+        for mode in ("full", "same", "valid"):
+            want = convolve2d(sig, ker, mode=mode)
+            got = orc.conv2d(sig, ker, mode)
+            if mode == "valid" and (sshape[0] < kshape[0] or sshape[1] < kshape[1]):
+                assert got.size == 0  # host returns an empty 0x0 (simple_provider.rs:1937-1938)
+                continue
+            assert got.shape == want.shape and np.allclose(got, want, rtol=1e-13, atol=1e-13)
