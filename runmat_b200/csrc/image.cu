@@ -497,8 +497,10 @@ RM_EXPORT rm_status rm_conv2d(rm_provider* p, const rm_handle* signal, const rm_
     uint64_t es[2] = {mode == RM_CONV_SAME ? sr : 0, mode == RM_CONV_SAME ? sc : 0};
     return rm_zeros(p, es, 2, out);
   }
-  // out(o) = sum_k flipped_ker(k) * sig(o + start - (K-1) + k), zero outside: the host's full convolution followed by its
-  // MATLAB conv2 slicing (simple_provider.rs:1908-1956); the tap order equals the host's scatter order (signal index ascending).
+  // The host scatters out[r+i, c+j] += a[r,c] * ker[K-1-i, K-1-j] (conv2.rs:603-617 == simple_provider.rs:1856-1873). In
+  // gather form that is out(o) = sum_u ker(u) * sig(o + start - (K-1) + u) with the kernel as stored, zero outside, then
+  // the conv2 slicing (simple_provider.rs:1908-1956). The reference's KATs pin exactly this (conv2.rs:736-978). Visiting u
+  // in column-major order equals the host's accumulation order (signal index ascending), so the result is bit-identical.
   FilterParams fp{};
   const uint64_t se[2] = {sr, sc}, ke[2] = {kr, kc};
   for (int d = 0; d < 3; ++d) { fp.ie[d] = d < 2 ? se[d] : 1; fp.ke[d] = d < 2 ? ke[d] : 1; fp.oe[d] = 1; fp.origin[d] = 0; fp.base[d] = 0; }
@@ -511,7 +513,7 @@ RM_EXPORT rm_status rm_conv2d(rm_provider* p, const rm_handle* signal, const rm_
   }
   if (mode == RM_CONV_VALID && (fp.oe[0] == 0 || fp.oe[1] == 0)) { uint64_t es[2] = {0, 0}; return rm_zeros(p, es, 2, out); }
   fp.padding = 0;
-  fp.mode = 1;
+  fp.mode = 0;
   fp.cval = 0.0;
   uint64_t oshape[2] = {fp.oe[0], fp.oe[1]};
   void* po;

@@ -160,17 +160,16 @@ def test_image_normalize_matches_test_restatement(orc):
     assert_same(got, want, tol=1e-12)
 
 
-def test_conv2d_oracle_matches_scipy(orc):
-    # simple_provider.rs:1845-1956 restated; cross-checked against scipy's direct convolution (same maths, any order)
-    from scipy.signal import convolve2d
-
-    rng = np.random.default_rng(5)
-    for sshape, kshape in [((5, 6), (3, 3)), ((4, 4), (2, 5)), ((2, 2), (3, 3))]:
-        sig, ker = rng.uniform(-1, 1, sshape), rng.uniform(-1, 1, kshape)
-        for mode in ("full", "same", "valid"):
-            want = convolve2d(sig, ker, mode=mode)
-            got = orc.conv2d(sig, ker, mode)
-            if mode == "valid" and (sshape[0] < kshape[0] or sshape[1] < kshape[1]):
-                assert got.size == 0  # host returns an empty 0x0 (simple_provider.rs:1937-1938)
-                continue
-            assert got.shape == want.shape and np.allclose(got, want, rtol=1e-13, atol=1e-13)
+def test_conv2d_reference_kats(orc):
+    """Literal expectations of the reference's conv2 unit tests (runmat-runtime/src/builtins/math/signal/conv2.rs:736-978;
+    `tensor_from_rows` there takes row-major literals). They pin the reference's kernel orientation and 'same' alignment."""
+    rows = lambda r, c, d: np.array(d, dtype=np.float64).reshape(r, c)  # noqa: E731
+    a22, ones22 = rows(2, 2, [1, 2, 3, 4]), rows(2, 2, [1, 1, 1, 1])
+    assert_same(orc.conv2d(a22, ones22, "full"), rows(3, 3, [1, 3, 2, 4, 10, 6, 3, 7, 4]))                       # :736 conv2_full_basic
+    a33 = rows(3, 3, [1, 2, 3, 4, 5, 6, 7, 8, 9])
+    assert_same(orc.conv2d(a33, np.ones((3, 3)), "same"), rows(3, 3, [12, 21, 16, 27, 45, 33, 24, 39, 28]))     # :753 conv2_same_matches_reference
+    assert_same(orc.conv2d(a33, rows(3, 3, [1, 0, -1, 1, 0, -1, 1, 0, -1]), "same"),
+                rows(3, 3, [-7, -4, 7, -15, -6, 15, -13, -4, 13]))                                              # :778 conv2_same_flips_kernel
+    assert_same(orc.conv2d(a33, np.ones((3, 3)), "valid"), np.array([[45.0]]))                                  # :803 conv2_valid_returns_expected_sum
+    assert_same(orc.conv2d(a33, rows(2, 2, [1, 2, 3, 4]), "same"), rows(3, 3, [4, 11, 18, 18, 37, 47, 36, 67, 77]))  # :948 even kernel alignment
+    assert orc.conv2d(np.ones((2, 2)), np.ones((3, 3)), "valid").size == 0
