@@ -410,6 +410,14 @@ def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
             px = Bi * H * W
             out["image_normalize_8x4k_f32"] = {"ms": ms, "gb_per_s_at_12B_per_px": 12 * px / (ms * 1e-3) / 1e9,
                                                "gb_per_s_at_8B_per_px_algorithmic": 8 * px / (ms * 1e-3) / 1e9}
+            for _ in range(2):
+                p32.free(p32.reduce_mean_nd(hI, [1, 2]))
+            p32.synchronize()
+            p32.timer_begin()
+            for _ in range(5):
+                p32.free(p32.reduce_mean_nd(hI, [1, 2]))
+            ms = p32.timer_end_ms() / 5
+            out["mean_dims23_8x4k_f32"] = {"ms": ms, "gb_per_s": 4 * px / (ms * 1e-3) / 1e9, "kernel": "rm_fused_red (Strided layout, 8 slices)"}
             p32.free(hI)
             frame = np.random.default_rng(4).random(H * W * 3, dtype=np.float32)
             g = np.exp(-((np.arange(5) - 2)[:, None] ** 2 + (np.arange(5) - 2)[None, :] ** 2) / 2.0)

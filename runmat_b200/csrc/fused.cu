@@ -79,7 +79,7 @@ std::string cache_dir() {
 }
 
 const char* kNvrtcOpts[] = {"--gpu-architecture=sm_100a", "-fmad=false", "-lineinfo", "--std=c++17"};
-const char* kOptsTag = "sm_100a|-fmad=false|v3";
+const char* kOptsTag = "sm_100a|-fmad=false|v4";
 
 }  // namespace
 
@@ -345,7 +345,7 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
     dim3 grid, block;
     uint64_t partial_elems = 0;
     int vec_ok = 0;
-    unsigned bps = 1;
+    unsigned bps = 1, sl = 1;
     if (layout == RedLayout::Contig) {
       vec_ok = (reduce_len % vec == 0 || num_slices == 1) ? 1 : 0;
       uint64_t threads = 256;
@@ -362,10 +362,14 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       block = dim3((unsigned)threads);
       partial_elems = bps > 1 ? (uint64_t)bps * num_slices : 0;
     } else {
-      const uint64_t gx = (num_slices + 255) / 256;
+      // sl adjacent slices per CTA (power of two), 256/sl row lanes; split rows over gridDim.y until the SMs are full
+      while (sl < 256 && sl < num_slices) sl <<= 1;
+      const uint64_t rl = 256 / sl;
+      const uint64_t gx = (num_slices + sl - 1) / sl;
       uint64_t chunks = 1;
-      if (num_slices < sms * 2048 && gx <= FusedCache::kTicketCap)
-        chunks = std::min<uint64_t>(std::min<uint64_t>((sms * 2048 + num_slices - 1) / num_slices, 65535), std::max<uint64_t>(1, reduce_len / 8));
+      if (gx < sms * 8 && gx <= FusedCache::kTicketCap)
+        chunks = std::min<uint64_t>(std::min<uint64_t>((sms * 8 + gx - 1) / gx, 65535), std::max<uint64_t>(1, reduce_len / (rl * 8)));
+      RM_REQUIRE(gx < (1ull << 31), RM_UNSUPPORTED, "fused_reduction: too many slices");
       grid = dim3((unsigned)gx, (unsigned)chunks);
       block = dim3(256);
       partial_elems = chunks > 1 ? chunks * num_slices : 0;
@@ -389,6 +393,7 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       args.push_back(&factor);
       args.push_back(&bps);
       args.push_back(&inner_arg);
+      args.push_back(&sl);
       st = launch(p, kern, grid, block, args.data());
     }
   }

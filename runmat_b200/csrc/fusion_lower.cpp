@@ -461,7 +461,7 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     else o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(";
     o << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
-         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner) {\n";
+         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl) {\n";
     o << "  __shared__ double smem[32];\n  __shared__ bool is_last;\n";
     o << "  const u64 slice = blockIdx.x / bps;\n  const u32 bidx = blockIdx.x % bps;\n  const u64 base = slice * len;\n";
     o << "  const u64 nvec = vec_ok ? len / VEC : 0;\n";
@@ -516,33 +516,53 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
 }
 )CUDA";
   } else {
-    // element r of slice s lives at s + r*num_slices (row reductions of a column-major matrix):
-    // one thread per slice keeps the warp's accesses contiguous; grid = (ceil(slices/256), chunks).
+    // Strided layout: element r of slice s lives at sbase(s) + r*inner. A CTA owns `sl` adjacent slices x (256/sl) row
+    // lanes, so a warp always touches contiguous memory even when there are only a handful of slices (e.g. the 8 images
+    // of mean(imgs,[2 3])); lanes are combined through shared memory in a fixed order, chunks (gridDim.y) through the
+    // same deterministic last-block finish as the contiguous layout.
     o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(" << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
-         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner) {\n";
-    o << "  __shared__ bool is_last;\n";
-    o << "  const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n";
+         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl) {\n";
+    o << "  __shared__ bool is_last;\n  __shared__ double sacc[256];\n  __shared__ u32 snan[256];\n";
+    o << "  const u32 sloc = threadIdx.x % sl, lane = threadIdx.x / sl, rl = blockDim.x / sl;\n";
+    o << "  const u64 s = (u64)blockIdx.x * sl + sloc;\n";
     o << "  const u64 chunk = (len + gridDim.y - 1) / gridDim.y;\n";
     o << "  const u64 r0 = (u64)blockIdx.y * chunk; const u64 r1 = r0 + chunk < len ? r0 + chunk : len;\n";
     o << "  double acc = IDENT; bool saw_nan = false;\n";
     o << "  const u64 sbase = (s % inner) + (s / inner) * inner * len;\n";
-    o << "  if (s < num_slices) {\n    for (u64 r = r0; r < r1; ++r) {\n";
+    o << "  if (s < num_slices) {\n    u64 r = r0 + lane;\n";
+    o << "    for (; r + 3 * (u64)rl < r1; r += 4 * (u64)rl) {\n";
+    for (int u = 0; u < 4; ++u)
+      for (uint32_t k = 0; k < ni; ++k) o << "      const T w" << u << "_" << k << " = in" << k << "[sbase + (r + " << u << " * (u64)rl) * inner];\n";
+    for (int u = 0; u < 4; ++u) {
+      o << "      {\n";
+      for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = w" << u << "_" << k << ";\n";
+      o << "        accumulate(acc, saw_nan, " << prog.val_expr << ");\n      }\n";
+    }
+    o << "    }\n    for (; r < r1; r += rl) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = in" << k << "[sbase + r * inner];\n";
     o << "      accumulate(acc, saw_nan, " << prog.val_expr << ");\n    }\n  }\n";
     o << R"CUDA(
+  sacc[threadIdx.x] = acc;
+  snan[threadIdx.x] = saw_nan ? 1u : 0u;
+  __syncthreads();
+  u32 nanf = saw_nan ? 1u : 0u;
+  if (lane == 0) {
+    for (u32 l = 1; l < rl; ++l) { acc = COMBINE(acc, sacc[l * sl + sloc]); nanf |= snan[l * sl + sloc]; }
+  }
+  const bool owner = lane == 0 && s < num_slices;
   if (gridDim.y == 1) {
-    if (s < num_slices) out[s] = finish(acc, saw_nan, use_div, factor);
+    if (owner) out[s] = finish(acc, nanf != 0, use_div, factor);
     return;
   }
-  if (s < num_slices) { partial[(u64)blockIdx.y * num_slices + s] = acc; pflags[(u64)blockIdx.y * num_slices + s] = saw_nan ? 1u : 0u; }
+  if (owner) { partial[(u64)blockIdx.y * num_slices + s] = acc; pflags[(u64)blockIdx.y * num_slices + s] = nanf; }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) { const u32 t = atomicAdd(&tickets[blockIdx.x], 1u); is_last = (t == gridDim.y - 1); }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (s < num_slices) {
+  if (owner) {
     double acc2 = IDENT; u32 nan2 = 0;
     for (u32 y = 0; y < gridDim.y; ++y) { acc2 = COMBINE(acc2, __ldcg(&partial[(u64)y * num_slices + s])); nan2 |= __ldcg(&pflags[(u64)y * num_slices + s]); }
     out[s] = finish(acc2, nan2 != 0, use_div, factor);
