@@ -123,6 +123,8 @@ rm_status rm_upload_f32(rm_provider* p, const float* data, const uint64_t* shape
                         rm_handle* out);
 rm_status rm_download(rm_provider* p, const rm_handle* h, double* out, uint64_t out_len);
 rm_status rm_download_f32(rm_provider* p, const rm_handle* h, float* out, uint64_t out_len);
+/* stream-ordered D2H without the final wait: `out` is valid after rm_synchronize() (pipelined host<->device steps) */
+rm_status rm_download_async(rm_provider* p, const rm_handle* h, double* out, uint64_t out_len);
 rm_status rm_free(rm_provider* p, const rm_handle* h);
 rm_status rm_read_scalar(rm_provider* p, const rm_handle* h, uint64_t linear_index, double* out); /* :1463 */
 uint64_t rm_live_buffers(rm_provider* p);

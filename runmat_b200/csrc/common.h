@@ -110,6 +110,10 @@ struct rm_provider {
   void* l2_flush = nullptr;
   size_t l2_flush_bytes = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  // uploads run on their own stream so H2D copies overlap compute and D2H traffic queued on `stream`
+  cudaStream_t h2d_stream = nullptr;
+  cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr;
+  std::mutex h2d_mu;
   int matmul_engine = 0;
 
   rm::FusedCache* fused = nullptr;

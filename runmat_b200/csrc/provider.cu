@@ -216,6 +216,9 @@ RM_EXPORT rm_status rm_provider_create(int ordinal, uint32_t device_id, rm_preci
   RM_CUDA(cudaMemPoolSetAttribute(p->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   RM_CUDA(cudaEventCreate(&p->ev_begin));
   RM_CUDA(cudaEventCreate(&p->ev_end));
+  RM_CUDA(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+  RM_CUDA(cudaEventCreateWithFlags(&p->ev_alloc, cudaEventDisableTiming));
+  RM_CUDA(cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
   RM_TRY(fused_cache_create(p.get()));
   *out = p.release();
   return RM_OK;
@@ -231,6 +234,9 @@ RM_EXPORT rm_status rm_provider_destroy(rm_provider* p) {
   if (p->l2_flush) cudaFreeAsync(p->l2_flush, p->stream);
   cudaStreamSynchronize(p->stream);
   fused_cache_destroy(p);
+  if (p->h2d_stream) { cudaStreamSynchronize(p->h2d_stream); cudaStreamDestroy(p->h2d_stream); }
+  if (p->ev_alloc) cudaEventDestroy(p->ev_alloc);
+  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_end) cudaEventDestroy(p->ev_end);
   if (p->owns_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -311,7 +317,14 @@ static rm_status upload_impl(rm_provider* p, const HostT* data, const uint64_t* 
   const bool dev_f64 = p->precision == RM_F64;
   const bool host_f64 = sizeof(HostT) == 8;
   if (dev_f64 == host_f64) {
-    RM_CUDA(cudaMemcpyAsync(ptr, data, n * sizeof(HostT), cudaMemcpyHostToDevice, p->stream));
+    // H2D on the dedicated upload stream: it only waits for the (stream-ordered) allocation, and the compute stream only
+    // waits for the copy, so the transfer overlaps kernels and D2H copies already queued on the compute stream.
+    std::lock_guard<std::mutex> lk(p->h2d_mu);
+    RM_CUDA(cudaEventRecord(p->ev_alloc, p->stream));
+    RM_CUDA(cudaStreamWaitEvent(p->h2d_stream, p->ev_alloc, 0));
+    RM_CUDA(cudaMemcpyAsync(ptr, data, n * sizeof(HostT), cudaMemcpyHostToDevice, p->h2d_stream));
+    RM_CUDA(cudaEventRecord(p->ev_copied, p->h2d_stream));
+    RM_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copied, 0));
   } else {
     // precision mismatch: stage the host bytes, convert on the device (wgpu narrows per element: io.rs:87)
     void* stage = nullptr;
@@ -363,6 +376,21 @@ static rm_status download_impl(rm_provider* p, const rm_handle* h, HostT* out, u
 }
 RM_EXPORT rm_status rm_download(rm_provider* p, const rm_handle* h, double* out, uint64_t out_len) { return download_impl<double>(p, h, out, out_len); }
 RM_EXPORT rm_status rm_download_f32(rm_provider* p, const rm_handle* h, float* out, uint64_t out_len) { return download_impl<float>(p, h, out, out_len); }
+
+// Stream-ordered download without the final synchronisation: the host buffer is valid after rm_synchronize(). Lets a
+// caller overlap the D2H of one chunk with the upload/compute of the next (bench.py e2e leg).
+RM_EXPORT rm_status rm_download_async(rm_provider* p, const rm_handle* h, double* out, uint64_t out_len) {
+  RM_REQUIRE(p && h && out, RM_INVALID_ARG, "download_async: bad arguments");
+  RM_REQUIRE(p->precision == RM_F64, RM_UNSUPPORTED, "download_async: f32 storage not supported (use rm_download)");
+  DeviceGuard g(p->ordinal);
+  void* ptr;
+  uint64_t n;
+  RM_TRY(resolve(p, h, &ptr, &n));
+  RM_REQUIRE(out_len >= n, RM_INVALID_ARG, "download_async: host buffer holds %llu elements, tensor has %llu", (unsigned long long)out_len, (unsigned long long)n);
+  if (n) RM_CUDA(cudaMemcpyAsync(out, ptr, n * 8, cudaMemcpyDeviceToHost, p->stream));
+  p->download_bytes.fetch_add(n * 8, std::memory_order_relaxed);
+  return RM_OK;
+}
 
 RM_EXPORT rm_status rm_free(rm_provider* p, const rm_handle* h) {
   RM_REQUIRE(p && h, RM_INVALID_ARG, "free: bad arguments");

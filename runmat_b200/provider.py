@@ -165,6 +165,9 @@ class B200Provider:
         fn = lib.rm_download_f32 if f32 else lib.rm_download
         _check(fn(self._p, C.byref(h), C.c_void_p(ptr), C.c_uint64(n)))
 
+    def download_async_into_ptr(self, h: Handle, ptr: int, n: int) -> None:
+        _check(lib.rm_download_async(self._p, C.byref(h), C.c_void_p(ptr), C.c_uint64(n)))
+
     def free(self, h: Handle) -> None:
         _check(lib.rm_free(self._p, C.byref(h)))
 

@@ -67,6 +67,73 @@ def test_upload_download_roundtrip_and_free(prov):
         prov.free(h)
 
 
+def test_pipelined_upload_compute_download(prov, orc):
+    """Uploads ride a dedicated H2D stream and rm_download_async skips the final wait: a chunked, software-pipelined pass over
+    host buffers must equal the one-shot result (this is the e2e leg of bench.py)."""
+    from runmat_b200.provider import pinned_empty
+
+    n, chunks = 1 << 20, 8
+    rng = np.random.default_rng(31)
+    hostA, hostB, hostC = pinned_empty(n), pinned_empty(n), pinned_empty(n)
+    hostA[:] = rng.uniform(0, 6, n)
+    hostB[:] = rng.uniform(-1, 1, n)
+    hostC[:] = 0.0
+    one = prov.upload(np.array([[1.0]]))
+    c = n // chunks
+    pending = None
+    for i in range(chunks + 1):
+        nxt = None
+        if i < chunks:
+            nxt = (i, prov.upload_ptr(hostA.ctypes.data + i * c * 8, (c, 1)), prov.upload_ptr(hostB.ctypes.data + i * c * 8, (c, 1)))
+        if pending is not None:
+            j, pa, pb, pc = pending
+            prov.download_async_into_ptr(pc, hostC.ctypes.data + j * c * 8, c)
+            for h in (pa, pb, pc):
+                prov.free(h)
+        if nxt is not None:
+            pending = (nxt[0], nxt[1], nxt[2], prov.fused_elementwise(ft.sin_mul_add_wgsl(), [nxt[1], nxt[2], one], (c, 1), c))
+        else:
+            pending = None
+    prov.synchronize()
+    ha, hb = prov.upload(np.array(hostA).reshape(-1, 1)), prov.upload(np.array(hostB).reshape(-1, 1))
+    whole = prov.download(prov.fused_elementwise(ft.sin_mul_add_wgsl(), [ha, hb, one], (n, 1), n))[:, 0]
+    assert np.array_equal(np.array(hostC), whole)
+    close(np.array(hostC), orc.sin_mul_add(np.array(hostA), np.array(hostB), 1.0))
+
+
+def test_concurrent_host_threads(prov, orc):
+    """The provider is Send + Sync (accelerate-api lib.rs:1386): several host threads (think GC finalizer + VM) issue
+    uploads, ops, downloads and frees concurrently."""
+    import threading
+
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(20):
+                a, b = rng.uniform(-1, 1, (257, 13)), rng.uniform(-1, 1, (257, 13))
+                ha, hb = prov.upload(a), prov.upload(b)
+                hc = prov.elem_mul(ha, hb)
+                hs = prov.reduce_sum_dim(hc, 0)
+                got_c, got_s = prov.download(hc), prov.download(hs)
+                assert np.array_equal(got_c, a * b)
+                assert np.allclose(got_s, (a * b).sum(axis=0, keepdims=True), rtol=1e-13, atol=1e-13)
+                for h in (ha, hb, hc, hs):
+                    prov.free(h)
+        except Exception as e:  # noqa
+            errors.append(e)
+
+    n0 = prov.live_buffers()
+    ts = [threading.Thread(target=worker, args=(s,)) for s in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    assert prov.live_buffers() == n0
+
+
 def test_precision_and_device_info(prov, prov32):
     assert prov.precision() == "f64" and prov32.precision() == "f32"
     info = prov.device_info_struct()
