@@ -59,6 +59,7 @@ rm_status fail(rm_status code, const char* fmt, ...);
 struct Buffer {
   void* ptr = nullptr;
   uint64_t elems = 0;  // logical elements (real storage only)
+  cudaEvent_t ready = nullptr;  // set by upload: recorded on the H2D stream; the compute stream waits for it at first use
 };
 
 struct DispatchCounter {
@@ -112,8 +113,8 @@ struct rm_provider {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   // uploads run on their own stream so H2D copies overlap compute and D2H traffic queued on `stream`
   cudaStream_t h2d_stream = nullptr;
-  cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr;
-  std::mutex h2d_mu;
+  std::mutex ev_mu;
+  std::vector<cudaEvent_t> event_pool;  // recycled per-buffer "ready" events
   int matmul_engine = 0;
 
   rm::FusedCache* fused = nullptr;

@@ -62,11 +62,21 @@ rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* ele
   RM_REQUIRE(h->device_id == p->device_id, RM_INVALID_HANDLE, "handle belongs to device %u, but this provider owns device %u", h->device_id, p->device_id);
   RM_REQUIRE(h->rank <= RM_MAX_RANK, RM_INVALID_ARG, "handle rank %u exceeds RM_MAX_RANK", h->rank);
   Buffer b;
+  cudaEvent_t ready = nullptr;
   {
     std::lock_guard<std::mutex> lk(p->mu);
     auto it = p->buffers.find(h->buffer_id);
     if (it == p->buffers.end()) return fail(RM_INVALID_HANDLE, "buffer not found: %llu", (unsigned long long)h->buffer_id);
     b = it->second;
+    ready = it->second.ready;
+    it->second.ready = nullptr;
+    // first use of an uploaded buffer: order the compute stream after its H2D copy (enqueued while the table lock is held, so
+    // a concurrent resolve() of the same buffer cannot launch ahead of the wait), then recycle the event
+    if (ready) cudaStreamWaitEvent(p->stream, ready, 0);
+  }
+  if (ready) {
+    std::lock_guard<std::mutex> lk(p->ev_mu);
+    p->event_pool.push_back(ready);
   }
   const uint64_t n = handle_elems(h);
   RM_REQUIRE(n == b.elems, RM_INVALID_ARG, "handle shape holds %llu elements but buffer %llu stores %llu",
@@ -217,8 +227,7 @@ RM_EXPORT rm_status rm_provider_create(int ordinal, uint32_t device_id, rm_preci
   RM_CUDA(cudaEventCreate(&p->ev_begin));
   RM_CUDA(cudaEventCreate(&p->ev_end));
   RM_CUDA(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
-  RM_CUDA(cudaEventCreateWithFlags(&p->ev_alloc, cudaEventDisableTiming));
-  RM_CUDA(cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
+
   RM_TRY(fused_cache_create(p.get()));
   *out = p.release();
   return RM_OK;
@@ -228,15 +237,16 @@ RM_EXPORT rm_status rm_provider_destroy(rm_provider* p) {
   if (!p) return RM_OK;
   DeviceGuard g(p->ordinal);
   cudaStreamSynchronize(p->stream);
-  for (auto& kv : p->buffers) cudaFreeAsync(kv.second.ptr, p->stream);
+  if (p->h2d_stream) cudaStreamSynchronize(p->h2d_stream);
+  for (auto& kv : p->buffers) { if (kv.second.ready) { cudaEventDestroy(kv.second.ready); kv.second.ready = nullptr; } cudaFreeAsync(kv.second.ptr, p->stream); }
   p->buffers.clear();
   if (p->reduce_scratch) cudaFreeAsync(p->reduce_scratch, p->stream);
   if (p->l2_flush) cudaFreeAsync(p->l2_flush, p->stream);
   cudaStreamSynchronize(p->stream);
   fused_cache_destroy(p);
   if (p->h2d_stream) { cudaStreamSynchronize(p->h2d_stream); cudaStreamDestroy(p->h2d_stream); }
-  if (p->ev_alloc) cudaEventDestroy(p->ev_alloc);
-  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
+  for (auto& kv : p->buffers) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+  for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_end) cudaEventDestroy(p->ev_end);
   if (p->owns_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -311,20 +321,46 @@ static rm_status upload_impl(rm_provider* p, const HostT* data, const uint64_t* 
   DeviceGuard g(p->ordinal);
   const uint64_t n = shape_elems(shape, rank);
   RM_REQUIRE(data != nullptr || n == 0, RM_INVALID_ARG, "upload: null host data");
-  void* ptr;
-  RM_TRY(alloc_tensor(p, shape, rank, out, &ptr));
-  if (n == 0) return RM_OK;
   const bool dev_f64 = p->precision == RM_F64;
   const bool host_f64 = sizeof(HostT) == 8;
-  if (dev_f64 == host_f64) {
-    // H2D on the dedicated upload stream: it only waits for the (stream-ordered) allocation, and the compute stream only
-    // waits for the copy, so the transfer overlaps kernels and D2H copies already queued on the compute stream.
-    std::lock_guard<std::mutex> lk(p->h2d_mu);
-    RM_CUDA(cudaEventRecord(p->ev_alloc, p->stream));
-    RM_CUDA(cudaStreamWaitEvent(p->h2d_stream, p->ev_alloc, 0));
+  void* ptr = nullptr;
+  if (dev_f64 == host_f64 && n > 0) {
+    // Allocation and copy both live on the dedicated H2D stream, so an upload never queues behind kernels or D2H copies on
+    // the compute stream. The buffer carries a "ready" event; resolve() makes the compute stream wait for it at first use.
+    RM_REQUIRE(rank <= RM_MAX_RANK, RM_UNSUPPORTED, "tensor rank %u exceeds RM_MAX_RANK=%d", rank, RM_MAX_RANK);
+    const size_t bytes = std::max<size_t>(n * sizeof(HostT), 32);
+    cudaError_t e = cudaMallocAsync(&ptr, bytes, p->h2d_stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? RM_OOM : RM_ERROR, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
+    cudaEvent_t ev = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(p->ev_mu);
+      if (!p->event_pool.empty()) { ev = p->event_pool.back(); p->event_pool.pop_back(); }
+    }
+    if (!ev) RM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     RM_CUDA(cudaMemcpyAsync(ptr, data, n * sizeof(HostT), cudaMemcpyHostToDevice, p->h2d_stream));
-    RM_CUDA(cudaEventRecord(p->ev_copied, p->h2d_stream));
-    RM_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copied, 0));
+    RM_CUDA(cudaEventRecord(ev, p->h2d_stream));
+    const uint64_t id = p->next_id.fetch_add(1, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(p->mu);
+      Buffer b;
+      b.ptr = ptr;
+      b.elems = n;
+      b.ready = ev;
+      p->buffers[id] = b;
+    }
+    p->live_bytes.fetch_add(bytes, std::memory_order_relaxed);
+    memset(out, 0, sizeof *out);
+    out->buffer_id = id;
+    out->device_id = p->device_id;
+    out->rank = rank;
+    for (uint32_t i = 0; i < rank; ++i) out->shape[i] = shape[i];
+    p->upload_bytes.fetch_add(n * sizeof(HostT), std::memory_order_relaxed);
+    return RM_OK;
+  }
+  RM_TRY(alloc_tensor(p, shape, rank, out, &ptr));
+  if (n == 0) return RM_OK;
+  if (dev_f64 == host_f64) {
+    RM_CUDA(cudaMemcpyAsync(ptr, data, n * sizeof(HostT), cudaMemcpyHostToDevice, p->stream));
   } else {
     // precision mismatch: stage the host bytes, convert on the device (wgpu narrows per element: io.rs:87)
     void* stage = nullptr;
@@ -406,6 +442,11 @@ RM_EXPORT rm_status rm_free(rm_provider* p, const rm_handle* h) {
   }
   DeviceGuard g(p->ordinal);
   p->live_bytes.fetch_sub(std::max<size_t>(b.elems * p->elem_size(), 32), std::memory_order_relaxed);
+  if (b.ready) {  // uploaded but never used: the free must still be ordered after the copy
+    cudaStreamWaitEvent(p->stream, b.ready, 0);
+    std::lock_guard<std::mutex> lk(p->ev_mu);
+    p->event_pool.push_back(b.ready);
+  }
   RM_CUDA(cudaFreeAsync(b.ptr, p->stream));
   return RM_OK;
 }
