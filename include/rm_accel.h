@@ -152,6 +152,20 @@ rm_status rm_repmat(rm_provider* p, const rm_handle* a, const uint64_t* reps, ui
 /* cat (lib.rs:2686): concatenate along the 1-based dimension `dim` */
 rm_status rm_cat(rm_provider* p, uint32_t dim_one_based, const rm_handle* inputs, uint32_t n_inputs, rm_handle* out);
 
+/* ---- indexing class of the "next" rows; all results are exact index arithmetic ------------ */
+/* find (lib.rs:2937): 1-based linear/row/col indices + values of the non-zeros, ascending (direction_last=0) or the last
+ * ones in descending order (direction_last=1); has_limit/limit = Option<usize>. Outputs are [count,1]. */
+rm_status rm_find(rm_provider* p, const rm_handle* a, int has_limit, uint64_t limit, int direction_last,
+                  rm_handle* linear, rm_handle* rows, rm_handle* cols, rm_handle* values);
+rm_status rm_scatter_column(rm_provider* p, const rm_handle* matrix, uint64_t col_index, const rm_handle* values, rm_handle* out); /* :3064 */
+rm_status rm_scatter_row(rm_provider* p, const rm_handle* matrix, uint64_t row_index, const rm_handle* values, rm_handle* out);    /* :3075 */
+/* sub2ind (lib.rs:3084): subscripts are 1-based doubles; scalar_mask[d] != 0 broadcasts input d; errors like the host's
+ * coerce_sub2ind_value (simple_provider.rs:2268-2291) */
+rm_status rm_sub2ind(rm_provider* p, const uint64_t* dims, const uint64_t* strides, uint32_t ndims, const rm_handle* inputs,
+                     const uint8_t* scalar_mask, uint64_t len, const uint64_t* output_shape, uint32_t rank, rm_handle* out);
+rm_status rm_ind2sub(rm_provider* p, const uint64_t* dims, const uint64_t* strides, uint32_t ndims, const rm_handle* indices,
+                     uint64_t total, uint64_t len, const uint64_t* output_shape, uint32_t rank, rm_handle* outs); /* :3102; outs[ndims] */
+
 /* ---- a5: unfused operator surface (lib.rs:1890-2357) --------------------------------------------- */
 typedef enum rm_binary_op {
   RM_BIN_ADD = 0, RM_BIN_SUB, RM_BIN_MUL, RM_BIN_DIV, RM_BIN_POW, RM_BIN_MAX, RM_BIN_MIN,

@@ -234,6 +234,38 @@ class B200Provider:
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
         _check(lib.rm_scatter_linear(self._p, C.byref(target), idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(idx.size), C.byref(values)))
 
+    def find(self, a: Handle, limit: Optional[int] = None, direction: str = "first"):
+        """ProviderFindResult{linear, rows, cols, values}"""
+        outs = [Handle() for _ in range(4)]
+        _check(lib.rm_find(self._p, C.byref(a), int(limit is not None), C.c_uint64(limit or 0), int(direction == "last"), *[C.byref(o) for o in outs]))
+        return tuple(outs)
+
+    def scatter_column(self, matrix: Handle, col_index: int, values: Handle) -> Handle:
+        h = Handle()
+        _check(lib.rm_scatter_column(self._p, C.byref(matrix), C.c_uint64(col_index), C.byref(values), C.byref(h)))
+        return h
+
+    def scatter_row(self, matrix: Handle, row_index: int, values: Handle) -> Handle:
+        h = Handle()
+        _check(lib.rm_scatter_row(self._p, C.byref(matrix), C.c_uint64(row_index), C.byref(values), C.byref(h)))
+        return h
+
+    def sub2ind(self, dims: Sequence[int], strides: Sequence[int], inputs: Sequence[Handle], scalar_mask: Sequence[bool], length: int, output_shape) -> Handle:
+        nd = len(dims)
+        arr = (Handle * nd)(*inputs)
+        sa, rank = _shape_arr(output_shape)
+        h = Handle()
+        _check(lib.rm_sub2ind(self._p, (C.c_uint64 * nd)(*dims), (C.c_uint64 * nd)(*strides), nd, arr, (C.c_uint8 * nd)(*[int(b) for b in scalar_mask]),
+                              C.c_uint64(length), sa, rank, C.byref(h)))
+        return h
+
+    def ind2sub(self, dims: Sequence[int], strides: Sequence[int], indices: Handle, total: int, length: int, output_shape) -> list[Handle]:
+        nd = len(dims)
+        outs = (Handle * nd)()
+        sa, rank = _shape_arr(output_shape)
+        _check(lib.rm_ind2sub(self._p, (C.c_uint64 * nd)(*dims), (C.c_uint64 * nd)(*strides), nd, C.byref(indices), C.c_uint64(total), C.c_uint64(length), sa, rank, outs))
+        return list(outs)
+
     # ---- unfused operator surface ----------------------------------------------------------------------------
     def elem_binary(self, op: str, a: Handle, b: Handle) -> Handle:
         h = Handle()

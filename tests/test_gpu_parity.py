@@ -545,6 +545,60 @@ def test_gather_scatter_linear_exact(prov):
         prov.scatter_linear(h, np.array([1, 2], dtype=np.uint32), prov.upload(np.ones((3, 1))))
 
 
+def test_find_sub2ind_ind2sub_scatter_rowcol(prov):
+    rng = np.random.default_rng(41)
+    x = rng.uniform(-1, 1, (97, 53))
+    x[rng.uniform(0, 1, x.shape) < 0.7] = 0.0
+    x[3, 7] = np.nan  # NaN counts as non-zero (value != 0.0)
+    h = prov.upload(x)
+    flat = x.reshape(-1, order="F")
+    nz = np.flatnonzero((flat != 0) | np.isnan(flat))
+
+    def check(res, want_idx):
+        lin, rows, cols, vals = (prov.download(r)[:, 0] for r in res)
+        assert np.array_equal(lin, want_idx + 1.0)
+        assert np.array_equal(rows, want_idx % 97 + 1.0) and np.array_equal(cols, want_idx // 97 + 1.0)
+        assert_same(vals, flat[want_idx])
+
+    check(prov.find(h), nz)                                    # simple_provider.rs:7529-7541
+    check(prov.find(h, limit=10), nz[:10])
+    check(prov.find(h, direction="last"), nz[::-1][:1])        # Last defaults to a limit of 1 (:7516)
+    check(prov.find(h, limit=25, direction="last"), nz[::-1][:25])
+    check(prov.find(h, limit=10**9), nz)
+    assert prov.find(prov.upload(np.zeros((4, 4))))[0].shape == (0, 1)
+    big = np.zeros(300000)
+    big[::7] = 1.5
+    assert np.array_equal(prov.download(prov.find(prov.upload(big.reshape(-1, 1)))[0])[:, 0], np.flatnonzero(big) + 1.0)
+
+    dims, strides = (5, 7, 3), (1, 5, 35)
+    r, c, k = rng.integers(1, 6, 400), rng.integers(1, 8, 400), rng.integers(1, 4, 400)
+    hr, hc, hk = (prov.upload(v.astype(np.float64).reshape(-1, 1)) for v in (r, c, k))
+    lin = prov.download(prov.sub2ind(dims, strides, [hr, hc, hk], [False, False, False], 400, (400, 1)))[:, 0]
+    assert np.array_equal(lin, (r - 1) + (c - 1) * 5 + (k - 1) * 35 + 1.0)
+    lin2 = prov.download(prov.sub2ind(dims, strides, [hr, prov.upload(np.array([[2.0]])), hk], [False, True, False], 400, (400, 1)))[:, 0]
+    assert np.array_equal(lin2, (r - 1) + 1 * 5 + (k - 1) * 35 + 1.0)
+    subs = prov.ind2sub(dims, strides, prov.upload(lin.reshape(-1, 1)), 105, 400, (400, 1))
+    for got, want in zip(subs, (r, c, k)):
+        assert np.array_equal(prov.download(got)[:, 0], want.astype(np.float64))
+    with pytest.raises(ProviderError, match="exceeds dimension 2"):
+        prov.sub2ind(dims, strides, [hr, prov.upload(np.full((400, 1), 8.0)), hk], [False, False, False], 400, (400, 1))
+    with pytest.raises(ProviderError, match="must be an integer"):
+        prov.sub2ind(dims, strides, [prov.upload(np.full((400, 1), 1.5)), hc, hk], [False, False, False], 400, (400, 1))
+    with pytest.raises(ProviderError, match="exceeds the number of elements"):
+        prov.ind2sub(dims, strides, prov.upload(np.array([[106.0]])), 105, 1, (1, 1))
+
+    m = rng.uniform(-1, 1, (6, 9))
+    hm = prov.upload(m)
+    col, row = rng.uniform(5, 6, (6, 1)), rng.uniform(7, 8, (1, 9))
+    want = m.copy(); want[:, 4] = col[:, 0]
+    out = prov.scatter_column(hm, 4, prov.upload(col))
+    assert out.buffer_id != hm.buffer_id and np.array_equal(prov.download(out), want) and np.array_equal(prov.download(hm), m)
+    want = m.copy(); want[2, :] = row[0, :]
+    assert np.array_equal(prov.download(prov.scatter_row(hm, 2, prov.upload(row))), want)
+    with pytest.raises(ProviderError, match="out of bounds"):
+        prov.scatter_column(hm, 9, prov.upload(col))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # a7 / a8: matmul
 # ---------------------------------------------------------------------------------------------------------------
