@@ -279,6 +279,10 @@ rm_status rm_matmul(rm_provider* p, const rm_handle* a, const rm_handle* b, rm_h
 rm_status rm_matmul_epilogue_apply(rm_provider* p, const rm_handle* a, const rm_handle* b,
                                    const rm_matmul_epilogue* ep, rm_handle* out);
 rm_status rm_syrk(rm_provider* p, const rm_handle* a, rm_handle* out); /* A' * A, lib.rs:2383 */
+/* hooks of the planner's special fusion kinds */
+rm_status rm_matmul_power_step(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, double epsilon, rm_handle* out); /* lib.rs:2414 */
+rm_status rm_covariance(rm_provider* p, const rm_handle* matrix, int normalization_biased, rm_handle* out); /* lib.rs:2857, rows=All, unweighted */
+rm_status rm_diag_extract(rm_provider* p, const rm_handle* matrix, int64_t offset, rm_handle* out);         /* lib.rs:1626 */
 /* selects the GEMM engine: 0 = auto, 1 = FP64 DMMA (mma.sync m8n8k4), 2 = Ozaki split on tcgen05 i8 */
 rm_status rm_set_matmul_engine(rm_provider* p, int engine);
 

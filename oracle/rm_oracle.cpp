@@ -535,6 +535,36 @@ ORC_API void orc_conv2d(const double* sig, uint64_t sr, uint64_t sc, const doubl
     for (uint64_t r = 0; r < orows; ++r) out[c * orows + r] = full[(c0 + c) * fr + r0 + r];
 }
 
+// matmul_power_step: simple_provider.rs:7852-7890 — every column of C divided by sqrt(sum(col.^2) + eps), in place.
+ORC_API void orc_power_step_normalize(double* c, uint64_t rows, uint64_t cols, double eps) {
+  for (uint64_t j = 0; j < cols; ++j) {
+    double acc = 0.0;
+    for (uint64_t i = 0; i < rows; ++i) { const double v = c[i + j * rows]; acc += v * v; }
+    acc += eps;
+    const double nrm = std::sqrt(acc);
+    for (uint64_t i = 0; i < rows; ++i) c[i + j * rows] /= nrm;
+  }
+}
+// unweighted covariance, rows = All: runmat-runtime/src/builtins/stats/summary/cov.rs:916-960
+// (means per column; cov_ij = sum((x_i - m_i)(x_j - m_j)) / denom; denom <= 0 -> NaN; non-finite column -> NaN mean)
+ORC_API void orc_covariance(const double* x, uint64_t rows, uint64_t cols, int biased, double* out) {
+  const double denom = biased ? (double)rows : (double)rows - 1.0;
+  for (uint64_t i = 0; i < cols * cols; ++i) out[i] = NAN;
+  if (!(denom > 0.0)) return;
+  std::vector<double> means(cols);
+  for (uint64_t c = 0; c < cols; ++c) {
+    double sum = 0.0; bool valid = true;
+    for (uint64_t r = 0; r < rows; ++r) { const double v = x[r + c * rows]; if (!std::isfinite(v)) { valid = false; break; } sum += v; }
+    means[c] = valid ? sum / (double)rows : NAN;
+  }
+  for (uint64_t i = 0; i < cols; ++i)
+    for (uint64_t j = i; j < cols; ++j) {
+      double acc = 0.0;
+      for (uint64_t r = 0; r < rows; ++r) acc += (x[r + i * rows] - means[i]) * (x[r + j * rows] - means[j]);
+      out[i + j * cols] = out[j + i * cols] = acc / denom;
+    }
+}
+
 // ---- RNG: common/random.rs ---------------------------------------------------------------------------------
 ORC_API uint64_t orc_default_seed(void) { return DEFAULT_RNG_SEED; }
 ORC_API uint64_t orc_mix_seed(uint64_t seed) {  // random.rs:128-142

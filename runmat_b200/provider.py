@@ -414,6 +414,21 @@ class B200Provider:
         _check(lib.rm_cat(self._p, C.c_uint32(dim_one_based), arr, len(inputs), C.byref(h)))
         return h
 
+    def matmul_power_step(self, lhs: Handle, rhs: Handle, epsilon: float) -> Handle:
+        h = Handle()
+        _check(lib.rm_matmul_power_step(self._p, C.byref(lhs), C.byref(rhs), C.c_double(epsilon), C.byref(h)))
+        return h
+
+    def covariance(self, matrix: Handle, normalization: str = "unbiased") -> Handle:
+        h = Handle()
+        _check(lib.rm_covariance(self._p, C.byref(matrix), int(normalization == "biased"), C.byref(h)))
+        return h
+
+    def diag_extract(self, matrix: Handle, offset: int = 0) -> Handle:
+        h = Handle()
+        _check(lib.rm_diag_extract(self._p, C.byref(matrix), C.c_int64(offset), C.byref(h)))
+        return h
+
     def set_matmul_engine(self, engine: int) -> None:
         _check(lib.rm_set_matmul_engine(self._p, int(engine)))
 

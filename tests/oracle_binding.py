@@ -204,6 +204,19 @@ class Oracle:
         self.lib.orc_conv2d(_dp(fs), C.c_uint64(sig.shape[0]), C.c_uint64(sig.shape[1]), _dp(fk), C.c_uint64(ker.shape[0]), C.c_uint64(ker.shape[1]), m, _dp(out), dims)
         return out.reshape((dims[0], dims[1]), order="F")
 
+    def power_step_normalize(self, c, eps):
+        c = np.asarray(c, dtype=np.float64)
+        fc = f64(c).copy()
+        self.lib.orc_power_step_normalize(_dp(fc), C.c_uint64(c.shape[0]), C.c_uint64(c.shape[1]), C.c_double(eps))
+        return fc.reshape(c.shape, order="F")
+
+    def covariance(self, x, biased=False):
+        x = np.asarray(x, dtype=np.float64)
+        out = np.empty(x.shape[1] * x.shape[1])
+        fx = f64(x)
+        self.lib.orc_covariance(_dp(fx), C.c_uint64(x.shape[0]), C.c_uint64(x.shape[1]), int(biased), _dp(out))
+        return out.reshape((x.shape[1], x.shape[1]), order="F")
+
     def linspace(self, start, stop, count):
         out = np.empty(count)
         self.lib.orc_linspace(C.c_double(start), C.c_double(stop), C.c_uint64(count), _dp(out))

@@ -700,6 +700,28 @@ def test_matmul_epilogue_kat_and_order(prov, orc):
     assert np.array_equal(prov.download(prov.matmul_epilogue(prov.upload(a), prov.upload(b), MatmulEpilogue())), plain)
 
 
+def test_fusion_pattern_hooks(prov, orc):
+    """covariance (CenteredGram), matmul_power_step (PowerStepNormalize), diag_extract (ExplainedVariance)."""
+    rng = np.random.default_rng(51)
+    x = rng.uniform(-1, 1, (500, 37)) + rng.uniform(-5, 5, (1, 37))
+    hx = prov.upload(x)
+    for biased in (False, True):
+        got = prov.download(prov.covariance(hx, "biased" if biased else "unbiased"))
+        want = orc.covariance(x, biased)
+        assert np.all(np.abs(got - want) <= 1e-10 * np.sqrt(np.outer(np.diag(want), np.diag(want))) + 1e-14)
+    assert np.all(np.isnan(prov.download(prov.covariance(prov.upload(np.ones((1, 3)))))))   # n-1 == 0 -> NaN (cov.rs:931-933)
+    a, b = rng.uniform(-1, 1, (120, 80)), rng.uniform(-1, 1, (80, 9))
+    got = prov.download(prov.matmul_power_step(prov.upload(a), prov.upload(b), 1e-9))
+    want = orc.power_step_normalize(orc.matmul(a, b), 1e-9)
+    close(got, want, rtol=1e-10, atol=1e-13)
+    assert np.allclose(np.linalg.norm(got, axis=0), 1.0, atol=1e-6)
+    m = rng.uniform(-1, 1, (7, 5))
+    hm = prov.upload(m)
+    for off in (0, 1, -2, 4, -6, 9):
+        d = prov.download(prov.diag_extract(hm, off))
+        assert d.shape == (len(np.diag(m, off)), 1) and np.array_equal(d[:, 0], np.diag(m, off))
+
+
 def test_syrk(prov, orc):
     a = np.random.default_rng(16).uniform(-1, 1, (300, 40))
     got = prov.download(prov.syrk(prov.upload(a)))
