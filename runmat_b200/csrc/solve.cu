@@ -129,6 +129,83 @@ lu_panel_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, i
   }
 }
 
+// Shared-memory variant (used whenever the panel's rows fit 256 per resident CTA): each CTA keeps its 256 x NB slab of the
+// panel in shared memory (one row per thread, padded: conflict-free), so the rank-1 updates never leave the SM. Only the
+// pivot search result and the two exchanged rows cross CTAs (global scratch + grid.sync): 2 grid syncs per column and
+// no dependent L2 round trips in the update (the first version spent ~6 us per column waiting on them).
+constexpr int SLAB_ROWS = 256;
+__global__ void __launch_bounds__(SLAB_ROWS)
+lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, int jb, unsigned long long* __restrict__ ipiv,
+                     PivotEntry* __restrict__ scratch, int* __restrict__ info, double* __restrict__ piv_minmax, double* __restrict__ rowbuf) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double slab_smem[];
+  double (*slab)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(slab_smem);  // [SLAB_ROWS][NB+1]
+  __shared__ double s_val[SLAB_ROWS];
+  __shared__ unsigned long long s_idx[SLAB_ROWS];
+  __shared__ double s_row[NB];
+  __shared__ unsigned long long s_piv;
+  const uint64_t m = n - j0;
+  const int tid = threadIdx.x;
+  const uint64_t r = (uint64_t)blockIdx.x * SLAB_ROWS + tid;  // panel-local row owned by this thread
+  const bool valid = r < m;
+  double* P = A + j0 + j0 * lda;
+  for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = valid ? P[r + (uint64_t)cc * lda] : 0.0;  // coalesced: threads = consecutive rows
+
+  for (int c = 0; c < jb; ++c) {
+    s_val[tid] = (valid && r >= (uint64_t)c) ? fabs(slab[tid][c]) : -1.0;
+    s_idx[tid] = r;
+    __syncthreads();
+    for (int off = SLAB_ROWS / 2; off > 0; off >>= 1) {
+      if (tid < off) {
+        const double ov = s_val[tid + off];
+        const unsigned long long oi = s_idx[tid + off];
+        if (ov > s_val[tid] || (ov == s_val[tid] && oi < s_idx[tid])) { s_val[tid] = ov; s_idx[tid] = oi; }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { scratch[blockIdx.x].val = s_val[0]; scratch[blockIdx.x].idx = s_idx[0]; }
+    grid.sync();
+    if (tid == 0) {
+      double bv = -1.0;
+      unsigned long long bi = 0;
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        const double v = scratch[b].val;
+        const unsigned long long i = scratch[b].idx;
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+      s_piv = bi;
+      if (blockIdx.x == 0) {
+        ipiv[j0 + c] = j0 + bi;
+        if (!(bv > 0.0)) atomicExch(info, 1);
+        if (bv > 0.0) {
+          if (bv < piv_minmax[0]) piv_minmax[0] = bv;
+          if (bv > piv_minmax[1]) piv_minmax[1] = bv;
+        }
+      }
+    }
+    __syncthreads();
+    const uint64_t prow = s_piv;
+    if (valid && r == prow) for (int cc = 0; cc < jb; ++cc) rowbuf[cc] = slab[tid][cc];        // pivot row
+    if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) rowbuf[NB + cc] = slab[tid][cc];  // row c (moves to prow)
+    grid.sync();
+    for (int cc = tid; cc < jb; cc += SLAB_ROWS) s_row[cc] = rowbuf[cc];
+    if (prow != (uint64_t)c) {
+      if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = rowbuf[cc];
+      else if (valid && r == prow) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = rowbuf[NB + cc];
+    }
+    __syncthreads();
+    const double pivot = s_row[c];
+    if (valid && r > (uint64_t)c && pivot != 0.0) {
+      const double l = slab[tid][c] / pivot;
+      slab[tid][c] = l;
+#pragma unroll 8
+      for (int cc = c + 1; cc < jb; ++cc) slab[tid][cc] -= l * s_row[cc];
+    }
+    __syncthreads();
+  }
+  if (valid) for (int cc = 0; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = slab[tid][cc];
+}
+
 // Apply the panel's row interchanges (in order) to columns [c0, c1) of M (ld): one thread per column.
 __global__ void laswp_kernel(double* __restrict__ M, uint64_t ld, uint64_t c0, uint64_t c1, const unsigned long long* __restrict__ ipiv, uint64_t j0, int jb) {
   const uint64_t col = c0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,6 +302,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   unsigned long long* amax = nullptr;
   void* px = nullptr;
   bool have_out = false;
+  double* rowbuf = nullptr;  // [2][NB]: pivot row + displaced row exchanged between CTAs by the slab panel kernel
   auto cleanup = [&](bool drop_out) {
     if (LU) cudaFreeAsync(LU, st);
     if (ipiv) cudaFreeAsync(ipiv, st);
@@ -232,6 +310,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     if (info) cudaFreeAsync(info, st);
     if (pivmm) cudaFreeAsync(pivmm, st);
     if (amax) cudaFreeAsync(amax, st);
+    if (rowbuf) cudaFreeAsync(rowbuf, st);
     if (drop_out && have_out) rm_free(p, out);
   };
 #define SV_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); cleanup(true); return fail(_e == cudaErrorMemoryAllocation ? RM_OOM : RM_ERROR, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
@@ -247,6 +326,12 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, lu_panel_kernel, 256, 0);
   const unsigned max_grid = (unsigned)std::max(1, max_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
 
+  constexpr size_t SLAB_SMEM = (size_t)SLAB_ROWS * (NB + 1) * sizeof(double);
+  cudaFuncSetAttribute(lu_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM);
+  int slab_blocks_per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slab_blocks_per_sm, lu_panel_smem_kernel, SLAB_ROWS, SLAB_SMEM);
+  const unsigned slab_max_grid = (unsigned)std::max(0, slab_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
+  SV_CUDA(cudaMallocAsync((void**)&rowbuf, 2 * NB * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&LU, n * n * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&ipiv, n * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&scratch, (size_t)max_grid * sizeof(PivotEntry), st));
@@ -271,8 +356,14 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, max_grid);
     grid = std::max(grid, 1u);
     uint64_t lda = n, nn = n, jj = j0;
-    void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
-    SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st));
+    const unsigned slab_grid = (unsigned)((m + SLAB_ROWS - 1) / SLAB_ROWS);
+    if (slab_grid <= slab_max_grid && slab_grid <= max_grid && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+      void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm, &rowbuf};
+      SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_smem_kernel, dim3(slab_grid), dim3(SLAB_ROWS), args, SLAB_SMEM, st));
+    } else {
+      void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
+      SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st));
+    }
     // row interchanges: left of the panel, right of the panel, and the right-hand sides
     if (j0 > 0) laswp_kernel<<<(unsigned)((j0 + 127) / 128), 128, 0, st>>>(LU, n, 0, j0, ipiv, j0, jb);
     const uint64_t rest = n - j0 - jb;
