@@ -206,14 +206,48 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
   if (valid) for (int cc = 0; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = slab[tid][cc];
 }
 
-// Apply the panel's row interchanges (in order) to columns [c0, c1) of M (ld): one thread per column.
-__global__ void laswp_kernel(double* __restrict__ M, uint64_t ld, uint64_t c0, uint64_t c1, const unsigned long long* __restrict__ ipiv, uint64_t j0, int jb) {
-  const uint64_t col = c0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= c1) return;
-  double* colp = M + col * ld;
+// Row interchanges of one panel, applied as a gather. The jb sequential swaps (row j0+c <-> ipiv[j0+c]) touch at most 2*jb
+// distinct rows; `perm_build_kernel` (one thread) composes them into (dst_row <- src_row) moves, and `perm_apply_kernel`
+// performs all moves of a column with independent loads followed by independent stores. (The first version walked the jb
+// swaps sequentially per column: 64 dependent, uncoalesced round trips per thread and three launches per panel.)
+struct RowMoves {
+  uint32_t count;
+  unsigned long long dst[2 * NB];
+  unsigned long long src[2 * NB];
+};
+__global__ void perm_build_kernel(const unsigned long long* __restrict__ ipiv, uint64_t j0, int jb, RowMoves* __restrict__ mv) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long rows[2 * NB], cur[2 * NB];  // cur[k] = original row whose data currently sits in rows[k]
+  uint32_t n = 0;
+  auto slot = [&](unsigned long long r) -> uint32_t {
+    for (uint32_t k = 0; k < n; ++k) if (rows[k] == r) return k;
+    rows[n] = r; cur[n] = r;
+    return n++;
+  };
   for (int c = 0; c < jb; ++c) {
-    const uint64_t r0 = j0 + c, r1 = ipiv[j0 + c];
-    if (r1 != r0) { const double t = colp[r0]; colp[r0] = colp[r1]; colp[r1] = t; }
+    const unsigned long long r0 = j0 + c, r1 = ipiv[j0 + c];
+    if (r0 == r1) continue;
+    const uint32_t a = slot(r0), b = slot(r1);
+    const unsigned long long t = cur[a]; cur[a] = cur[b]; cur[b] = t;
+  }
+  uint32_t m = 0;
+  for (uint32_t k = 0; k < n; ++k) if (cur[k] != rows[k]) { mv->dst[m] = rows[k]; mv->src[m] = cur[k]; ++m; }
+  mv->count = m;
+}
+// Columns [0, ncols) of the logical range; columns >= skip_from are shifted by skip_len (to jump over the panel itself).
+__global__ void __launch_bounds__(2 * NB) perm_apply_kernel(double* __restrict__ M, uint64_t ld, uint64_t ncols, uint64_t skip_from, uint64_t skip_len,
+                                                            const RowMoves* __restrict__ mv) {
+  const uint32_t cnt = mv->count;
+  if (cnt == 0) return;
+  const bool active = threadIdx.x < cnt;
+  const unsigned long long d = active ? mv->dst[threadIdx.x] : 0, sr = active ? mv->src[threadIdx.x] : 0;
+  for (uint64_t c = blockIdx.x; c < ncols; c += gridDim.x) {
+    const uint64_t col = c < skip_from ? c : c + skip_len;
+    double* colp = M + col * ld;
+    const double v = active ? colp[sr] : 0.0;
+    __syncthreads();  // all loads of this column before any store (moves may chain)
+    if (active) colp[d] = v;
+    __syncthreads();
   }
 }
 
@@ -302,6 +336,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   unsigned long long* amax = nullptr;
   void* px = nullptr;
   bool have_out = false;
+  RowMoves* moves = nullptr;
   double* rowbuf = nullptr;  // [2][NB]: pivot row + displaced row exchanged between CTAs by the slab panel kernel
   auto cleanup = [&](bool drop_out) {
     if (LU) cudaFreeAsync(LU, st);
@@ -311,6 +346,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     if (pivmm) cudaFreeAsync(pivmm, st);
     if (amax) cudaFreeAsync(amax, st);
     if (rowbuf) cudaFreeAsync(rowbuf, st);
+    if (moves) cudaFreeAsync(moves, st);
     if (drop_out && have_out) rm_free(p, out);
   };
 #define SV_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); cleanup(true); return fail(_e == cudaErrorMemoryAllocation ? RM_OOM : RM_ERROR, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
@@ -332,6 +368,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slab_blocks_per_sm, lu_panel_smem_kernel, SLAB_ROWS, SLAB_SMEM);
   const unsigned slab_max_grid = (unsigned)std::max(0, slab_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
   SV_CUDA(cudaMallocAsync((void**)&rowbuf, 2 * NB * 8, st));
+  SV_CUDA(cudaMallocAsync((void**)&moves, sizeof(RowMoves), st));
   SV_CUDA(cudaMallocAsync((void**)&LU, n * n * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&ipiv, n * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&scratch, (size_t)max_grid * sizeof(PivotEntry), st));
@@ -364,11 +401,11 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
       void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
       SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st));
     }
-    // row interchanges: left of the panel, right of the panel, and the right-hand sides
-    if (j0 > 0) laswp_kernel<<<(unsigned)((j0 + 127) / 128), 128, 0, st>>>(LU, n, 0, j0, ipiv, j0, jb);
+    // row interchanges outside the panel (LU columns left and right of it) and on the right-hand sides
     const uint64_t rest = n - j0 - jb;
-    if (rest > 0) laswp_kernel<<<(unsigned)((rest + 127) / 128), 128, 0, st>>>(LU, n, j0 + jb, n, ipiv, j0, jb);
-    laswp_kernel<<<(unsigned)((nrhs + 127) / 128), 128, 0, st>>>(X, n, 0, nrhs, ipiv, j0, jb);
+    perm_build_kernel<<<1, 32, 0, st>>>(ipiv, j0, jb, moves);
+    if (n - jb > 0) perm_apply_kernel<<<(unsigned)std::min<uint64_t>(n - jb, 4096), 2 * NB, 0, st>>>(LU, n, n - jb, j0, (uint64_t)jb, moves);
+    perm_apply_kernel<<<(unsigned)std::min<uint64_t>(nrhs, 4096), 2 * NB, 0, st>>>(X, n, nrhs, nrhs, 0, moves);
     count_launch(p, 3);
     if (rest > 0) {
       // A12 <- L11^-1 A12 ; A22 -= A21 * A12
