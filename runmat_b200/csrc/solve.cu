@@ -134,68 +134,124 @@ lu_panel_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, i
 // pivot search result and the two exchanged rows cross CTAs (global scratch + grid.sync): 2 grid syncs per column and
 // no dependent L2 round trips in the update (the first version spent ~6 us per column waiting on them).
 constexpr int SLAB_ROWS = 256;
+struct RowMoves {
+  uint32_t count;
+  unsigned long long dst[2 * NB];
+  unsigned long long src[2 * NB];
+};
+// Per-CTA candidate published before the (single) grid.sync of a column: local max |a(r,c)|, its row, that row's panel
+// values, and — from the CTA that owns row c — row c itself (it moves to the pivot's position).
+struct Candidate {
+  double val;
+  unsigned long long idx;
+  double row[NB];
+};
 __global__ void __launch_bounds__(SLAB_ROWS)
 lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, int jb, unsigned long long* __restrict__ ipiv,
-                     PivotEntry* __restrict__ scratch, int* __restrict__ info, double* __restrict__ piv_minmax, double* __restrict__ rowbuf) {
+                     Candidate* __restrict__ cand /*[2][gridDim.x]*/, double* __restrict__ rowc /*[2][NB]*/, int* __restrict__ info,
+                     double* __restrict__ piv_minmax, RowMoves* __restrict__ moves) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double slab_smem[];
   double (*slab)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(slab_smem);  // [SLAB_ROWS][NB+1]
-  __shared__ double s_val[SLAB_ROWS];
-  __shared__ unsigned long long s_idx[SLAB_ROWS];
-  __shared__ double s_row[NB];
+  __shared__ double s_wval[SLAB_ROWS / 32];
+  __shared__ unsigned long long s_widx[SLAB_ROWS / 32];
+  __shared__ double s_row[NB], s_rowc[NB];
   __shared__ unsigned long long s_piv;
+  __shared__ unsigned s_pblock;
+  // net row permutation of this panel, maintained by warp 0 of CTA 0 (rows touched <= 2*NB)
+  __shared__ unsigned long long p_rows[2 * NB], p_cur[2 * NB];
+  __shared__ unsigned p_n;
   const uint64_t m = n - j0;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t r = (uint64_t)blockIdx.x * SLAB_ROWS + tid;  // panel-local row owned by this thread
   const bool valid = r < m;
   double* P = A + j0 + j0 * lda;
-  for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = valid ? P[r + (uint64_t)cc * lda] : 0.0;  // coalesced: threads = consecutive rows
+  for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = valid ? P[r + (uint64_t)cc * lda] : 0.0;
+  if (blockIdx.x == 0 && tid == 0) p_n = 0;
+  __syncthreads();
 
   for (int c = 0; c < jb; ++c) {
-    s_val[tid] = (valid && r >= (uint64_t)c) ? fabs(slab[tid][c]) : -1.0;
-    s_idx[tid] = r;
-    __syncthreads();
-    for (int off = SLAB_ROWS / 2; off > 0; off >>= 1) {
-      if (tid < off) {
-        const double ov = s_val[tid + off];
-        const unsigned long long oi = s_idx[tid + off];
-        if (ov > s_val[tid] || (ov == s_val[tid] && oi < s_idx[tid])) { s_val[tid] = ov; s_idx[tid] = oi; }
-      }
-      __syncthreads();
+    const int buf = c & 1;  // double-buffered exchange area: column c+1 may be published while a slow CTA still reads column c
+    Candidate* mine = cand + (size_t)buf * gridDim.x + blockIdx.x;
+    // ---- local argmax over this CTA's rows >= c: warp shuffles, then one shared hop (ties -> smallest row) ----
+    double bv = (valid && r >= (uint64_t)c) ? fabs(slab[tid][c]) : -1.0;
+    unsigned long long bi = r;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const unsigned long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    if (tid == 0) { scratch[blockIdx.x].val = s_val[0]; scratch[blockIdx.x].idx = s_idx[0]; }
-    grid.sync();
+    if (lane == 0) { s_wval[warp] = bv; s_widx[warp] = bi; }
+    __syncthreads();
     if (tid == 0) {
-      double bv = -1.0;
-      unsigned long long bi = 0;
-      for (unsigned b = 0; b < gridDim.x; ++b) {
-        const double v = scratch[b].val;
-        const unsigned long long i = scratch[b].idx;
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
+      for (int w = 1; w < SLAB_ROWS / 32; ++w)
+        if (s_wval[w] > bv || (s_wval[w] == bv && s_widx[w] < bi)) { bv = s_wval[w]; bi = s_widx[w]; }
       s_piv = bi;
+      mine->val = bv;
+      mine->idx = bi;
+    }
+    __syncthreads();
+    // publish the candidate row and (if owned here) row c BEFORE the sync, so one grid.sync per column is enough
+    if (valid && r == s_piv) for (int cc = 0; cc < jb; ++cc) mine->row[cc] = slab[tid][cc];
+    if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) rowc[buf * NB + cc] = slab[tid][cc];
+    grid.sync();
+    // ---- every CTA resolves the global pivot redundantly ----
+    if (tid == 0) {
+      double gv = -1.0;
+      unsigned long long gi = 0;
+      unsigned gb = 0;
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        const Candidate* cb = cand + (size_t)buf * gridDim.x + b;
+        const double v = __ldcg(&cb->val);
+        const unsigned long long i = __ldcg(&cb->idx);
+        if (v > gv || (v == gv && i < gi)) { gv = v; gi = i; gb = b; }
+      }
+      s_piv = gi;
+      s_pblock = gb;
       if (blockIdx.x == 0) {
-        ipiv[j0 + c] = j0 + bi;
-        if (!(bv > 0.0)) atomicExch(info, 1);
-        if (bv > 0.0) {
-          if (bv < piv_minmax[0]) piv_minmax[0] = bv;
-          if (bv > piv_minmax[1]) piv_minmax[1] = bv;
+        ipiv[j0 + c] = j0 + gi;
+        if (!(gv > 0.0)) atomicExch(info, 1);
+        if (gv > 0.0) {
+          if (gv < piv_minmax[0]) piv_minmax[0] = gv;
+          if (gv > piv_minmax[1]) piv_minmax[1] = gv;
         }
       }
     }
     __syncthreads();
     const uint64_t prow = s_piv;
-    if (valid && r == prow) for (int cc = 0; cc < jb; ++cc) rowbuf[cc] = slab[tid][cc];        // pivot row
-    if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) rowbuf[NB + cc] = slab[tid][cc];  // row c (moves to prow)
-    grid.sync();
-    for (int cc = tid; cc < jb; cc += SLAB_ROWS) s_row[cc] = rowbuf[cc];
-    if (prow != (uint64_t)c) {
-      if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = rowbuf[cc];
-      else if (valid && r == prow) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = rowbuf[NB + cc];
+    const Candidate* win = cand + (size_t)buf * gridDim.x + s_pblock;
+    for (int cc = tid; cc < jb; cc += SLAB_ROWS) { s_row[cc] = __ldcg(&win->row[cc]); s_rowc[cc] = __ldcg(&rowc[buf * NB + cc]); }
+    // CTA 0 / warp 0: fold swap (j0+c <-> j0+prow) into the net permutation (32-lane parallel lookup of the two rows)
+    if (blockIdx.x == 0 && warp == 0 && prow != (uint64_t)c) {
+      const unsigned long long want[2] = {j0 + (uint64_t)c, j0 + prow};
+      unsigned slot[2];
+      for (int q = 0; q < 2; ++q) {
+        unsigned found = 0xffffffffu;
+        const unsigned cnt = p_n;
+        for (unsigned base = 0; base < cnt; base += 32) {
+          const unsigned k = base + lane;
+          const unsigned hit = __ballot_sync(0xffffffffu, k < cnt && p_rows[k] == want[q]);
+          if (hit) { found = base + __ffs(hit) - 1; break; }
+        }
+        if (found == 0xffffffffu) {
+          found = cnt;
+          if (lane == 0) { p_rows[cnt] = want[q]; p_cur[cnt] = want[q]; p_n = cnt + 1; }
+        }
+        __syncwarp();
+        slot[q] = found;
+      }
+      if (lane == 0) { const unsigned long long t = p_cur[slot[0]]; p_cur[slot[0]] = p_cur[slot[1]]; p_cur[slot[1]] = t; }
+      __syncwarp();
     }
     __syncthreads();
+    if (prow != (uint64_t)c) {
+      if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = s_row[cc];
+      else if (valid && r == prow) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = s_rowc[cc];
+    }
     const double pivot = s_row[c];
     if (valid && r > (uint64_t)c && pivot != 0.0) {
+      // note: a thread that just received a swapped row (r == prow) updates the new contents
       const double l = slab[tid][c] / pivot;
       slab[tid][c] = l;
 #pragma unroll 8
@@ -204,20 +260,25 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     __syncthreads();
   }
   if (valid) for (int cc = 0; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = slab[tid][cc];
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t k2 = 0;
+      for (unsigned k = 0; k < p_n; ++k) if (p_cur[k] != p_rows[k]) { moves->dst[k2] = p_rows[k]; moves->src[k2] = p_cur[k]; ++k2; }
+      moves->count = k2;
+    }
+  }
 }
 
 // Row interchanges of one panel, applied as a gather. The jb sequential swaps (row j0+c <-> ipiv[j0+c]) touch at most 2*jb
 // distinct rows; `perm_build_kernel` (one thread) composes them into (dst_row <- src_row) moves, and `perm_apply_kernel`
 // performs all moves of a column with independent loads followed by independent stores. (The first version walked the jb
 // swaps sequentially per column: 64 dependent, uncoalesced round trips per thread and three launches per panel.)
-struct RowMoves {
-  uint32_t count;
-  unsigned long long dst[2 * NB];
-  unsigned long long src[2 * NB];
-};
+// Fallback builder (used with the global-memory panel kernel, i.e. panels taller than the resident slab capacity): one warp,
+// shared-memory tables.
 __global__ void perm_build_kernel(const unsigned long long* __restrict__ ipiv, uint64_t j0, int jb, RowMoves* __restrict__ mv) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  unsigned long long rows[2 * NB], cur[2 * NB];  // cur[k] = original row whose data currently sits in rows[k]
+  __shared__ unsigned long long rows[2 * NB], cur[2 * NB];
+  if (threadIdx.x != 0) return;
   uint32_t n = 0;
   auto slot = [&](unsigned long long r) -> uint32_t {
     for (uint32_t k = 0; k < n; ++k) if (rows[k] == r) return k;
@@ -337,6 +398,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   void* px = nullptr;
   bool have_out = false;
   RowMoves* moves = nullptr;
+  Candidate* cand = nullptr;
   double* rowbuf = nullptr;  // [2][NB]: pivot row + displaced row exchanged between CTAs by the slab panel kernel
   auto cleanup = [&](bool drop_out) {
     if (LU) cudaFreeAsync(LU, st);
@@ -347,6 +409,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     if (amax) cudaFreeAsync(amax, st);
     if (rowbuf) cudaFreeAsync(rowbuf, st);
     if (moves) cudaFreeAsync(moves, st);
+    if (cand) cudaFreeAsync(cand, st);
     if (drop_out && have_out) rm_free(p, out);
   };
 #define SV_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); cleanup(true); return fail(_e == cudaErrorMemoryAllocation ? RM_OOM : RM_ERROR, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
@@ -368,6 +431,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slab_blocks_per_sm, lu_panel_smem_kernel, SLAB_ROWS, SLAB_SMEM);
   const unsigned slab_max_grid = (unsigned)std::max(0, slab_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
   SV_CUDA(cudaMallocAsync((void**)&rowbuf, 2 * NB * 8, st));
+  SV_CUDA(cudaMallocAsync((void**)&cand, (size_t)2 * std::max(slab_max_grid, 1u) * sizeof(Candidate), st));
   SV_CUDA(cudaMallocAsync((void**)&moves, sizeof(RowMoves), st));
   SV_CUDA(cudaMallocAsync((void**)&LU, n * n * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&ipiv, n * 8, st));
@@ -395,15 +459,15 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     uint64_t lda = n, nn = n, jj = j0;
     const unsigned slab_grid = (unsigned)((m + SLAB_ROWS - 1) / SLAB_ROWS);
     if (slab_grid <= slab_max_grid && slab_grid <= max_grid && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
-      void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm, &rowbuf};
+      void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &cand, &rowbuf, &info, &pivmm, &moves};
       SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_smem_kernel, dim3(slab_grid), dim3(SLAB_ROWS), args, SLAB_SMEM, st));
     } else {
       void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
       SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st));
+      perm_build_kernel<<<1, 32, 0, st>>>(ipiv, j0, jb, moves);
     }
     // row interchanges outside the panel (LU columns left and right of it) and on the right-hand sides
     const uint64_t rest = n - j0 - jb;
-    perm_build_kernel<<<1, 32, 0, st>>>(ipiv, j0, jb, moves);
     if (n - jb > 0) perm_apply_kernel<<<(unsigned)std::min<uint64_t>(n - jb, 4096), 2 * NB, 0, st>>>(LU, n, n - jb, j0, (uint64_t)jb, moves);
     perm_apply_kernel<<<(unsigned)std::min<uint64_t>(nrhs, 4096), 2 * NB, 0, st>>>(X, n, nrhs, nrhs, 0, moves);
     count_launch(p, 3);
