@@ -70,12 +70,12 @@ moments_partial_vec_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, 
   typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
   const V* xv = reinterpret_cast<const V*>(x);
   uint64_t v = v0;
-  for (; v + 3 * nthr < nvec; v += 4 * nthr) {
-    V a[4];
+  for (; v + 7 * nthr < nvec; v += 8 * nthr) {  // 8 x 16 B in flight per thread (r02 ncu: 4 were latency-bound at 2.85 TB/s)
+    V a[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
+    for (int u = 0; u < 8; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const T* e = reinterpret_cast<const T*>(&a[u]);
 #pragma unroll
       for (int l = 0; l < VEC; ++l) { const double d = (double)e[l] - K[l]; s1[l] += d; s2[l] += d * d; }

@@ -381,6 +381,25 @@ def test_fused_full_size_4096(prov, orc):
         prov.free(h)
 
 
+def test_more_than_u32_elements(prov32):
+    """Maximum sizes: the wgpu provider rejects len > u32::MAX ("fused_elementwise: tensor too large", elementwise.rs:1577) and
+    chunks dispatches at 65,535 workgroups; here indexing is 64-bit end to end. 2^32 + 37 f32 elements (17.2 GB per tensor)."""
+    n = (1 << 32) + 37
+    h = prov32.fill((n, 1), 1.5)
+    hs = prov32.scalar_add(h, 0.25)                       # fused one-node program, Flat variant, ragged tail
+    assert prov32.read_scalar(hs, n - 1) == 1.75 and prov32.read_scalar(hs, (1 << 32) + 1) == 1.75 and prov32.read_scalar(hs, 0) == 1.75
+    tot = prov32.download(prov32.reduce_sum(hs))[0, 0]      # f64 accumulation: exact
+    assert tot == 1.75 * n
+    X, T0 = 0, 10
+    sh = ft.elementwise_wgsl([X, 1], [ft.FusionOp("primitive", "ElemMul", [X, 1], T0)], [T0], "f32")
+    two = prov32.upload(np.array([[2.0]]))
+    hm = prov32.fused_elementwise(sh, [hs, two], (n, 1), n)   # planner-style program with a 1-element constant input
+    assert prov32.read_scalar(hm, n - 5) == 3.5
+    assert prov32.download(prov32.reduce_max(hm))[0, 0] == 3.5
+    for x in (h, hs, hm):
+        prov32.free(x)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # a4 / a6: reductions
 # ---------------------------------------------------------------------------------------------------------------
