@@ -327,6 +327,84 @@ imfilter_tiled_kernel(const T* __restrict__ img, const T* __restrict__ ker, T* _
   }
 }
 
+// Register-blocked specialisation for the common square kernels (3x3, 5x5, 7x7). The generic tiled kernel issues one shared
+// load per (tap, output) and is LDS-bound (r03: 0.9 TB/s at 8 B/sample). Here the K0*K1 weights live in registers and each
+// thread produces RB = 8 outputs along dim 1: walking the staged input columns j (outer) and k0 (inner), every staged value
+// is loaded once and feeds up to K1 outputs. For a fixed output the taps still arrive as k1 ascending, k0 ascending —
+// exactly the host's column-major kernel order (imfilter.rs:731-745) — with separate multiply and add, so results stay
+// bit-identical to the reference.
+constexpr int RB = 8, FX = 64, FY = 32;  // CTA tile: 64 (dim 0) x 32 (dim 1) outputs; 256 threads = 64 x 4 strips of RB
+template <typename T, int K0, int K1>
+__global__ void __launch_bounds__(256)
+imfilter_regblock_kernel(const T* __restrict__ img, const T* __restrict__ ker, T* __restrict__ out, const __grid_constant__ FilterParams fp) {
+  constexpr int SX = FX + K0 - 1, SY = FY + K1 - 1;
+  __shared__ T tile[SY][SX];
+  __shared__ int map0[SX], map1[SY];
+  const int64_t t0 = (int64_t)blockIdx.x * FX, t1 = (int64_t)blockIdx.y * FY;
+  const uint64_t plane = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto remap = [&](int64_t c, int64_t len) -> int {
+    if (c >= 0 && c < len) return (int)c;
+    if (fp.padding == 0) return -1;
+    return (int)(fp.padding == 1 ? clamp_index(c, len) : (fp.padding == 3 ? wrap_index(c, len) : reflect_index(c, len)));
+  };
+  for (int i = tid; i < SX; i += 256) map0[i] = remap(t0 + i + fp.base[0] - fp.origin[0], (int64_t)fp.ie[0]);
+  for (int i = tid; i < SY; i += 256) map1[i] = remap(t1 + i + fp.base[1] - fp.origin[1], (int64_t)fp.ie[1]);
+  T w[K0 * K1];  // application order (already flipped for convolution)
+#pragma unroll
+  for (int i = 0; i < K0 * K1; ++i) {
+    const int k0 = i % K0, k1 = i / K0;
+    w[i] = __ldg(ker + (fp.mode == 0 ? k0 + k1 * K0 : (K0 - 1 - k0) + (K1 - 1 - k1) * K0));
+  }
+  __syncthreads();
+  const T* src = img + plane * fp.ie[0] * fp.ie[1];
+  for (int sy = warp; sy < SY; sy += 8) {  // one warp per staged column: coalesced along dim 0
+    const int c = map1[sy];
+    for (int sx = lane; sx < SX; sx += 32) {
+      const int r = map0[sx];
+      tile[sy][sx] = (r < 0 || c < 0) ? (T)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+    }
+  }
+  __syncthreads();
+  const int lx = tid & 63, ly0 = (tid >> 6) * RB;
+  T acc[RB];
+#pragma unroll
+  for (int o = 0; o < RB; ++o) acc[o] = (T)0;
+#pragma unroll
+  for (int j = 0; j < RB + K1 - 1; ++j) {
+#pragma unroll
+    for (int k0 = 0; k0 < K0; ++k0) {
+      const T v = tile[ly0 + j][lx + k0];
+#pragma unroll
+      for (int k1 = 0; k1 < K1; ++k1) {
+        const int o = j - k1;
+        if (o >= 0 && o < RB) acc[o] += w[k0 + k1 * K0] * v;
+      }
+    }
+  }
+  const uint64_t o0 = (uint64_t)t0 + lx;
+  if (o0 < fp.oe[0]) {
+#pragma unroll
+    for (int o = 0; o < RB; ++o) {
+      const uint64_t o1 = (uint64_t)t1 + ly0 + o;
+      if (o1 < fp.oe[1]) out[o0 + o1 * fp.oe[0] + plane * fp.oe[0] * fp.oe[1]] = acc[o];
+    }
+  }
+}
+template <typename T>
+static bool launch_regblock(rm_provider* p, const void* pi, const void* pk, void* po, const FilterParams& fp) {
+  if (fp.ke[2] != 1 || fp.ke[0] != fp.ke[1]) return false;
+  dim3 grid((unsigned)((fp.oe[0] + FX - 1) / FX), (unsigned)((fp.oe[1] + FY - 1) / FY), (unsigned)fp.oe[2]);
+  if (grid.y > 65535 || grid.z > 65535) return false;
+  const T* a = (const T*)pi; const T* k = (const T*)pk; T* o = (T*)po;
+  switch (fp.ke[0]) {
+    case 3: imfilter_regblock_kernel<T, 3, 3><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return true;
+    case 5: imfilter_regblock_kernel<T, 5, 5><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return true;
+    case 7: imfilter_regblock_kernel<T, 7, 7><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return true;
+    default: return false;
+  }
+}
+
 // ---- value + index reductions along one dim of [pre, n, post] (simple_provider.rs:7387-7445) ---------------------------
 template <typename T, bool IS_MIN>
 __global__ void minmax_dim_kernel(const T* __restrict__ a, T* __restrict__ vals, T* __restrict__ idx, uint64_t pre, uint64_t n, uint64_t post) {
@@ -430,7 +508,11 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
 static void launch_filter(rm_provider* p, const void* pi, const void* pk, void* po, uint64_t total, const FilterParams& fp) {
   const bool tiled = fp.ke[2] == 1 && fp.ke[0] <= IMF_MAXK && fp.ke[1] <= IMF_MAXK && fp.oe[2] <= 65535 && (fp.oe[1] + IMF_TY - 1) / IMF_TY <= 65535 &&
                      fp.ie[0] < (1ull << 31) && fp.ie[1] < (1ull << 31);
-  if (tiled) {
+  const bool small_dims = fp.ie[0] < (1ull << 31) && fp.ie[1] < (1ull << 31);
+  if (small_dims && !getenv("RUNMAT_B200_IMFILTER_GENERIC") &&
+      (p->precision == RM_F64 ? launch_regblock<double>(p, pi, pk, po, fp) : launch_regblock<float>(p, pi, pk, po, fp))) {
+    // register-blocked 3x3 / 5x5 / 7x7 path
+  } else if (tiled) {
     const int SX = IMF_TX + (int)fp.ke[0] - 1, SY = IMF_TY + (int)fp.ke[1] - 1;
     const size_t sh = (size_t)(SX * SY + (int)(fp.ke[0] * fp.ke[1])) * p->elem_size() + (size_t)(SX + SY) * sizeof(int) + 16;
     dim3 grid((unsigned)((fp.oe[0] + IMF_TX - 1) / IMF_TX), (unsigned)((fp.oe[1] + IMF_TY - 1) / IMF_TY), (unsigned)fp.oe[2]);

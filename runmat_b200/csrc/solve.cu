@@ -146,6 +146,7 @@ struct Candidate {
   unsigned long long idx;
   double row[NB];
 };
+template <bool CLUSTER>
 __global__ void __launch_bounds__(SLAB_ROWS)
 lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, int jb, unsigned long long* __restrict__ ipiv,
                      Candidate* __restrict__ cand /*[2][gridDim.x]*/, double* __restrict__ rowc /*[2][NB]*/, int* __restrict__ info,
@@ -161,6 +162,11 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
   // net row permutation of this panel, maintained by warp 0 of CTA 0 (rows touched <= 2*NB)
   __shared__ unsigned long long p_rows[2 * NB], p_cur[2 * NB];
   __shared__ unsigned p_n;
+  // CLUSTER variant: the per-column exchange (candidates, row c) stays in distributed shared memory and the per-column
+  // barrier is a cluster barrier (~0.3 us) instead of a grid-wide cooperative sync (~2.5 us). One cluster = the whole grid.
+  __shared__ Candidate s_cand[2];
+  __shared__ double s_pub_rowc[2][NB];
+  const unsigned nblk = gridDim.x;
   const uint64_t m = n - j0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t r = (uint64_t)blockIdx.x * SLAB_ROWS + tid;  // panel-local row owned by this thread
@@ -172,7 +178,7 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
 
   for (int c = 0; c < jb; ++c) {
     const int buf = c & 1;  // double-buffered exchange area: column c+1 may be published while a slow CTA still reads column c
-    Candidate* mine = cand + (size_t)buf * gridDim.x + blockIdx.x;
+    Candidate* mine = CLUSTER ? &s_cand[buf] : cand + (size_t)buf * nblk + blockIdx.x;
     // ---- local argmax over this CTA's rows >= c: warp shuffles, then one shared hop (ties -> smallest row) ----
     double bv = (valid && r >= (uint64_t)c) ? fabs(slab[tid][c]) : -1.0;
     unsigned long long bi = r;
@@ -194,22 +200,35 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     __syncthreads();
     // publish the candidate row and (if owned here) row c BEFORE the sync, so one grid.sync per column is enough
     if (valid && r == s_piv) for (int cc = 0; cc < jb; ++cc) mine->row[cc] = slab[tid][cc];
-    if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) rowc[buf * NB + cc] = slab[tid][cc];
-    grid.sync();
-    // ---- every CTA resolves the global pivot redundantly ----
-    if (tid == 0) {
+    if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) (CLUSTER ? s_pub_rowc[buf] : rowc + buf * NB)[cc] = slab[tid][cc];
+    if constexpr (CLUSTER) cg::this_cluster().sync(); else grid.sync();
+    // ---- every CTA resolves the global pivot redundantly: warp 0, one candidate per lane ----
+    if (warp == 0) {
       double gv = -1.0;
-      unsigned long long gi = 0;
+      unsigned long long gi = ~0ull;
       unsigned gb = 0;
-      for (unsigned b = 0; b < gridDim.x; ++b) {
-        const Candidate* cb = cand + (size_t)buf * gridDim.x + b;
-        const double v = __ldcg(&cb->val);
-        const unsigned long long i = __ldcg(&cb->idx);
+      for (unsigned b = lane; b < nblk; b += 32) {
+        double v;
+        unsigned long long i;
+        if constexpr (CLUSTER) {
+          const Candidate* cb = cg::this_cluster().map_shared_rank(&s_cand[buf], b);
+          v = cb->val; i = cb->idx;
+        } else {
+          const Candidate* cb = cand + (size_t)buf * nblk + b;
+          v = __ldcg(&cb->val); i = __ldcg(&cb->idx);
+        }
         if (v > gv || (v == gv && i < gi)) { gv = v; gi = i; gb = b; }
       }
-      s_piv = gi;
-      s_pblock = gb;
-      if (blockIdx.x == 0) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, gv, off);
+        const unsigned long long oi = __shfl_xor_sync(0xffffffffu, gi, off);
+        const unsigned ob = __shfl_xor_sync(0xffffffffu, gb, off);
+        if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; gb = ob; }
+      }
+      if (gi == ~0ull) gi = (unsigned long long)c;  // NaN column: no candidate compared greater; keep the swap in bounds (the solve is rejected later)
+      if (lane == 0) { s_piv = gi; s_pblock = gb; }
+      if (blockIdx.x == 0 && lane == 0) {
         ipiv[j0 + c] = j0 + gi;
         if (!(gv > 0.0)) atomicExch(info, 1);
         if (gv > 0.0) {
@@ -220,8 +239,14 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     }
     __syncthreads();
     const uint64_t prow = s_piv;
-    const Candidate* win = cand + (size_t)buf * gridDim.x + s_pblock;
-    for (int cc = tid; cc < jb; cc += SLAB_ROWS) { s_row[cc] = __ldcg(&win->row[cc]); s_rowc[cc] = __ldcg(&rowc[buf * NB + cc]); }
+    if constexpr (CLUSTER) {
+      const Candidate* win = cg::this_cluster().map_shared_rank(&s_cand[buf], s_pblock);
+      const double* rc = cg::this_cluster().map_shared_rank(&s_pub_rowc[buf][0], 0);  // row c always lives in CTA 0 (c < NB <= SLAB_ROWS)
+      for (int cc = tid; cc < jb; cc += SLAB_ROWS) { s_row[cc] = win->row[cc]; s_rowc[cc] = rc[cc]; }
+    } else {
+      const Candidate* win = cand + (size_t)buf * nblk + s_pblock;
+      for (int cc = tid; cc < jb; cc += SLAB_ROWS) { s_row[cc] = __ldcg(&win->row[cc]); s_rowc[cc] = __ldcg(&rowc[buf * NB + cc]); }
+    }
     // CTA 0 / warp 0: fold swap (j0+c <-> j0+prow) into the net permutation (32-lane parallel lookup of the two rows)
     if (blockIdx.x == 0 && warp == 0 && prow != (uint64_t)c) {
       const unsigned long long want[2] = {j0 + (uint64_t)c, j0 + prow};
@@ -260,6 +285,7 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     __syncthreads();
   }
   if (valid) for (int cc = 0; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = slab[tid][cc];
+  if constexpr (CLUSTER) cg::this_cluster().sync();  // nobody exits while a peer may still read its shared memory
   if (blockIdx.x == 0) {
     __syncthreads();
     if (tid == 0) {
@@ -426,9 +452,26 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   const unsigned max_grid = (unsigned)std::max(1, max_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
 
   constexpr size_t SLAB_SMEM = (size_t)SLAB_ROWS * (NB + 1) * sizeof(double);
-  cudaFuncSetAttribute(lu_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM);
+  cudaFuncSetAttribute(lu_panel_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM);
+  cudaFuncSetAttribute(lu_panel_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM);
+  cudaFuncSetAttribute(lu_panel_smem_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  // largest power-of-two cluster (<= 16 CTAs = 4096 panel rows) the device can co-schedule with this footprint
+  unsigned cluster_max = 0;
+  if (!getenv("RUNMAT_B200_LU_NO_CLUSTER")) {
+    for (unsigned cs = 16; cs >= 1 && !cluster_max; cs >>= 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs); cfg.blockDim = dim3(SLAB_ROWS); cfg.dynamicSmemBytes = SLAB_SMEM; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, lu_panel_smem_kernel<true>, &cfg) == cudaSuccess && nc >= 1) cluster_max = cs;
+    }
+    cudaGetLastError();
+  }
   int slab_blocks_per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slab_blocks_per_sm, lu_panel_smem_kernel, SLAB_ROWS, SLAB_SMEM);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slab_blocks_per_sm, lu_panel_smem_kernel<false>, SLAB_ROWS, SLAB_SMEM);
   const unsigned slab_max_grid = (unsigned)std::max(0, slab_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
   SV_CUDA(cudaMallocAsync((void**)&rowbuf, 2 * NB * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&cand, (size_t)2 * std::max(slab_max_grid, 1u) * sizeof(Candidate), st));
@@ -458,9 +501,20 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     grid = std::max(grid, 1u);
     uint64_t lda = n, nn = n, jj = j0;
     const unsigned slab_grid = (unsigned)((m + SLAB_ROWS - 1) / SLAB_ROWS);
-    if (slab_grid <= slab_max_grid && slab_grid <= max_grid && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+    unsigned cl = 1;
+    while (cl < slab_grid) cl <<= 1;
+    if (cl <= cluster_max && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+      // whole panel inside one thread-block cluster (grid rounded up to a power of two; surplus CTAs own no rows)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cl); cfg.blockDim = dim3(SLAB_ROWS); cfg.dynamicSmemBytes = SLAB_SMEM; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      SV_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_smem_kernel<true>, LU, lda, nn, jj, jb, ipiv, cand, rowbuf, info, pivmm, moves));
+    } else if (slab_grid <= slab_max_grid && slab_grid <= max_grid && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
       void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &cand, &rowbuf, &info, &pivmm, &moves};
-      SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_smem_kernel, dim3(slab_grid), dim3(SLAB_ROWS), args, SLAB_SMEM, st));
+      SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_smem_kernel<false>, dim3(slab_grid), dim3(SLAB_ROWS), args, SLAB_SMEM, st));
     } else {
       void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
       SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st));

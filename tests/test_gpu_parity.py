@@ -9,6 +9,7 @@ Tolerances (stated per BASELINE.json north_star):
     magnitude bound of the sum (sum |terms|).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -388,8 +389,17 @@ def test_more_than_u32_elements(prov32):
     h = prov32.fill((n, 1), 1.5)
     hs = prov32.scalar_add(h, 0.25)                       # fused one-node program, Flat variant, ragged tail
     assert prov32.read_scalar(hs, n - 1) == 1.75 and prov32.read_scalar(hs, (1 << 32) + 1) == 1.75 and prov32.read_scalar(hs, 0) == 1.75
-    tot = prov32.download(prov32.reduce_sum(hs))[0, 0]      # f64 accumulation: exact
-    assert tot == 1.75 * n
+    tot = prov32.download(prov32.reduce_sum(hs))[0, 0]      # f64 accumulation is exact; the result tensor is f32
+    assert tot == float(np.float32(1.75 * n))
+    # a tail that the f32 result can resolve: [2^32 x 1.75, 37 x 2^20] -> sum = 2^20 * 7205 exactly
+    base, tail = prov32.fill((1 << 32, 1), 1.75), prov32.fill((37, 1), float(1 << 20))
+    hcat = prov32.cat(1, [base, tail])
+    prov32.free(base)
+    assert hcat.shape == (n, 1)
+    assert prov32.download(prov32.reduce_sum(hcat))[0, 0] == float((1 << 20) * 7205)
+    assert prov32.download(prov32.reduce_max(hcat))[0, 0] == float(1 << 20)
+    assert prov32.download(prov32.reduce_min(hcat))[0, 0] == 1.75
+    prov32.free(hcat)
     X, T0 = 0, 10
     sh = ft.elementwise_wgsl([X, 1], [ft.FusionOp("primitive", "ElemMul", [X, 1], T0)], [T0], "f32")
     two = prov32.upload(np.array([[2.0]]))
@@ -1001,6 +1011,31 @@ def test_imfilter_kats_and_modes(prov, orc):
     big = rng.uniform(0, 1, (300, 200))
     got = prov.download(prov.imfilter(prov.upload(big), hk, padding="replicate"))
     assert_same(got, orc.imfilter(big, ker, padding="replicate"))
+
+
+def test_imfilter_register_blocked_kernels(prov, prov32, orc):
+    """3x3 / 5x5 / 7x7 take the register-blocked kernel: many tiles, ragged edges, every padding/shape/mode, f64 and f32,
+    and the result must equal the generic kernel's bit for bit (same per-output tap order)."""
+    rng = np.random.default_rng(190)
+    img = rng.uniform(-1, 1, (150, 101, 2))
+    hi = prov.upload(img)
+    for K in (3, 5, 7):
+        kk = rng.uniform(-1, 1, (K, K))
+        hk = prov.upload(kk)
+        for padding in ("constant", "replicate", "symmetric", "circular"):
+            for shape in ("same", "full", "valid"):
+                for mode in ("corr", "conv"):
+                    got = prov.download(prov.imfilter(hi, hk, padding=padding, constant_value=-0.25, shape=shape, mode=mode))
+                    assert_same(got, orc.imfilter(img, kk, padding=padding, cval=-0.25, shape=shape, mode=mode))
+    img32 = rng.uniform(0, 1, (200, 67, 3)).astype(np.float32)
+    k32 = rng.uniform(0, 1, (5, 5)).astype(np.float32)
+    got = prov32.download_f32(prov32.imfilter(prov32.upload_f32(img32), prov32.upload_f32(k32), padding="symmetric"))
+    os.environ["RUNMAT_B200_IMFILTER_GENERIC"] = "1"
+    try:
+        ref = prov32.download_f32(prov32.imfilter(prov32.upload_f32(img32), prov32.upload_f32(k32), padding="symmetric"))
+    finally:
+        del os.environ["RUNMAT_B200_IMFILTER_GENERIC"]
+    assert np.array_equal(got, ref)
 
 
 def test_conv2d_matches_host_order(prov, orc):
