@@ -348,21 +348,35 @@ imfilter_regblock_kernel(const T* __restrict__ img, const T* __restrict__ ker, T
     if (fp.padding == 0) return -1;
     return (int)(fp.padding == 1 ? clamp_index(c, len) : (fp.padding == 3 ? wrap_index(c, len) : reflect_index(c, len)));
   };
-  for (int i = tid; i < SX; i += 256) map0[i] = remap(t0 + i + fp.base[0] - fp.origin[0], (int64_t)fp.ie[0]);
-  for (int i = tid; i < SY; i += 256) map1[i] = remap(t1 + i + fp.base[1] - fp.origin[1], (int64_t)fp.ie[1]);
+  // tiles whose halo lies inside the image (all but the border ring) skip the index maps
+  const int64_t h0 = t0 + fp.base[0] - fp.origin[0], h1 = t1 + fp.base[1] - fp.origin[1];
+  const bool interior = h0 >= 0 && h1 >= 0 && h0 + SX <= (int64_t)fp.ie[0] && h1 + SY <= (int64_t)fp.ie[1];
+  if (!interior) {
+    for (int i = tid; i < SX; i += 256) map0[i] = remap(h0 + i, (int64_t)fp.ie[0]);
+    for (int i = tid; i < SY; i += 256) map1[i] = remap(h1 + i, (int64_t)fp.ie[1]);
+  }
   T w[K0 * K1];  // application order (already flipped for convolution)
 #pragma unroll
   for (int i = 0; i < K0 * K1; ++i) {
     const int k0 = i % K0, k1 = i / K0;
     w[i] = __ldg(ker + (fp.mode == 0 ? k0 + k1 * K0 : (K0 - 1 - k0) + (K1 - 1 - k1) * K0));
   }
-  __syncthreads();
   const T* src = img + plane * fp.ie[0] * fp.ie[1];
-  for (int sy = warp; sy < SY; sy += 8) {  // one warp per staged column: coalesced along dim 0
-    const int c = map1[sy];
-    for (int sx = lane; sx < SX; sx += 32) {
-      const int r = map0[sx];
-      tile[sy][sx] = (r < 0 || c < 0) ? (T)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+  if (interior) {
+    const T* col = src + (uint64_t)h0 + (uint64_t)(h1 + warp) * fp.ie[0];
+    const uint64_t step = 8 * fp.ie[0];
+    for (int sy = warp; sy < SY; sy += 8, col += step) {  // one warp per staged column: coalesced along dim 0
+#pragma unroll
+      for (int sx = lane; sx < SX; sx += 32) tile[sy][sx] = col[sx];
+    }
+  } else {
+    __syncthreads();
+    for (int sy = warp; sy < SY; sy += 8) {
+      const int c = map1[sy];
+      for (int sx = lane; sx < SX; sx += 32) {
+        const int r = map0[sx];
+        tile[sy][sx] = (r < 0 || c < 0) ? (T)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+      }
     }
   }
   __syncthreads();
@@ -382,13 +396,13 @@ imfilter_regblock_kernel(const T* __restrict__ img, const T* __restrict__ ker, T
       }
     }
   }
-  const uint64_t o0 = (uint64_t)t0 + lx;
+  const uint64_t o0 = (uint64_t)t0 + lx, o1 = (uint64_t)t1 + ly0;
   if (o0 < fp.oe[0]) {
+    T* dst = out + o0 + o1 * fp.oe[0] + plane * fp.oe[0] * fp.oe[1];
+    const int nvalid = o1 + RB <= fp.oe[1] ? RB : (o1 < fp.oe[1] ? (int)(fp.oe[1] - o1) : 0);
 #pragma unroll
-    for (int o = 0; o < RB; ++o) {
-      const uint64_t o1 = (uint64_t)t1 + ly0 + o;
-      if (o1 < fp.oe[1]) out[o0 + o1 * fp.oe[0] + plane * fp.oe[0] * fp.oe[1]] = acc[o];
-    }
+    for (int o = 0; o < RB; ++o, dst += fp.oe[0])
+      if (o < nvalid) *dst = acc[o];
   }
 }
 template <typename T>

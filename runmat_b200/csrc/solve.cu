@@ -190,17 +190,25 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     }
     if (lane == 0) { s_wval[warp] = bv; s_widx[warp] = bi; }
     __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < SLAB_ROWS / 32; ++w)
-        if (s_wval[w] > bv || (s_wval[w] == bv && s_widx[w] < bi)) { bv = s_wval[w]; bi = s_widx[w]; }
-      s_piv = bi;
-      mine->val = bv;
-      mine->idx = bi;
+    if (warp == 0) {
+      bv = lane < SLAB_ROWS / 32 ? s_wval[lane] : -1.0;
+      bi = lane < SLAB_ROWS / 32 ? s_widx[lane] : ~0ull;
+#pragma unroll
+      for (int off = SLAB_ROWS / 64; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const unsigned long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_piv = bi; mine->val = bv; mine->idx = bi; }
     }
     __syncthreads();
-    // publish the candidate row and (if owned here) row c BEFORE the sync, so one grid.sync per column is enough
-    if (valid && r == s_piv) for (int cc = 0; cc < jb; ++cc) mine->row[cc] = slab[tid][cc];
-    if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) (CLUSTER ? s_pub_rowc[buf] : rowc + buf * NB)[cc] = slab[tid][cc];
+    // publish the candidate row and (if owned here) row c BEFORE the sync, so one barrier per column is enough. One thread
+    // per panel column: a single thread walking the 64-wide row cost ~1 us per column of the factorisation.
+    {
+      const uint64_t lp = s_piv - (uint64_t)blockIdx.x * SLAB_ROWS;  // local row of this CTA's candidate
+      if (tid < jb && lp < (uint64_t)SLAB_ROWS) mine->row[tid] = slab[lp][tid];
+      if (blockIdx.x == 0 && tid >= NB && tid < NB + jb) (CLUSTER ? s_pub_rowc[buf] : rowc + buf * NB)[tid - NB] = slab[c][tid - NB];
+    }
     if constexpr (CLUSTER) cg::this_cluster().sync(); else grid.sync();
     // ---- every CTA resolves the global pivot redundantly: warp 0, one candidate per lane ----
     if (warp == 0) {
@@ -271,8 +279,11 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     }
     __syncthreads();
     if (prow != (uint64_t)c) {
-      if (valid && r == (uint64_t)c) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = s_row[cc];
-      else if (valid && r == prow) for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = s_rowc[cc];
+      // row c (always in CTA 0) receives the pivot row; the pivot's home CTA receives the old row c
+      if (blockIdx.x == 0 && tid < jb) slab[c][tid] = s_row[tid];
+      const uint64_t lp = prow - (uint64_t)blockIdx.x * SLAB_ROWS;
+      if (lp < (uint64_t)SLAB_ROWS && tid >= NB && tid < NB + jb) slab[lp][tid - NB] = s_rowc[tid - NB];
+      __syncthreads();
     }
     const double pivot = s_row[c];
     if (valid && r > (uint64_t)c && pivot != 0.0) {

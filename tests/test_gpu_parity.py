@@ -1029,10 +1029,10 @@ def test_imfilter_register_blocked_kernels(prov, prov32, orc):
                     assert_same(got, orc.imfilter(img, kk, padding=padding, cval=-0.25, shape=shape, mode=mode))
     img32 = rng.uniform(0, 1, (200, 67, 3)).astype(np.float32)
     k32 = rng.uniform(0, 1, (5, 5)).astype(np.float32)
-    got = prov32.download_f32(prov32.imfilter(prov32.upload_f32(img32), prov32.upload_f32(k32), padding="symmetric"))
+    got = prov32.download(prov32.imfilter(prov32.upload(img32), prov32.upload(k32), padding="symmetric"), np.float32)
     os.environ["RUNMAT_B200_IMFILTER_GENERIC"] = "1"
     try:
-        ref = prov32.download_f32(prov32.imfilter(prov32.upload_f32(img32), prov32.upload_f32(k32), padding="symmetric"))
+        ref = prov32.download(prov32.imfilter(prov32.upload(img32), prov32.upload(k32), padding="symmetric"), np.float32)
     finally:
         del os.environ["RUNMAT_B200_IMFILTER_GENERIC"]
     assert np.array_equal(got, ref)
