@@ -1050,6 +1050,31 @@ def test_conv2d_matches_host_order(prov, orc):
             assert_same(got, want)  # same tap order as the host's scatter loop: bit-exact
 
 
+def test_explained_variance_hook_sequence(prov, orc):
+    """FusionKind::ExplainedVariance (fusion.rs:2481-2583) executes as matmul -> reshape -> matmul -> matmul -> diag_extract
+    (fusion_exec.rs:731-869); the "transpose" of Q is a metadata-only reshape there, and is here too."""
+    rng = np.random.default_rng(77)
+    n = 96
+    q, g = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    g = g @ g.T / n
+    hq, hg = prov.upload(q), prov.upload(g)
+    live0 = prov.live_buffers()
+    tmp0 = prov.matmul(hq, hg)
+    qt = prov.reshape(hq, (n, n))
+    assert qt.buffer_id == hq.buffer_id  # reshape: same buffer, new logical shape (lib.rs:2676-2684)
+    tmp = prov.matmul(qt, hg)
+    product = prov.matmul(tmp, prov.reshape(hq, (n, n)))
+    diag = prov.diag_extract(product, 0)
+    assert diag.shape in ((n, 1), (n,))
+    want = np.diagonal(orc.matmul(orc.matmul(q, g), q))
+    got = prov.download(diag).reshape(-1)
+    scale = np.abs(q) @ np.abs(g) @ np.abs(q)
+    assert np.all(np.abs(got - want) <= 1e-10 * np.diagonal(scale))
+    for h in (tmp0, tmp, product, diag):
+        prov.free(h)
+    assert prov.live_buffers() == live0
+
+
 def test_cat_and_mrdivide(prov):
     rng = np.random.default_rng(24)
     a, b, c = rng.uniform(-1, 1, (3, 4)), rng.uniform(-1, 1, (2, 4)), rng.uniform(-1, 1, (3, 5))
