@@ -22,6 +22,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 from pathlib import Path
 
@@ -48,7 +49,11 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / clock-event reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    The timed region of this workload is a few milliseconds, far shorter than one `nvidia-smi -lms` period, so the primary
+    sampler is an NVML polling thread (nvidia_ml_py, ~2 kHz; the main thread sits in GIL-free ctypes calls while the GPU works).
+    `nvidia-smi -lms 100` runs beside it as the fallback / cross-check."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -57,8 +62,47 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.nvml_sm, self.nvml_reasons, self.nvml_max = [], 0, None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:  # CUDA ordinal -> NVML handle by PCI bus id (robust under CUDA_VISIBLE_DEVICES)
+            import torch
+
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self, pynvml, h):
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.nvml_sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.nvml_reasons |= int(get_reasons(h))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        try:
+            pynvml, h = self._nvml_handle()
+            self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._pynvml = pynvml
+            self.thread = threading.Thread(target=self._poll, args=(pynvml, h), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -68,29 +112,42 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        if self.thread:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for line in Path(self.path).read_text().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
+        if self.proc:
+            if not self.nvml_sm:
+                time.sleep(0.15)  # no NVML samples: give nvidia-smi the chance to emit at least one line
+            self.proc.terminate()
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            for line in Path(self.path).read_text().splitlines():
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        if self.nvml_sm:
+            pn = self._pynvml
+            for name, attr in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                               ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+                if self.nvml_reasons & int(getattr(pn, attr, 0)):
                     reasons.add(name)
-        os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": statistics.median(self.nvml_sm), "sm_max_mhz": self.nvml_max or (max(mx) if mx else None), "reasons": sorted(reasons),
+                    "samples": len(self.nvml_sm), "source": "nvml", "nvidia_smi_samples": len(sm)}
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (nvml and nvidia-smi unavailable)"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def synth_inputs(rank: int):
@@ -224,6 +281,7 @@ def run_ours(args):
     t_before = p.telemetry_snapshot().kernel_launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
+        sys.setswitchinterval(0.0005)  # let the NVML polling thread run between the (GIL-holding) launch calls
         sampler.start()
     sync_all()
     p.timer_begin()

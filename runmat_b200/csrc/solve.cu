@@ -505,9 +505,15 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   absmax_kernel<<<(unsigned)std::min<uint64_t>((n * n + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 8), 256, 0, st>>>(LU, n * n, amax, info + 1);
   count_launch(p);
 
+  // Two-level blocking: 64-wide panels are factored and applied only inside the current NBO-wide outer block; the rest of
+  // the matrix sees ONE rank-NBO update per outer block (a k=64 DMMA update of the whole trailing matrix per panel ran at
+  // ~7 TFLOP/s and re-read/wrote the trailing matrix 4x as often).
+  uint64_t NBO = 256;
+  if (const char* e = getenv("RUNMAT_B200_LU_OUTER")) { const long v = atol(e); if (v >= NB && v % NB == 0) NBO = (uint64_t)v; }
   for (uint64_t j0 = 0; j0 < n; j0 += NB) {
     int jb = (int)std::min<uint64_t>(NB, n - j0);
     const uint64_t m = n - j0;
+    const uint64_t J0 = (j0 / NBO) * NBO, Jend = std::min<uint64_t>(J0 + NBO, n);
     unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, max_grid);
     grid = std::max(grid, 1u);
     uint64_t lda = n, nn = n, jj = j0;
@@ -536,11 +542,23 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     if (n - jb > 0) perm_apply_kernel<<<(unsigned)std::min<uint64_t>(n - jb, 4096), 2 * NB, 0, st>>>(LU, n, n - jb, j0, (uint64_t)jb, moves);
     perm_apply_kernel<<<(unsigned)std::min<uint64_t>(nrhs, 4096), 2 * NB, 0, st>>>(X, n, nrhs, nrhs, 0, moves);
     count_launch(p, 3);
-    if (rest > 0) {
-      // A12 <- L11^-1 A12 ; A22 -= A21 * A12
-      trsm_block_kernel<true><<<(unsigned)((rest + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest);
+    const uint64_t rest_in = Jend - (j0 + jb);  // columns of the outer block still to factor
+    if (rest_in > 0) {
+      // inside the outer block: A12 <- L11^-1 A12 ; A22 -= A21 * A12
+      trsm_block_kernel<true><<<(unsigned)((rest_in + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest_in);
       count_launch(p);
-      SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, LU + j0 + (j0 + jb) * n, n, LU + (j0 + jb) + (j0 + jb) * n, n, rest, rest, (uint64_t)jb));
+      SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, LU + j0 + (j0 + jb) * n, n, LU + (j0 + jb) + (j0 + jb) * n, n, rest, rest_in, (uint64_t)jb));
+    } else if (Jend < n) {
+      // outer block [J0, Jend) is factored: U12 <- L11^-1 A12 by 64-row steps, then one rank-(Jend-J0) trailing update
+      const uint64_t right = n - Jend;
+      for (uint64_t i0 = J0; i0 < Jend; i0 += NB) {
+        const int ib = (int)std::min<uint64_t>(NB, Jend - i0);
+        trsm_block_kernel<true><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, st>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
+        count_launch(p);
+        const uint64_t below = Jend - (i0 + ib);
+        if (below > 0) SV_TRY(dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, LU + i0 + Jend * n, n, LU + (i0 + ib) + Jend * n, n, below, right, (uint64_t)ib));
+      }
+      SV_TRY(dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + Jend * n, n, LU + Jend + Jend * n, n, right, right, Jend - J0));
     }
   }
   SV_CUDA(cudaGetLastError());
