@@ -104,6 +104,8 @@ uint32_t rm_abi_version(void);
 const char* rm_last_error(void);
 rm_status rm_device_info_string(rm_provider* p, char* buf, size_t buflen); /* device_info() :1390 */
 rm_status rm_device_info_struct(rm_provider* p, rm_device_info* out);      /* :1448 */
+/* PCI bus id ("0000:1b:00.0") of the provider's device: lets the host place its threads and pinned buffers on the GPU's NUMA node. */
+rm_status rm_device_pci_bus_id(rm_provider* p, char* buf, uint32_t buflen);
 uint32_t rm_device_id(rm_provider* p);                                     /* :1391 */
 rm_precision rm_provider_precision(rm_provider* p);                        /* precision() :1458 */
 rm_status rm_synchronize(rm_provider* p);

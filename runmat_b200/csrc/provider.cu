@@ -273,6 +273,11 @@ RM_EXPORT rm_status rm_device_info_struct(rm_provider* p, rm_device_info* out) {
   out->cc_minor = (uint32_t)p->prop.minor;
   return RM_OK;
 }
+RM_EXPORT rm_status rm_device_pci_bus_id(rm_provider* p, char* buf, uint32_t buflen) {
+  RM_REQUIRE(p && buf && buflen >= 13, RM_INVALID_ARG, "rm_device_pci_bus_id: bad arguments");
+  RM_CUDA(cudaDeviceGetPCIBusId(buf, (int)buflen, p->ordinal));
+  return RM_OK;
+}
 RM_EXPORT uint32_t rm_device_id(rm_provider* p) { return p ? p->device_id : 0; }
 RM_EXPORT rm_precision rm_provider_precision(rm_provider* p) { return p ? p->precision : RM_F64; }
 RM_EXPORT rm_status rm_synchronize(rm_provider* p) {

@@ -97,6 +97,11 @@ class B200Provider:
         _check(lib.rm_device_info_string(self._p, buf, 512))
         return buf.value.decode()
 
+    def pci_bus_id(self) -> str:
+        buf = C.create_string_buffer(32)
+        _check(lib.rm_device_pci_bus_id(self._p, buf, 32))
+        return buf.value.decode().lower()
+
     def device_info_struct(self) -> _capi.DeviceInfo:
         info = _capi.DeviceInfo()
         _check(lib.rm_device_info_struct(self._p, C.byref(info)))

@@ -37,3 +37,33 @@ def batch_slices_for_rank(batch: int, rank: int, world: int) -> Tuple[int, int]:
     """Images [b0, b1) of a [B,H,W] batch owned by `rank`. Batch is the stride-1 axis in RunMat's layout, so the host
     performs the strided split when it uploads a rank's [b1-b0, H, W] tensor."""
     return shard_range(batch, rank, world)
+
+
+def bind_process_to_gpu_numa(pci_bus_id: str):
+    """One process per GPU: run this process (and first-touch its pinned host buffers) on the NUMA node the GPU hangs off, so
+    H2D/D2H copies do not cross the inter-socket link. Returns {"node": n, "cpus": k} or None when the topology is not exposed
+    (containers without /sys, single-node hosts). Never raises: placement is an optimisation, not a requirement."""
+    import os
+
+    try:
+        bus = pci_bus_id.lower()
+        if len(bus.split(":")[0]) == 8:  # cudaDeviceGetPCIBusId may print an 8-digit domain; sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None

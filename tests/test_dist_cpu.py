@@ -69,3 +69,11 @@ def test_sharded_monte_carlo_sum_matches_single_process(orc):
         assert abs(total - whole) <= 1e-12 * abs(whole)  # only the order of the final two-term sum differs
     ranges = sorted((lo, hi) for _, _, lo, hi in results)
     assert ranges[0][0] == 0 and ranges[-1][1] == M and ranges[0][1] == ranges[1][0]
+
+
+def test_numa_binding_is_best_effort():
+    """Host placement helper never raises and reports None when the device is not in sysfs (as in this container)."""
+    from runmat_b200.sharding import bind_process_to_gpu_numa
+
+    assert bind_process_to_gpu_numa("0000:ff:1f.7") is None
+    assert bind_process_to_gpu_numa("garbage") is None
