@@ -242,6 +242,24 @@ def run_ours(args):
     # sum is copied (one C call, stream-ordered) into a 2-slot persistent buffer, the comm stream waits on that copy and
     # all-reduces the slot in place, so the collective's latency overlaps the next step's kernels. A slot is reused two
     # steps later, after the provider stream has waited for its previous reduction.
+    native_comm = False
+    if world > 1 and not os.environ.get("RUNMAT_B200_TORCH_ALLREDUCE"):
+        # Preferred exchange: the provider's own NCCL communicator (rm_comm_*): ONE C call per step issues the copy, the stream
+        # dependencies and the all-reduce on the provider's communication stream. torch.distributed only ships the 128-byte id.
+        ok = 1
+        try:
+            ident = [B200Provider.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ident, src=0)
+            p.comm_init(ident[0], rank, world)
+            probe = p.upload(np.array([float(rank + 1)]), (1, 1))
+            got = float(p.download(p.comm_allreduce_sum(probe))[0, 0])
+            ok = 1 if got == world * (world + 1) / 2 else 0
+        except Exception as exc:  # noqa: BLE001 - any failure selects the torch.distributed exchange below on ALL ranks
+            print(f"[bench] rank {rank}: native comm unavailable ({exc}); using torch.distributed", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{local_rank}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        native_comm = bool(flag.item())
     if world > 1:
         prov_stream = torch.cuda.ExternalStream(p.stream(), device=f"cuda:{local_rank}")
         comm_stream = torch.cuda.current_stream()
@@ -257,6 +275,10 @@ def run_ours(args):
     def step():
         hC = p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS)
         hS = p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1)
+        if native_comm:
+            hG = p.comm_allreduce_sum(hS)  # global sum of this step; overlaps the next step's kernels
+            p.free(hS)
+            return hC, hG
         if world > 1:
             slot = step_no[0] & 1
             step_no[0] += 1
@@ -296,7 +318,9 @@ def run_ours(args):
         if last_sum is not None:
             p.free(last_sum)
         last_sum = hS
-    if world > 1:
+    if native_comm:
+        p.comm_fence()  # the timed region ends when the last all-reduce has landed
+    elif world > 1:
         prov_stream.wait_stream(comm_stream)  # the timed region ends when the last all-reduce has landed
     ms = p.timer_end_ms()
     sync_all()
@@ -305,7 +329,7 @@ def run_ours(args):
     checksum = float(p.download(last_sum)[0, 0])
     checksum_local = checksum
     p.free(last_sum)
-    if world > 1:
+    if world > 1 and not native_comm:
         checksum = float(sum_slots[(step_no[0] - 1) & 1].item())  # the all-reduced sum of the last step
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -443,7 +467,8 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "elementwise-math fused chain + sum(), 4096x4096 f64 per GPU (BASELINE.json configs[1])",
                        "bytes_per_step_per_gpu": BYTES_STEP, "l2": "inputs (2x128 MiB) + output (128 MiB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"{world} independent batches, one NCCL all-reduce of 1 f64 per step" if world > 1 else "single GPU",
+                       "parallelism": (f"{world} independent batches, one NCCL all-reduce of 1 f64 per step "
+                                       f"({'provider communicator, rm_comm_allreduce_sum' if native_comm else 'torch.distributed'})") if world > 1 else "single GPU",
                        "host_numa_binding": numa},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "checksum": checksum, "extra": extra,

@@ -104,6 +104,16 @@ uint32_t rm_abi_version(void);
 const char* rm_last_error(void);
 rm_status rm_device_info_string(rm_provider* p, char* buf, size_t buflen); /* device_info() :1390 */
 rm_status rm_device_info_struct(rm_provider* p, rm_device_info* out);      /* :1448 */
+/* ---- multi-GPU exchange (no counterpart in the single-device trait) --------------------------------------
+ * One process per GPU. Rank 0 calls rm_comm_unique_id, the host ships the 128 bytes to every rank (torch.distributed,
+ * MPI, a file ...), every rank calls rm_comm_init. rm_comm_allreduce_sum(in) -> out is stream-ordered after the producer of
+ * `in`, runs on a communication stream, and `out` is waited for lazily at its first use. NCCL is dlopen'ed on first use. */
+#define RM_COMM_ID_BYTES 128
+rm_status rm_comm_unique_id(uint8_t* out, uint32_t len);
+rm_status rm_comm_init(rm_provider* p, const uint8_t* unique_id, uint32_t len, uint32_t rank, uint32_t world);
+uint32_t rm_comm_world_size(rm_provider* p);
+rm_status rm_comm_allreduce_sum(rm_provider* p, const rm_handle* in, rm_handle* out);
+rm_status rm_comm_fence(rm_provider* p);
 /* PCI bus id ("0000:1b:00.0") of the provider's device: lets the host place its threads and pinned buffers on the GPU's NUMA node. */
 rm_status rm_device_pci_bus_id(rm_provider* p, char* buf, uint32_t buflen);
 uint32_t rm_device_id(rm_provider* p);                                     /* :1391 */

@@ -116,6 +116,10 @@ struct rm_provider {
   std::mutex ev_mu;
   std::vector<cudaEvent_t> event_pool;  // recycled per-buffer "ready" events
   int matmul_engine = 0;
+  // multi-GPU exchange (comm.cu): one NCCL communicator per provider, collectives on their own stream
+  void* nccl_comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  int comm_rank = 0, comm_world = 1;
 
   rm::FusedCache* fused = nullptr;
 
@@ -143,6 +147,7 @@ inline uint64_t handle_elems(const rm_handle* h) { return shape_elems(h->shape, 
 
 // Allocates a device buffer of `elems` elements (provider precision) and fills `out` with a fresh handle.
 rm_status alloc_tensor(rm_provider* p, const uint64_t* shape, uint32_t rank, rm_handle* out, void** dptr);
+void comm_destroy(rm_provider* p);
 // Resolves a handle to its device pointer, validating device_id and element count.
 rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* elems);
 rm_status ensure_scratch(rm_provider* p, size_t bytes);

@@ -243,6 +243,7 @@ RM_EXPORT rm_status rm_provider_destroy(rm_provider* p) {
   if (p->reduce_scratch) cudaFreeAsync(p->reduce_scratch, p->stream);
   if (p->l2_flush) cudaFreeAsync(p->l2_flush, p->stream);
   cudaStreamSynchronize(p->stream);
+  comm_destroy(p);
   fused_cache_destroy(p);
   if (p->h2d_stream) { cudaStreamSynchronize(p->h2d_stream); cudaStreamDestroy(p->h2d_stream); }
   for (auto& kv : p->buffers) if (kv.second.ready) cudaEventDestroy(kv.second.ready);

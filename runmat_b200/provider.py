@@ -97,6 +97,29 @@ class B200Provider:
         _check(lib.rm_device_info_string(self._p, buf, 512))
         return buf.value.decode()
 
+    # ---- multi-GPU exchange (include/rm_accel.h: rm_comm_*) -------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(lib.rm_comm_unique_id(buf, 128))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id[:128])
+        _check(lib.rm_comm_init(self._p, buf, 128, C.c_uint32(rank), C.c_uint32(world)))
+
+    def comm_world_size(self) -> int:
+        return int(lib.rm_comm_world_size(self._p))
+
+    def comm_allreduce_sum(self, a: Handle) -> Handle:
+        """Sum of `a` over all ranks (new handle; stream-ordered, waited for lazily at first use)."""
+        out = Handle()
+        _check(lib.rm_comm_allreduce_sum(self._p, C.byref(a), C.byref(out)))
+        return out
+
+    def comm_fence(self) -> None:
+        _check(lib.rm_comm_fence(self._p))
+
     def pci_bus_id(self) -> str:
         buf = C.create_string_buffer(32)
         _check(lib.rm_device_pci_bus_id(self._p, buf, 32))

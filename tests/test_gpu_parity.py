@@ -1145,3 +1145,29 @@ def test_telemetry_counts(prov):
     assert prov.default_reduction_workgroup_size() == 256 and prov.two_pass_threshold() > 0
     with pytest.raises(ProviderError, match="not supported by provider"):
         prov.mldivide(h, h)
+
+
+def test_comm_single_rank_roundtrip():
+    """rm_comm_* with a one-rank communicator: the all-reduce is the identity, results arrive through the lazy ready event,
+    and errors are reported (not raised as crashes) before initialisation."""
+    from runmat_b200 import B200Provider
+
+    with B200Provider(0, device_id=77) as p:
+        x = np.arange(1000, dtype=np.float64).reshape(1000, 1) * 0.5
+        hx = p.upload(x)
+        with pytest.raises(ProviderError, match="rm_comm_init"):
+            p.comm_allreduce_sum(hx)
+        assert p.comm_world_size() == 1
+        p.comm_init(B200Provider.comm_unique_id(), 0, 1)
+        with pytest.raises(ProviderError, match="already"):
+            p.comm_init(B200Provider.comm_unique_id(), 0, 1)
+        outs = [p.comm_allreduce_sum(hx) for _ in range(3)]
+        p.comm_fence()
+        for h in outs:
+            assert h.shape == (1000, 1)
+            assert np.array_equal(p.download(h), x)
+        # the result feeds further device work without an explicit fence (ready-event ordering)
+        hs = p.reduce_sum(p.comm_allreduce_sum(p.scalar_mul(hx, 2.0)))
+        assert p.download(hs)[0, 0] == float(np.sum(x * 2.0))
+        p.free(p.comm_allreduce_sum(hx))  # freed before use: the free is ordered after the collective
+        p.synchronize()
