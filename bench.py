@@ -96,6 +96,8 @@ class ClockSampler:
 
     def start(self):
         try:
+            if os.environ.get("RUNMAT_B200_NO_CLOCK_THREAD"):
+                raise RuntimeError("NVML polling disabled")
             pynvml, h = self._nvml_handle()
             self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             self._pynvml = pynvml
