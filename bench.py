@@ -152,6 +152,9 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+WORKLOAD = "elementwise-math fused chain + sum(), 4096x4096 f64 per GPU (BASELINE.json configs[1])"
+
+
 def synth_inputs(rank: int):
     """Synthetic data of the named shape: A ~ U(0,4pi), B ~ U(-1,1), seeded per rank."""
     rng = np.random.default_rng(1234 + rank)
@@ -197,7 +200,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": "elementwise-math fused chain + sum(), 4096x4096 f64, CPU reference path"},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": BYTES_STEP, "arm": "reference CPU path (oracle port of the unfused builtin sequence), host cores"},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -467,7 +470,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "elementwise-math fused chain + sum(), 4096x4096 f64 per GPU (BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD,
                        "bytes_per_step_per_gpu": BYTES_STEP, "l2": "inputs (2x128 MiB) + output (128 MiB) exceed the 126 MB L2; no flush needed",
                        "parallelism": (f"{world} independent batches, one NCCL all-reduce of 1 f64 per step "
                                        f"({'provider communicator, rm_comm_allreduce_sum' if native_comm else 'torch.distributed'})") if world > 1 else "single GPU",
