@@ -562,10 +562,23 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (owner) {
+  // Last CTA: all 256 threads fold the gridDim.y chunk partials of this CTA's sl slices (a handful of owner threads walking
+  // ~1000 partials each was a ~200 us serial tail on mean(imgs,[2 3])). Thread t walks chunks t/sl, t/sl + W, ... of slice
+  // t % sl in ascending order; the W thread partials of a slice are then folded in thread order: fixed order, deterministic.
+  {
+    const u32 W = 256 / sl;
+    const u32 fs = threadIdx.x % sl, fy = threadIdx.x / sl;
+    const u64 gs = (u64)blockIdx.x * sl + fs;
     double acc2 = IDENT; u32 nan2 = 0;
-    for (u32 y = 0; y < gridDim.y; ++y) { acc2 = COMBINE(acc2, __ldcg(&partial[(u64)y * num_slices + s])); nan2 |= __ldcg(&pflags[(u64)y * num_slices + s]); }
-    out[s] = finish(acc2, nan2 != 0, use_div, factor);
+    if (gs < num_slices)
+      for (u32 y = fy; y < gridDim.y; y += W) { acc2 = COMBINE(acc2, __ldcg(&partial[(u64)y * num_slices + gs])); nan2 |= __ldcg(&pflags[(u64)y * num_slices + gs]); }
+    sacc[threadIdx.x] = acc2;
+    snan[threadIdx.x] = nan2;
+    __syncthreads();
+    if (threadIdx.x < sl && gs < num_slices) {
+      for (u32 w = 1; w < W; ++w) { acc2 = COMBINE(acc2, sacc[w * sl + fs]); nan2 |= snan[w * sl + fs]; }
+      out[gs] = finish(acc2, nan2 != 0, use_div, factor);
+    }
   }
   if (threadIdx.x == 0) tickets[blockIdx.x] = 0;
 }

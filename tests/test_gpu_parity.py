@@ -1171,3 +1171,45 @@ def test_comm_single_rank_roundtrip():
         assert p.download(hs)[0, 0] == float(np.sum(x * 2.0))
         p.free(p.comm_allreduce_sum(hx))  # freed before use: the free is ordered after the collective
         p.synchronize()
+
+
+def test_few_slices_strided_reduction(prov, prov32, orc):
+    """Row-direction reductions with a handful of slices and thousands of rows (many row chunks per slice, folded by the last
+    CTA with all threads): sums/means/max/min, NaN include and omit, ragged row counts, f64 and f32."""
+    rng = np.random.default_rng(515)
+    for P, shape, dims in ((prov, (4, 6001), [1]), (prov, (8, 70, 90), [1, 2]), (prov, (16, 4099), [1]), (prov, (64, 5000), [1]),
+                           (prov32, (8, 5003), [1]), (prov32, (8, 72, 91), [1, 2]), (prov32, (16, 4100), [1])):
+        f32 = P is prov32
+        x = rng.uniform(-1, 1, shape)
+        if f32:
+            x = x.astype(np.float32)
+        h = P.upload(x)
+        want = x.astype(np.float64).sum(axis=tuple(dims), keepdims=True)
+        bound = np.abs(x.astype(np.float64)).sum(axis=tuple(dims), keepdims=True)
+        if len(dims) == 1:
+            got = P.download(P.reduce_sum_dim(h, dims[0]))
+            ref = P.download(P.reduce_sum_dim(h, dims[0]))
+            assert got.shape == want.shape
+            assert np.all(np.abs(got - want) <= (1e-6 if f32 else 1e-10) * bound)
+            assert np.array_equal(got, ref)  # deterministic
+            for is_min in (False, True):
+                vals = (P.reduce_min_dim if is_min else P.reduce_max_dim)(h, dims[0])
+                v = P.download(vals[0] if isinstance(vals, (tuple, list)) else vals)
+                assert np.array_equal(v.reshape(-1), (x.min(axis=1) if is_min else x.max(axis=1)).astype(np.float64).reshape(-1))
+        else:
+            got = P.download(P.reduce_mean_nd(h, dims))
+            n = np.prod([shape[d] for d in dims])
+            assert got.shape == want.shape
+            assert np.all(np.abs(got - want / n) <= (1e-6 if f32 else 1e-10) * bound / n)
+        # NaN include -> NaN in that slice only; omit (fused program) skips it
+        xn = x.copy()
+        xn[(3,) + tuple(5 for _ in shape[1:])] = np.nan
+        hn = P.upload(xn)
+        if len(dims) == 1:
+            g = P.download(P.reduce_sum_dim(hn, 1)).reshape(-1)
+            assert np.isnan(g[3]) and not np.isnan(np.delete(g, 3)).any()
+            X = 0
+            sh = ft.reduction_wgsl([X], [], X, axis=1, omitnan=True, scalar_ty="f32" if f32 else "f64")
+            go = P.download(P.fused_reduction(sh, [hn], (shape[0], 1), shape[1], shape[0])).reshape(-1)
+            wo = np.nansum(xn.astype(np.float64), axis=1)
+            assert np.all(np.abs(go - wo) <= (1e-6 if f32 else 1e-10) * bound.reshape(-1))
