@@ -37,6 +37,83 @@ kats = {
         {"src": "sum.rs:1512-1519 sum_with_include_nan_propagates",
          "a": {"shape": [3, 1], "data": [1, NAN, 3]}, "dims": [0], "omitnan": False, "out": {"shape": [1, 1], "data": [NAN]}},
     ],
+    "mean": [
+        {"src": "runmat-runtime/src/builtins/math/reduction/mean.rs:1695-1705 mean_matrix_default_dimension",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "dims": [0], "omitnan": False, "out": {"shape": [1, 3], "data": [2.5, 3.5, 4.5]}},
+        {"src": "mean.rs:1709-1720 mean_matrix_dimension_two",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "dims": [1], "omitnan": False, "out": {"shape": [2, 1], "data": [2, 5]}},
+        {"src": "mean.rs:1724-1732 mean_with_omit_nan_default_dimension (tol 1e-12)",
+         "a": {"shape": [3, 1], "data": [1, NAN, 5]}, "dims": [0], "omitnan": True, "out": {"shape": [1, 1], "data": [3]}},
+        {"src": "mean.rs:1736-1744 mean_with_omit_nan_all_nan_returns_nan",
+         "a": {"shape": [2, 1], "data": [NAN, NAN]}, "dims": [0], "omitnan": True, "out": {"shape": [1, 1], "data": [NAN]}},
+        {"src": "mean.rs:1748-1756 mean_with_include_nan_propagates_nan",
+         "a": {"shape": [3, 1], "data": [1, NAN, 3]}, "dims": [0], "omitnan": False, "out": {"shape": [1, 1], "data": [NAN]}},
+    ],
+    "prod": [
+        {"src": "runmat-runtime/src/builtins/math/reduction/prod.rs:1248-1258 prod_matrix_default_dimension",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "dims": [0], "out": {"shape": [1, 3], "data": [4, 10, 18]}},
+        {"src": "prod.rs:1262-1273 prod_matrix_dimension_two",
+         "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "dims": [1], "out": {"shape": [2, 1], "data": [6, 120]}},
+        {"src": "prod.rs:1277-1282 prod_all_dimension",
+         "a": {"shape": [2, 3], "data": [1, 2, 3, 4, 5, 6]}, "dims": [0, 1], "out": {"shape": [1, 1], "data": [720]}},
+        {"src": "prod.rs:1286-1301 prod_vecdim_multiple_axes",
+         "a": {"shape": [3, 4, 2], "data": list(range(1, 25))}, "dims": [0, 2], "out": {"shape": [1, 4, 1], "data": [16380, 587520, 4021920, 16030080]}},
+    ],
+    "max_dim": [
+        {"src": "runmat-runtime/src/builtins/math/reduction/max.rs:2471-2477 max_vector_with_indices",
+         "a": {"shape": [3, 1], "data": [3, 1, 5]}, "dim": 0, "values": [5], "indices": [3]},
+        {"src": "max.rs:2608-2625 max_matrix_default_dimension",
+         "a": {"shape": [2, 3], "data": [3, 4, 1, 2, 5, 6]}, "dim": 0, "values": [4, 2, 6], "indices": [2, 2, 2]},
+    ],
+    "find": [
+        {"src": "runmat-runtime/src/builtins/array/indexing/find.rs:885-895 find_linear_indices_basic",
+         "a": {"shape": [2, 3], "data": [0, 4, 0, 7, 0, 9]}, "limit": None, "direction": "first", "linear": [2, 4, 6]},
+        {"src": "find.rs:912-922 find_limited_first", "a": {"shape": [1, 5], "data": [0, 3, 5, 0, 8]}, "limit": 2, "direction": "first", "linear": [2, 3]},
+        {"src": "find.rs:926-936 find_last_single", "a": {"shape": [1, 6], "data": [1, 0, 0, 6, 0, 2]}, "limit": 1, "direction": "last", "linear": [6]},
+        {"src": "find.rs:990-1006 find_multi_output_rows_cols_values", "a": {"shape": [2, 3], "data": [0, 2, 3, 0, 0, 6]}, "limit": None,
+         "direction": "first", "linear": [2, 3, 6], "rows": [2, 1, 2], "cols": [1, 2, 3], "vals": [2, 3, 6]},
+    ],
+    "sub2ind": [
+        {"src": "runmat-runtime/src/builtins/array/indexing/sub2ind.rs:460-465 converts_scalar_indices", "dims": [3, 4],
+         "subs": [{"shape": [1, 1], "data": [2]}, {"shape": [1, 1], "data": [3]}], "out": {"shape": [1, 1], "data": [8]}},
+        {"src": "sub2ind.rs:496-511 broadcasts_scalars_over_vectors", "dims": [3, 4],
+         "subs": [{"shape": [3, 1], "data": [1, 2, 3]}, {"shape": [1, 1], "data": [4]}], "out": {"shape": [3, 1], "data": [10, 11, 12]}},
+        {"src": "sub2ind.rs:515-532 handles_three_dimensions", "dims": [2, 3, 4],
+         "subs": [{"shape": [1, 2], "data": [1, 1]}, {"shape": [1, 2], "data": [2, 3]}, {"shape": [1, 2], "data": [1, 2]}],
+         "out": {"shape": [1, 2], "data": [3, 11]}},
+        {"src": "sub2ind.rs:536-549 rejects_out_of_range_subscripts", "dims": [3, 4],
+         "subs": [{"shape": [1, 1], "data": [4]}, {"shape": [1, 1], "data": [1]}], "error": "Index exceeds"},
+    ],
+    "ind2sub": [
+        {"src": "runmat-runtime/src/builtins/array/indexing/ind2sub.rs:376-388 recovers_tensor_indices", "dims": [3, 4],
+         "idx": {"shape": [1, 1], "data": [8]}, "out": [[2], [3]]},
+        {"src": "ind2sub.rs:406-432 handles_vector_indices", "dims": [3, 5], "idx": {"shape": [1, 3], "data": [7, 8, 9]},
+         "out": [[1, 2, 3], [3, 3, 3]]},
+        {"src": "ind2sub.rs:460-484 recovers_three_dimensional_indices", "dims": [2, 3, 4], "idx": {"shape": [1, 2], "data": [3, 11]},
+         "out": [[1, 1], [2, 3], [1, 2]]},
+    ],
+    "permute": [
+        {"src": "runmat-runtime/src/builtins/array/shape/permute.rs:619-631 permute_swaps_dims (shape only in the reference test)",
+         "a": {"shape": [2, 3, 4], "data": list(range(1, 25))}, "order": [2, 1, 3], "out_shape": [3, 2, 4]},
+        {"src": "permute.rs:635-645 permute_adds_trailing_dimension", "a": {"shape": [1, 3], "data": [1, 2, 3]}, "order": [2, 1, 3], "out_shape": [3, 1, 1]},
+    ],
+    "repmat": [
+        {"src": "runmat-runtime/src/builtins/array/shape/repmat.rs:755-781 repeats_matrix_with_vector_reps",
+         "a": {"shape": [2, 2], "data": [1, 3, 2, 4]}, "reps": [2, 3],
+         "out": {"shape": [4, 6], "data": [1, 3, 1, 3, 2, 4, 2, 4] * 3}},
+        {"src": "repmat.rs:812-844 repmat_high_dim_numeric (out[i,j,k] = base[j%3 + 3*(k%2)])",
+         "a": {"shape": [1, 3, 2], "data": [0, 1, 2, 3, 4, 5]}, "reps": [2, 1, 3],
+         "out": {"shape": [2, 3, 6], "data": [float((j % 3) + 3 * (k % 2)) for k in range(6) for j in range(3) for _ in range(2)]}},
+    ],
+    "cat": [
+        {"src": "runmat-runtime/src/builtins/array/shape/cat.rs:1305-1320 cat_numeric_rows", "dim": 1,
+         "inputs": [{"shape": [2, 2], "data": [1, 3, 2, 4]}, {"shape": [2, 2], "data": [5, 7, 6, 8]}],
+         "out": {"shape": [4, 2], "data": [1, 3, 5, 7, 2, 4, 6, 8]}},
+    ],
+    "eye": [
+        {"src": "runmat-runtime/src/builtins/array/creation/eye.rs:597-617 eye_rectangular_from_two_dims", "rows": 2, "cols": 4,
+         "out": {"shape": [2, 4], "data": [1, 0, 0, 1, 0, 0, 0, 0]}},
+    ],
     "matmul": [
         {"src": "runmat-runtime/src/builtins/math/linalg/ops/mtimes.rs:495-507 matrix_product_matches_expected",
          "a": {"shape": [2, 3], "data": [1, 4, 2, 5, 3, 6]}, "b": {"shape": [3, 2], "data": [7, 9, 11, 8, 10, 12]},

@@ -173,3 +173,99 @@ def test_conv2d_reference_kats(orc):
     assert_same(orc.conv2d(a33, np.ones((3, 3)), "valid"), np.array([[45.0]]))                                  # :803 conv2_valid_returns_expected_sum
     assert_same(orc.conv2d(a33, rows(2, 2, [1, 2, 3, 4]), "same"), rows(3, 3, [4, 11, 18, 18, 37, 47, 36, 67, 77]))  # :948 even kernel alignment
     assert orc.conv2d(np.ones((2, 2)), np.ones((3, 3)), "valid").size == 0
+
+
+# ---- reductions beyond sum: literals from mean.rs / prod.rs / max.rs ---------------------------------------------------
+def _mean_dims(orc, a, dims, omit):
+    """mean.rs:1121-1154: sum of the kept elements / their count (omitnan: count of non-NaN; an all-NaN slice gives NaN)."""
+    s = orc.sum_dims(a, dims, omit_nan=omit)
+    if omit:
+        cnt = orc.sum_dims((~np.isnan(a)).astype(np.float64), dims)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(cnt > 0, s / cnt, np.nan)
+    n = np.prod([a.shape[d] for d in dims])
+    return s / n
+
+
+def test_mean_kats(orc):
+    for k in KATS["mean"]:
+        a = arr(k["a"])
+        assert_same(_mean_dims(orc, a, k["dims"], k["omitnan"]), arr(k["out"]), tol=1e-12 if k["omitnan"] else 0.0)
+        if not k["omitnan"] and len(k["dims"]) == a.ndim:
+            assert_same(np.array(orc.reduce_mean(a)), arr(k["out"]).reshape(()))
+
+
+def test_prod_kats(orc):
+    for k in KATS["prod"]:
+        a, want = arr(k["a"]), arr(k["out"])
+        keep = [d for d in range(a.ndim) if d not in k["dims"]]
+        moved = np.transpose(a, keep + list(k["dims"]))  # slices first, reduced dims last; column-major order inside a slice
+        got = np.array([orc.reduce_prod(np.asfortranarray(moved[idx]).reshape(-1, order="F")) for idx in np.ndindex(*[a.shape[d] for d in keep])])
+        assert_same(got.reshape(want.shape, order="F") if keep else got.reshape(want.shape), want)
+
+
+def test_max_dim_kats_values_and_first_index(orc):
+    for k in KATS["max_dim"]:
+        a = arr(k["a"])
+        vals, idx = orc.reduce_minmax_dim(a, k["dim"], is_min=False)
+        assert_same(vals.reshape(-1), np.array(k["values"], dtype=np.float64))
+        assert_same(idx.reshape(-1), np.array(k["indices"], dtype=np.float64))  # 1-based, first occurrence
+
+
+# ---- indexing / layout class: numpy restatement (oracle/layout_ops.py) pinned to the reference's literals ----------------
+import importlib.util as _ilu
+from pathlib import Path as _Path
+
+_spec = _ilu.spec_from_file_location("layout_ops", _Path(__file__).resolve().parent.parent / "oracle" / "layout_ops.py")
+layout_ops = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(layout_ops)
+
+
+def test_find_kats():
+    for k in KATS["find"]:
+        lin, rows, cols, vals = layout_ops.find(arr(k["a"]), limit=k["limit"], direction=k["direction"])
+        assert lin.tolist() == [float(v) for v in k["linear"]]
+        if "rows" in k:
+            assert rows.tolist() == k["rows"] and cols.tolist() == k["cols"] and vals.tolist() == k["vals"]
+    lin, *_ = layout_ops.find(np.array([[0.0, np.nan], [-0.0, 1e-300]]))  # NaN and denormals are non-zero, -0.0 is zero
+    assert lin.tolist() == [3.0, 4.0]
+    assert layout_ops.find(np.zeros((3, 2)))[0].size == 0 and layout_ops.find(np.ones((2, 2)), limit=0)[0].size == 0
+
+
+def test_sub2ind_ind2sub_kats():
+    for k in KATS["sub2ind"]:
+        subs = [arr(s) for s in k["subs"]]
+        if "error" in k:
+            with pytest.raises(ValueError, match=k["error"]):
+                layout_ops.sub2ind(k["dims"], subs)
+            continue
+        assert_same(layout_ops.sub2ind(k["dims"], subs), arr(k["out"]))
+    for k in KATS["ind2sub"]:
+        outs = layout_ops.ind2sub(k["dims"], arr(k["idx"]))
+        assert len(outs) == len(k["dims"])
+        for o, w in zip(outs, k["out"]):
+            assert o.shape == tuple(k["idx"]["shape"]) and o.reshape(-1, order="F").tolist() == [float(v) for v in w]
+    # round trip and error wording (ind2sub.rs:326-352)
+    dims = [4, 3, 5]
+    idx = np.arange(1, 61, dtype=np.float64).reshape(6, 10, order="F")
+    assert_same(layout_ops.sub2ind(dims, layout_ops.ind2sub(dims, idx)), idx)
+    for bad, msg in ((0.0, "positive integers"), (2.5, "positive integers"), (61.0, "must not exceed 60")):
+        with pytest.raises(ValueError, match=msg):
+            layout_ops.ind2sub(dims, np.array([[bad]]))
+
+
+def test_permute_repmat_cat_eye_kats():
+    for k in KATS["permute"]:
+        a = arr(k["a"])
+        out = layout_ops.permute(a, k["order"])
+        assert list(out.shape) == k["out_shape"]
+        inv = np.argsort([o - 1 for o in k["order"]])
+        assert np.array_equal(np.transpose(out, inv).reshape(-1, order="F")[: a.size], a.reshape(-1, order="F"))
+    for k in KATS["repmat"]:
+        assert_same(layout_ops.repmat(arr(k["a"]), k["reps"]), arr(k["out"]))
+    for k in KATS["cat"]:
+        assert_same(layout_ops.cat(k["dim"], [arr(x) for x in k["inputs"]]), arr(k["out"]))
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        layout_ops.cat(1, [np.zeros((2, 2)), np.zeros((2, 3))])
+    for k in KATS["eye"]:
+        assert_same(layout_ops.eye(k["rows"], k["cols"]), arr(k["out"]))
