@@ -317,12 +317,17 @@ def run_ours(args):
     sync_all()
     p.timer_begin()
     last_sum = None
+    in_flight = []  # N>1: a step's global sum is consumed (freed) SUM_DEPTH steps later, so its all-reduce has that much slack
+    SUM_DEPTH = 4 if world > 1 else 1
     for _ in range(args.steps):
         hC, hS = step()
         p.free(hC)
-        if last_sum is not None:
-            p.free(last_sum)
-        last_sum = hS
+        in_flight.append(hS)
+        if len(in_flight) > SUM_DEPTH:
+            p.free(in_flight.pop(0))
+    last_sum = in_flight.pop()
+    for h in in_flight:
+        p.free(h)
     if native_comm:
         p.comm_fence()  # the timed region ends when the last all-reduce has landed
     elif world > 1:
