@@ -1213,3 +1213,73 @@ def test_few_slices_strided_reduction(prov, prov32, orc):
             go = P.download(P.fused_reduction(sh, [hn], (shape[0], 1), shape[1], shape[0])).reshape(-1)
             wo = np.nansum(xn.astype(np.float64), axis=1)
             assert np.all(np.abs(go - wo) <= (1e-6 if f32 else 1e-10) * bound.reshape(-1))
+
+
+def test_reference_kats_through_the_abi(prov):
+    """The reference's own literal test vectors (tests/golden/reference_kats.json: find.rs, sub2ind.rs, ind2sub.rs, permute.rs,
+    repmat.rs, cat.rs, eye.rs, mean.rs, prod.rs, max.rs) through the C ABI. Where a reference test only asserts shapes, the
+    expected array comes from oracle/layout_ops.py, which the CPU suite pins to the same literals."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("layout_ops", Path(__file__).resolve().parent.parent / "oracle" / "layout_ops.py")
+    lo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lo)
+
+    def col_major_strides(dims):
+        st, acc = [], 1
+        for d in dims:
+            st.append(acc)
+            acc *= d
+        return st
+
+    for k in KATS["find"]:
+        res = prov.find(prov.upload(arr(k["a"])), limit=k["limit"], direction=k["direction"])
+        lin, rows, cols, vals = (prov.download(r).reshape(-1) for r in res)
+        assert lin.tolist() == [float(v) for v in k["linear"]], k["src"]
+        if "rows" in k:
+            assert rows.tolist() == [float(v) for v in k["rows"]] and cols.tolist() == [float(v) for v in k["cols"]]
+            assert vals.tolist() == [float(v) for v in k["vals"]]
+    for k in KATS["sub2ind"]:
+        subs = [arr(x) for x in k["subs"]]
+        n = max(x.size for x in subs)
+        mask = [x.size == 1 and n > 1 for x in subs]
+        oshape = next((x.shape for x in subs if x.size == n), (1, 1))
+        hs = [prov.upload(x) for x in subs]
+        if "error" in k:
+            with pytest.raises(ProviderError, match="exceeds"):
+                prov.sub2ind(k["dims"], col_major_strides(k["dims"]), hs, mask, n, oshape)
+            continue
+        got = prov.download(prov.sub2ind(k["dims"], col_major_strides(k["dims"]), hs, mask, n, oshape))
+        assert_same(got, arr(k["out"]))
+    for k in KATS["ind2sub"]:
+        idx = arr(k["idx"])
+        outs = prov.ind2sub(k["dims"], col_major_strides(k["dims"]), prov.upload(idx), int(np.prod(k["dims"])), idx.size, idx.shape)
+        assert len(outs) == len(k["dims"])
+        for h, want in zip(outs, k["out"]):
+            assert prov.download(h).reshape(-1, order="F").tolist() == [float(v) for v in want], k["src"]
+    for k in KATS["permute"]:
+        a = arr(k["a"])
+        if len(k["order"]) != a.ndim:
+            continue  # order longer than the rank (adds a trailing dim) is resolved by the builtin before it reaches a provider
+        got = prov.download(prov.permute(prov.upload(a), [o - 1 for o in k["order"]]))
+        assert list(got.shape) == k["out_shape"]
+        assert np.array_equal(got, lo.permute(a, k["order"]))
+    for k in KATS["repmat"]:
+        assert_same(prov.download(prov.repmat(prov.upload(arr(k["a"])), k["reps"])), arr(k["out"]))
+    for k in KATS["cat"]:
+        assert_same(prov.download(prov.cat(k["dim"], [prov.upload(arr(x)) for x in k["inputs"]])), arr(k["out"]))
+    for k in KATS["eye"]:
+        assert_same(prov.download(prov.eye((k["rows"], k["cols"]))), arr(k["out"]))
+    for k in KATS["mean"]:
+        if k["omitnan"] or len(k["dims"]) != 1:
+            continue  # omitnan goes through fused_reduction (covered by test_fused_reduction_axes_omitnan_mean)
+        assert_same(prov.download(prov.reduce_mean_dim(prov.upload(arr(k["a"])), k["dims"][0])), arr(k["out"]))
+    for k in KATS["prod"]:
+        a = arr(k["a"])
+        if len(k["dims"]) == a.ndim:  # the trait only has the 'all' product (lib.rs:2733)
+            assert prov.download(prov.reduce_prod(prov.upload(a)))[0, 0] == arr(k["out"]).reshape(-1)[0]
+    for k in KATS["max_dim"]:
+        v, i = prov.reduce_max_dim(prov.upload(arr(k["a"])), k["dim"])
+        assert prov.download(v).reshape(-1).tolist() == [float(x) for x in k["values"]]
+        assert prov.download(i).reshape(-1).tolist() == [float(x) for x in k["indices"]]
