@@ -9,8 +9,10 @@
 use anyhow::{anyhow, Result};
 use runmat_accelerate_api::{
     AccelDownloadFuture, AccelProvider, AccelProviderFuture, ApiDeviceInfo, GpuTensorHandle, GpuTensorStorage,
-    HostTensorOwned, HostTensorView, ImageNormalizeDescriptor, MatmulEpilogue, ProviderPrecision, ProviderTelemetry,
-    ProviderDispatchStats, ReduceDimResult, ReductionFlavor, ScaleOp,
+    CovNormalization, CovRows, CovarianceOptions, FindDirection, HostTensorOwned, HostTensorView, ImageNormalizeDescriptor,
+    ImfilterMode, ImfilterOptions, ImfilterPadding, ImfilterShape, MatmulEpilogue, PowerStepEpilogue, ProviderConvMode,
+    ProviderDispatchStats, ProviderFindResult, ProviderMoments2, ProviderPrecision, ProviderTelemetry, ReduceDimResult,
+    ReductionFlavor, ScaleOp,
 };
 use std::ffi::{c_char, c_int, c_void, CStr, CString};
 
@@ -55,6 +57,14 @@ pub struct RmImageNormalizeDesc {
     pub has_gamma: c_int,
     pub gamma: f64,
     pub clamp_zero: c_int,
+}
+
+#[repr(C)]
+pub struct RmImfilterOptions {
+    pub padding: c_int,        // rm_imfilter_padding: constant, replicate, symmetric, circular
+    pub constant_value: f64,
+    pub shape: c_int,          // rm_imfilter_shape: same, full, valid
+    pub mode: c_int,           // rm_imfilter_mode: correlation, convolution
 }
 
 #[repr(C)]
@@ -114,6 +124,32 @@ extern "C" {
     fn rm_telemetry_snapshot(p: *mut c_void, out: *mut RmTelemetry) -> c_int;
     fn rm_reset_telemetry(p: *mut c_void) -> c_int;
     fn rm_fused_cache_counters(p: *mut c_void, hits: *mut u64, misses: *mut u64);
+    // "next" rows: solves, indexing/layout class, fusion-pattern hooks, filters
+    fn rm_mldivide(p: *mut c_void, lhs: *const RmHandle, rhs: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_mrdivide(p: *mut c_void, lhs: *const RmHandle, rhs: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_syrk(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_matmul_power_step(p: *mut c_void, lhs: *const RmHandle, rhs: *const RmHandle, epsilon: f64, out: *mut RmHandle) -> c_int;
+    fn rm_covariance(p: *mut c_void, m: *const RmHandle, normalization_biased: c_int, out: *mut RmHandle) -> c_int;
+    fn rm_diag_extract(p: *mut c_void, m: *const RmHandle, offset: i64, out: *mut RmHandle) -> c_int;
+    fn rm_imfilter(p: *mut c_void, image: *const RmHandle, kernel: *const RmHandle, opt: *const RmImfilterOptions, out: *mut RmHandle) -> c_int;
+    fn rm_conv2d(p: *mut c_void, signal: *const RmHandle, kernel: *const RmHandle, mode: c_int, out: *mut RmHandle) -> c_int;
+    fn rm_permute(p: *mut c_void, a: *const RmHandle, order: *const u32, n: u32, out: *mut RmHandle) -> c_int;
+    fn rm_repmat(p: *mut c_void, a: *const RmHandle, reps: *const u64, n: u32, out: *mut RmHandle) -> c_int;
+    fn rm_cat(p: *mut c_void, dim_one_based: u32, inputs: *const RmHandle, n: u32, out: *mut RmHandle) -> c_int;
+    fn rm_eye(p: *mut c_void, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_find(p: *mut c_void, a: *const RmHandle, has_limit: c_int, limit: u64, direction_last: c_int,
+               linear: *mut RmHandle, rows: *mut RmHandle, cols: *mut RmHandle, values: *mut RmHandle) -> c_int;
+    fn rm_scatter_column(p: *mut c_void, m: *const RmHandle, col: u64, values: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_scatter_row(p: *mut c_void, m: *const RmHandle, row: u64, values: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_sub2ind(p: *mut c_void, dims: *const u64, strides: *const u64, ndims: u32, inputs: *const RmHandle, scalar_mask: *const u8,
+                  len: u64, output_shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_ind2sub(p: *mut c_void, dims: *const u64, strides: *const u64, ndims: u32, indices: *const RmHandle, total: u64, len: u64,
+                  output_shape: *const u64, rank: u32, outs: *mut RmHandle) -> c_int;
+    fn rm_reduce_prod(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_mean_dim(p: *mut c_void, a: *const RmHandle, dim: u32, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_mean_nd(p: *mut c_void, a: *const RmHandle, dims: *const u32, n: u32, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_moments_nd(p: *mut c_void, a: *const RmHandle, dims: *const u32, n: u32, mean: *mut RmHandle, ex2: *mut RmHandle) -> c_int;
+    fn rm_warmup(p: *mut c_void) -> c_int;
 }
 
 pub struct CudaProvider {
@@ -375,6 +411,140 @@ impl AccelProvider for CudaProvider {
         Ok(from_raw(&out))
     }
     fn set_rng_state(&self, state: u64) -> Result<()> { check(unsafe { rm_set_rng_state(self.raw, state) }) }
+
+    // ---- "next" rows: every method below is again a 1:1 forward -------------------------------------------------
+    fn mldivide<'a>(&'a self, lhs: &'a GpuTensorHandle, rhs: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        // RM_UNSUPPORTED (least-squares / singular / ill-conditioned) surfaces as Err => host SVD path, as with wgpu today
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_mldivide(self.raw, &to_raw(lhs)?, &to_raw(rhs)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn mrdivide<'a>(&'a self, lhs: &'a GpuTensorHandle, rhs: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_mrdivide(self.raw, &to_raw(lhs)?, &to_raw(rhs)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn syrk(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_syrk(self.raw, &to_raw(a)?, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn matmul_power_step<'a>(&'a self, lhs: &'a GpuTensorHandle, rhs: &'a GpuTensorHandle, ep: &'a PowerStepEpilogue) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_matmul_power_step(self.raw, &to_raw(lhs)?, &to_raw(rhs)?, ep.epsilon, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn covariance<'a>(&'a self, matrix: &'a GpuTensorHandle, second: Option<&'a GpuTensorHandle>, weights: Option<&'a GpuTensorHandle>,
+                      options: &'a CovarianceOptions) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({
+            if second.is_some() || weights.is_some() || options.has_weight_vector || options.rows != CovRows::All {
+                return Err(anyhow!("covariance: this form is not supported by provider"));  // host fallback
+            }
+            let mut out = empty_raw();
+            check(unsafe { rm_covariance(self.raw, &to_raw(matrix)?, (options.normalization == CovNormalization::Biased) as c_int, &mut out) })?;
+            Ok(from_raw(&out))
+        })
+    }
+    fn diag_extract(&self, matrix: &GpuTensorHandle, offset: isize) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_diag_extract(self.raw, &to_raw(matrix)?, offset as i64, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn imfilter<'a>(&'a self, image: &'a GpuTensorHandle, kernel: &'a GpuTensorHandle, o: &'a ImfilterOptions) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({
+            let raw = RmImfilterOptions {
+                padding: match o.padding { ImfilterPadding::Constant => 0, ImfilterPadding::Replicate => 1, ImfilterPadding::Symmetric => 2, ImfilterPadding::Circular => 3 },
+                constant_value: o.constant_value,
+                shape: match o.shape { ImfilterShape::Same => 0, ImfilterShape::Full => 1, ImfilterShape::Valid => 2 },
+                mode: match o.mode { ImfilterMode::Correlation => 0, ImfilterMode::Convolution => 1 },
+            };
+            let mut out = empty_raw();
+            check(unsafe { rm_imfilter(self.raw, &to_raw(image)?, &to_raw(kernel)?, &raw, &mut out) })?;
+            Ok(from_raw(&out))
+        })
+    }
+    fn conv2d(&self, signal: &GpuTensorHandle, kernel: &GpuTensorHandle, mode: ProviderConvMode) -> Result<GpuTensorHandle> {
+        let m = match mode { ProviderConvMode::Full => 0, ProviderConvMode::Same => 1, ProviderConvMode::Valid => 2 };
+        let mut out = empty_raw();
+        check(unsafe { rm_conv2d(self.raw, &to_raw(signal)?, &to_raw(kernel)?, m, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn permute(&self, handle: &GpuTensorHandle, order: &[usize]) -> Result<GpuTensorHandle> {
+        let o: Vec<u32> = order.iter().map(|&d| d as u32).collect();  // zero-based, as the trait passes it
+        let mut out = empty_raw();
+        check(unsafe { rm_permute(self.raw, &to_raw(handle)?, o.as_ptr(), o.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn repmat(&self, handle: &GpuTensorHandle, reps: &[usize]) -> Result<GpuTensorHandle> {
+        let r: Vec<u64> = reps.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_repmat(self.raw, &to_raw(handle)?, r.as_ptr(), r.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn cat(&self, dim: usize, inputs: &[GpuTensorHandle]) -> Result<GpuTensorHandle> {
+        let raws: Vec<RmHandle> = inputs.iter().map(to_raw).collect::<Result<_>>()?;
+        let mut out = empty_raw();
+        check(unsafe { rm_cat(self.raw, dim as u32, raws.as_ptr(), raws.len() as u32, &mut out) })?;  // dim is one-based (lib.rs:2686)
+        Ok(from_raw(&out))
+    }
+    fn eye(&self, shape: &[usize]) -> Result<GpuTensorHandle> {
+        let s: Vec<u64> = shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_eye(self.raw, s.as_ptr(), s.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn find(&self, a: &GpuTensorHandle, limit: Option<usize>, direction: FindDirection) -> Result<ProviderFindResult> {
+        let (mut lin, mut rows, mut cols, mut vals) = (empty_raw(), empty_raw(), empty_raw(), empty_raw());
+        check(unsafe {
+            rm_find(self.raw, &to_raw(a)?, limit.is_some() as c_int, limit.unwrap_or(0) as u64, (direction == FindDirection::Last) as c_int,
+                    &mut lin, &mut rows, &mut cols, &mut vals)
+        })?;
+        Ok(ProviderFindResult { linear: from_raw(&lin), rows: from_raw(&rows), cols: from_raw(&cols), values: Some(from_raw(&vals)) })
+    }
+    fn scatter_column(&self, matrix: &GpuTensorHandle, col_index: usize, values: &GpuTensorHandle) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_scatter_column(self.raw, &to_raw(matrix)?, col_index as u64, &to_raw(values)?, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn scatter_row(&self, matrix: &GpuTensorHandle, row_index: usize, values: &GpuTensorHandle) -> Result<GpuTensorHandle> {
+        let mut out = empty_raw();
+        check(unsafe { rm_scatter_row(self.raw, &to_raw(matrix)?, row_index as u64, &to_raw(values)?, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn sub2ind(&self, dims: &[usize], strides: &[usize], inputs: &[&GpuTensorHandle], scalar_mask: &[bool], len: usize, output_shape: &[usize]) -> Result<GpuTensorHandle> {
+        let (d, st): (Vec<u64>, Vec<u64>) = (dims.iter().map(|&v| v as u64).collect(), strides.iter().map(|&v| v as u64).collect());
+        let raws: Vec<RmHandle> = inputs.iter().map(|h| to_raw(h)).collect::<Result<_>>()?;
+        let mask: Vec<u8> = scalar_mask.iter().map(|&b| b as u8).collect();
+        let os: Vec<u64> = output_shape.iter().map(|&v| v as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_sub2ind(self.raw, d.as_ptr(), st.as_ptr(), d.len() as u32, raws.as_ptr(), mask.as_ptr(), len as u64, os.as_ptr(), os.len() as u32, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn supports_ind2sub(&self) -> bool { true }
+    fn ind2sub(&self, dims: &[usize], strides: &[usize], indices: &GpuTensorHandle, total: usize, len: usize, output_shape: &[usize]) -> Result<Vec<GpuTensorHandle>> {
+        let (d, st): (Vec<u64>, Vec<u64>) = (dims.iter().map(|&v| v as u64).collect(), strides.iter().map(|&v| v as u64).collect());
+        let os: Vec<u64> = output_shape.iter().map(|&v| v as u64).collect();
+        let mut outs = vec![empty_raw(); d.len()];
+        check(unsafe { rm_ind2sub(self.raw, d.as_ptr(), st.as_ptr(), d.len() as u32, &to_raw(indices)?, total as u64, len as u64, os.as_ptr(), os.len() as u32, outs.as_mut_ptr()) })?;
+        Ok(outs.iter().map(from_raw).collect())
+    }
+    fn reduce_prod<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_prod(self.raw, &to_raw(a)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_mean_dim<'a>(&'a self, a: &'a GpuTensorHandle, dim: usize) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_mean_dim(self.raw, &to_raw(a)?, dim as u32, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_mean_nd<'a>(&'a self, a: &'a GpuTensorHandle, dims_zero_based: &'a [usize]) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({
+            let d: Vec<u32> = dims_zero_based.iter().map(|&v| v as u32).collect();
+            let mut out = empty_raw();
+            check(unsafe { rm_reduce_mean_nd(self.raw, &to_raw(a)?, d.as_ptr(), d.len() as u32, &mut out) })?;
+            Ok(from_raw(&out))
+        })
+    }
+    fn reduce_moments_nd<'a>(&'a self, a: &'a GpuTensorHandle, dims_zero_based: &'a [usize]) -> AccelProviderFuture<'a, ProviderMoments2> {
+        ready!({
+            let d: Vec<u32> = dims_zero_based.iter().map(|&v| v as u32).collect();
+            let (mut mean, mut ex2) = (empty_raw(), empty_raw());
+            check(unsafe { rm_reduce_moments_nd(self.raw, &to_raw(a)?, d.as_ptr(), d.len() as u32, &mut mean, &mut ex2) })?;
+            Ok(ProviderMoments2 { mean: from_raw(&mean), ex2: from_raw(&ex2) })
+        })
+    }
+    fn warmup(&self) { unsafe { rm_warmup(self.raw) }; }
 
     fn telemetry_snapshot(&self) -> ProviderTelemetry {
         let mut t = RmTelemetry::default();
