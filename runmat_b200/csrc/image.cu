@@ -96,6 +96,61 @@ moments_partial_vec_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, 
   }
 }
 
+// Same sweep with a deterministic, atomic-free finish (r04 harness, scripts/img_dev/moments_variants.cu: 41.4 us vs 88.3 us on
+// [8,2160,3840] f32; the atomic version ended every thread with 2*VEC shared-memory f64 atomics onto 2*B addresses, 128-way
+// contended, and summed in arrival order). Consecutive threads own consecutive vectors, so the lanes of a warp cycle through
+// the G = B / VEC image groups with period G. For G a power of two <= 32 an xor-butterfly over the offsets 16 .. G folds exactly
+// the lanes that share a group; lanes 0 .. G-1 then publish per-warp slots and the slots are folded in warp order.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+moments_partial_fold_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, double* __restrict__ partial /*[grid][2][B]*/) {
+  extern __shared__ double shw[];  // [8 warps][2][B]
+  const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t b0 = (uint32_t)((v0 * VEC) % B);  // fixed for this thread: (nthr*VEC) %% B == 0
+  double K[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int l = 0; l < VEC; ++l) { K[l] = (double)x[b0 + l]; s1[l] = 0.0; s2[l] = 0.0; }
+  typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
+  const V* xv = reinterpret_cast<const V*>(x);
+  uint64_t v = v0;
+  for (; v + 7 * nthr < nvec; v += 8 * nthr) {
+    V a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const T* e = reinterpret_cast<const T*>(&a[u]);
+#pragma unroll
+      for (int l = 0; l < VEC; ++l) { const double d = (double)e[l] - K[l]; s1[l] += d; s2[l] += d * d; }
+    }
+  }
+  for (; v < nvec; v += nthr) {
+    const V a = __ldcs(xv + v);
+    const T* e = reinterpret_cast<const T*>(&a);
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) { const double d = (double)e[l] - K[l]; s1[l] += d; s2[l] += d * d; }
+  }
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = B / VEC;
+#pragma unroll
+  for (int l = 0; l < VEC; ++l)
+    for (uint32_t off = 16; off >= G && off > 0; off >>= 1) {
+      s1[l] += __shfl_xor_sync(0xffffffffu, s1[l], off);
+      s2[l] += __shfl_xor_sync(0xffffffffu, s2[l], off);
+    }
+  if (lane < G) {
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) { shw[(warp * 2 + 0) * B + b0 + l] = s1[l]; shw[(warp * 2 + 1) * B + b0 + l] = s2[l]; }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < 2 * B; i += blockDim.x) {
+    const uint32_t m = i / B, b = i % B;
+    double t = 0.0;
+    for (uint32_t w = 0; w < 8; ++w) t += shw[(w * 2 + m) * B + b];  // warp order: deterministic
+    partial[((uint64_t)blockIdx.x * 2 + m) * B + b] = t;
+  }
+}
+
 // stats[b] = {mean, inv_sigma}. One CTA per image: threads stride over the per-block partials, fixed-order tree in
 // shared memory (deterministic).
 template <typename T>
@@ -491,8 +546,13 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   const size_t sh = fast_blocks ? (size_t)2 * B * sizeof(double) : (size_t)lanes * 2 * B * sizeof(double);
   NormParams np{d->has_gain, d->has_bias, d->has_gamma, d->clamp_zero, d->gain, d->bias, d->gamma};
   const unsigned ngrid = (unsigned)std::min<uint64_t>((total / 4 + 255) / 256 + 1, (uint64_t)sms * 16);
+  const uint64_t groups = B / (uint64_t)VEC;  // image groups a warp's lanes cycle through on the fast path
+  const bool fold = fast_blocks && B % VEC == 0 && groups >= 1 && groups <= 32 && (groups & (groups - 1)) == 0 && !getenv("RUNMAT_B200_MOMENTS_ATOMIC");
+  const size_t sh_fold = (size_t)8 * 2 * B * sizeof(double);
   if (p->precision == RM_F64) {
-    if (fast_blocks) {
+    if (fold) {
+      moments_partial_fold_kernel<double, 2><<<nblocks, 256, sh_fold, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
+    } else if (fast_blocks) {
       moments_partial_vec_kernel<double, 2><<<nblocks, 256, sh, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
     } else {
       cudaFuncSetAttribute(moments_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
@@ -502,7 +562,9 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
     if (fast_blocks) normalize_fixed_kernel<double, 2><<<fast_blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, (uint32_t)B, total, stats, np);
     else normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
   } else {
-    if (fast_blocks) {
+    if (fold) {
+      moments_partial_fold_kernel<float, 4><<<nblocks, 256, sh_fold, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
+    } else if (fast_blocks) {
       moments_partial_vec_kernel<float, 4><<<nblocks, 256, sh, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
     } else {
       cudaFuncSetAttribute(moments_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
