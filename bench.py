@@ -153,6 +153,9 @@ class ClockSampler:
 
 
 WORKLOAD = "elementwise-math fused chain + sum(), 4096x4096 f64 per GPU (BASELINE.json configs[1])"
+# identical in both arms (the driver compares the dicts); per-arm details live in the sibling key "run"
+CONFIG = {"workload": WORKLOAD, "bytes_per_step_per_gpu": BYTES_STEP,
+          "l2": "inputs (2x128 MiB) + output (128 MiB) per step exceed the 126 MB L2; no flush needed between iterations"}
 
 
 def synth_inputs(rank: int):
@@ -200,7 +203,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": BYTES_STEP, "arm": "reference CPU path (oracle port of the unfused builtin sequence), host cores"},
+        "data": "synthetic", "config": CONFIG,
+        "run": {"arm": "reference CPU path (oracle port of the unfused builtin sequence), host cores"},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,6 +216,114 @@ def run_reference(args):
 # =====================================================================================================================
 # our arm
 # =====================================================================================================================
+class Exchange:
+    """The sharded paths' only exchange: the sum of one scalar per rank. Preference order:
+    'p2p'   peer-memory slots over NVLink (rm_comm_p2p_*: publish fused into the producing kernel, lazy combine),
+    'nccl'  the provider's own NCCL communicator (rm_comm_allreduce_sum),
+    'torch' torch.distributed on a side stream.
+    Every rank takes the same branch (agreed with a MIN all-reduce)."""
+
+    def __init__(self, p, rank, world, local_rank, dist, torch, label=""):
+        self.p, self.rank, self.world, self.local_rank, self.dist, self.torch = p, rank, world, local_rank, dist, torch
+        self.kind = "none"
+        if world == 1:
+            return
+        dev = f"cuda:{local_rank}"
+
+        def agree(ok):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return bool(flag.item())
+
+        def probe():
+            h = p.upload(np.array([float(rank + 1)]), (1, 1))
+            got = float(p.download(p.comm_allreduce_sum(h))[0, 0])
+            p.free(h)
+            return got == world * (world + 1) / 2
+
+        if not os.environ.get("RUNMAT_B200_NO_P2P") and not os.environ.get("RUNMAT_B200_TORCH_ALLREDUCE"):
+            ok = True
+            try:
+                mine = p.comm_p2p_export()
+                handles = [None] * world
+                dist.all_gather_object(handles, mine)
+                p.comm_p2p_connect(handles, rank, world)
+                ok = probe() and probe()
+            except Exception as exc:  # noqa: BLE001 - any failure selects the next exchange on ALL ranks
+                print(f"[bench{label}] rank {rank}: peer-memory exchange unavailable ({exc})", file=sys.stderr)
+                ok = False
+            if agree(ok):
+                self.kind = "p2p"
+                return
+        if not os.environ.get("RUNMAT_B200_TORCH_ALLREDUCE") and not p.comm_p2p_connected():
+            ok = True
+            try:
+                from runmat_b200 import B200Provider
+
+                ident = [B200Provider.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ident, src=0)
+                p.comm_init(ident[0], rank, world)
+                ok = probe()
+            except Exception as exc:  # noqa: BLE001
+                print(f"[bench{label}] rank {rank}: native NCCL communicator unavailable ({exc}); using torch.distributed", file=sys.stderr)
+                ok = False
+            if agree(ok):
+                self.kind = "nccl"
+                return
+        self.kind = "torch"
+        self.prov_stream = torch.cuda.ExternalStream(p.stream(), device=dev)
+        self.comm_stream = torch.cuda.current_stream()
+        self.slots = torch.zeros(2, dtype=torch.float64 if p.precision() == "f64" else torch.float32, device=dev)
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.reduced = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.reduced:
+            e.record(self.comm_stream)
+        self.n = 0
+
+    def allreduce(self, h):
+        """Global sum of the 1x1 handle `h` (consumed). Returns a handle that is valid once the exchange has landed
+        (p2p / nccl: lazily ordered by its ready event; torch: the LOCAL handle, the global value sits in self.slots)."""
+        if self.kind in ("p2p", "nccl"):
+            g = self.p.comm_allreduce_sum(h)
+            self.p.free(h)
+            return g
+        if self.kind == "torch":
+            slot = self.n & 1
+            self.n += 1
+            self.prov_stream.wait_event(self.reduced[slot])
+            self.p.copy_to_device(h, self.slots[slot:slot + 1].data_ptr(), 1)
+            self.copied[slot].record(self.prov_stream)
+            self.comm_stream.wait_event(self.copied[slot])
+            self.dist.all_reduce(self.slots[slot:slot + 1])
+            self.reduced[slot].record(self.comm_stream)
+        return h
+
+    def fence(self):
+        """Order the provider's stream after every exchange issued so far (closes a timed region on the device)."""
+        if self.kind in ("p2p", "nccl"):
+            self.p.comm_fence()
+        elif self.kind == "torch":
+            self.prov_stream.wait_stream(self.comm_stream)
+
+    def align(self, scratch):
+        """Device-side rendezvous: one exchange whose result the provider's stream waits for, so every rank's timed region
+        starts within microseconds of the others' (a host barrier leaves ~0.1-1 ms of skew, which a 15 ms Monte-Carlo shard
+        then pays as waiting time inside its final exchange)."""
+        if self.world > 1:
+            g = self.allreduce(self.p.scalar_mul(scratch, 1.0))
+            self.fence()
+            self.p.free(g)
+
+    def last_value(self, h):
+        if self.kind == "torch":
+            return float(self.slots[(self.n - 1) & 1].item())
+        return float(self.p.download(h)[0, 0])
+
+    def describe(self):
+        return {"none": "single GPU", "p2p": "peer-memory slot exchange over NVLink (publish fused into the reduction's last block, rm_fused_reduction_allreduce)",
+                "nccl": "provider NCCL communicator (rm_comm_allreduce_sum)", "torch": "torch.distributed all_reduce"}[self.kind]
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -238,62 +350,15 @@ def run_ours(args):
     shape = (N_SIDE, N_SIDE)
     hA, hB = p.upload(A, shape), p.upload(B, shape)
     hOne = p.upload(np.array([1.0]), (1, 1))
-
-    class CudaArray:  # zero-copy torch view of a provider buffer (for the NCCL all-reduce)
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-    # Multi-GPU: the provider keeps its own stream; torch's current stream is the communication stream. Per step the 8-byte
-    # sum is copied (one C call, stream-ordered) into a 2-slot persistent buffer, the comm stream waits on that copy and
-    # all-reduces the slot in place, so the collective's latency overlaps the next step's kernels. A slot is reused two
-    # steps later, after the provider stream has waited for its previous reduction.
-    native_comm = False
-    if world > 1 and not os.environ.get("RUNMAT_B200_TORCH_ALLREDUCE"):
-        # Preferred exchange: the provider's own NCCL communicator (rm_comm_*): ONE C call per step issues the copy, the stream
-        # dependencies and the all-reduce on the provider's communication stream. torch.distributed only ships the 128-byte id.
-        ok = 1
-        try:
-            ident = [B200Provider.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ident, src=0)
-            p.comm_init(ident[0], rank, world)
-            probe = p.upload(np.array([float(rank + 1)]), (1, 1))
-            got = float(p.download(p.comm_allreduce_sum(probe))[0, 0])
-            ok = 1 if got == world * (world + 1) / 2 else 0
-        except Exception as exc:  # noqa: BLE001 - any failure selects the torch.distributed exchange below on ALL ranks
-            print(f"[bench] rank {rank}: native comm unavailable ({exc}); using torch.distributed", file=sys.stderr)
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{local_rank}")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        native_comm = bool(flag.item())
-    if world > 1:
-        prov_stream = torch.cuda.ExternalStream(p.stream(), device=f"cuda:{local_rank}")
-        comm_stream = torch.cuda.current_stream()
-        sum_slots = torch.zeros(2, dtype=torch.float64, device=f"cuda:{local_rank}")
-        slot_ptr = [sum_slots[i:i + 1].data_ptr() for i in range(2)]
-        slot_view = [sum_slots[i:i + 1] for i in range(2)]
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        reduced = [torch.cuda.Event(), torch.cuda.Event()]
-        for e in reduced:
-            e.record(comm_stream)
-    step_no = [0]
+    ex = Exchange(p, rank, world, local_rank, dist, torch)
 
     def step():
         hC = p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS)
+        if ex.kind == "p2p":
+            # ONE kernel: the per-rank reduction whose last block publishes the scalar into every peer's slot
+            return hC, p.fused_reduction_allreduce(red_shader, [hA, hB], ELEMS)
         hS = p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1)
-        if native_comm:
-            hG = p.comm_allreduce_sum(hS)  # global sum of this step; overlaps the next step's kernels
-            p.free(hS)
-            return hC, hG
-        if world > 1:
-            slot = step_no[0] & 1
-            step_no[0] += 1
-            prov_stream.wait_event(reduced[slot])
-            p.copy_to_device(hS, slot_ptr[slot], 1)
-            copied[slot].record(prov_stream)
-            comm_stream.wait_event(copied[slot])
-            dist.all_reduce(slot_view[slot])
-            reduced[slot].record(comm_stream)
-        return hC, hS
+        return hC, ex.allreduce(hS)  # global sum of this step; overlaps the next step's kernels
 
     def sync_all():
         p.synchronize()
@@ -315,9 +380,9 @@ def run_ours(args):
         sys.setswitchinterval(0.0005)  # let the NVML polling thread run between the (GIL-holding) launch calls
         sampler.start()
     sync_all()
+    ex.align(hOne)
     p.timer_begin()
-    last_sum = None
-    in_flight = []  # N>1: a step's global sum is consumed (freed) SUM_DEPTH steps later, so its all-reduce has that much slack
+    in_flight = []  # N>1: a step's global sum is consumed (freed) SUM_DEPTH steps later, so its exchange has that much slack
     SUM_DEPTH = 4 if world > 1 else 1
     for _ in range(args.steps):
         hC, hS = step()
@@ -328,49 +393,66 @@ def run_ours(args):
     last_sum = in_flight.pop()
     for h in in_flight:
         p.free(h)
-    if native_comm:
-        p.comm_fence()  # the timed region ends when the last all-reduce has landed
-    elif world > 1:
-        prov_stream.wait_stream(comm_stream)  # the timed region ends when the last all-reduce has landed
+    ex.fence()  # the timed region ends when the last exchange has landed
     ms = p.timer_end_ms()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     launches = p.telemetry_snapshot().kernel_launches - t_before
-    checksum = float(p.download(last_sum)[0, 0])
-    checksum_local = checksum
+    checksum = ex.last_value(last_sum) if world > 1 else float(p.download(last_sum)[0, 0])
     p.free(last_sum)
-    if world > 1 and not native_comm:
-        checksum = float(sum_slots[(step_no[0] - 1) & 1].item())  # the all-reduced sum of the last step
+    hL = p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1)
+    checksum_local = float(p.download(hL)[0, 0])
+    p.free(hL)
+    exchange_ok = None
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+        # the exchanged sum must equal the sum of the ranks' local values (folded here by NCCL in some order: 1e-12)
+        tl = torch.tensor([checksum_local], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tl)
+        exchange_ok = bool(abs(float(tl.item()) - checksum) <= 1e-12 * abs(checksum)) and (ex.kind != "p2p" or p.comm_p2p_error() == 0)
     value = BYTES_STEP * world * args.steps / (ms * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (fused elementwise, 24 B/elem): isolated launches, CUDA events ------------
     def time_kernel(fn, reps):
+        def free(r):
+            for h in (r if isinstance(r, (list, tuple)) else [r]):
+                p.free(h)
         for _ in range(3):
-            p.free(fn())
+            free(fn())
         p.synchronize()
         p.timer_begin()
         for _ in range(reps):
-            p.free(fn())  # stream-ordered free: the pool hands the same block back, as in the step loop
+            free(fn())  # stream-ordered free: the pool hands the same block back, as in the step loop
         return p.timer_end_ms() / reps
 
     reps = max(args.steps, 10)
     ew_ms = time_kernel(lambda: p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS), reps)
     red_ms = time_kernel(lambda: p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1), reps)
+
+    def planner_pair():  # what the reference planner emits for sum(sin(A).*B+1): sin does not fold into a reduction (fusion.rs:1198-1258)
+        hC = p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS)
+        return [hC, p.reduce_sum(hC)]
+
+    pair_ms = time_kernel(planner_pair, reps)
     peak, peak_src = measured_peaks()
     achieved = BYTES_EW / (ew_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "rm_fused_ew (C = sin(A).*B+1, 24 B/elem)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": ew_ms * 1e3,
+                "frac": achieved / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src, "us_per_launch": ew_ms * 1e3,
+                "algorithmic_bytes_per_launch": BYTES_EW,
                 "reduction_kernel": {"kernel": "rm_fused_red (sum(sin(A).*B+1), 16 B/elem)", "achieved": BYTES_RED / (red_ms * 1e-3) / 1e9,
-                                     "frac": BYTES_RED / (red_ms * 1e-3) / 1e9 / peak, "us_per_launch": red_ms * 1e3}}
+                                     "frac": BYTES_RED / (red_ms * 1e-3) / 1e9 / peak, "us_per_launch": red_ms * 1e3},
+                "planner_shaped_pair": {"what": "fused_elementwise (writes C) + reduce_sum(C): the two calls the reference planner emits for sum(sin(A).*B+1) "
+                                                "(sin does not fold into a reduction, fusion.rs:1198-1258); 32 B/elem",
+                                        "us": pair_ms * 1e3, "achieved": 32 * ELEMS / (pair_ms * 1e-3) / 1e9, "frac": 32 * ELEMS / (pair_ms * 1e-3) / 1e9 / peak,
+                                        "vs_fused_16B_form_us": red_ms * 1e3}}
     profs = sorted((ROOT / "profiles").glob("r*_traffic.json"))
     prof = profs[-1] if profs else ROOT / "profiles" / "none"
     if prof.exists():
         try:
             roofline["traffic"] = json.loads(prof.read_text()).get("rm_fused_ew_dram_bytes_per_launch")
+            roofline["traffic_source"] = f"committed ncu capture profiles/{prof.name} (dram__bytes_read.sum + dram__bytes_write.sum, per launch); not re-measured in this run"
         except Exception:
             pass
 
@@ -449,9 +531,9 @@ def run_ours(args):
     extra = {}
     if not args.no_extra:
         try:
-            extra = extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray)
+            extra = extra_workloads(p, ex, rank, world, local_rank, dist, torch)
         except Exception as e:  # an optional workload must never take the headline line down
-            extra = {"error": str(e)}
+            extra = {"error": f"{type(e).__name__}: {e}"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -475,11 +557,11 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "bytes_per_step_per_gpu": BYTES_STEP, "l2": "inputs (2x128 MiB) + output (128 MiB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": (f"{world} independent batches, one NCCL all-reduce of 1 f64 per step "
-                                       f"({'provider communicator, rm_comm_allreduce_sum' if native_comm else 'torch.distributed'})") if world > 1 else "single GPU",
-                       "host_numa_binding": numa},
+            "config": CONFIG,
+            "run": {"arm": "B200 provider through the C ABI (ctypes)",
+                    "parallelism": f"{world} independent batches, the per-rank sums meet in one scalar exchange per step: {ex.describe()}" if world > 1 else "single GPU",
+                    "exchange": ex.kind, "exchange_verified": exchange_ok, "host_numa_binding": numa,
+                    "timed_region": "device-side rendezvous, K steps, closing fence on the last exchange; CUDA events on the provider stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "checksum": checksum, "extra": extra,
         }
@@ -490,115 +572,216 @@ def run_ours(args):
     return 0
 
 
-def extra_workloads(p, rank, world, local_rank, dist, torch, CudaArray):
-    """configs[2] (matmul 8192^3, single GPU) and configs[4] (Monte-Carlo 1e8 x 256, sharded + one all-reduce)."""
+def fp64_peak_tflops():
+    """148 SMs x 64 FP64 FMA lanes x 2 flop x 1.965 GHz (no measured FP64 peak is provided; stated, not measured)."""
+    return 148 * 64 * 2 * 1.965e9 / 1e12
+
+
+def extra_workloads(p, ex, rank, world, local_rank, dist, torch):
+    """The other BASELINE.json configs, each with its own roofline entry and stated work model:
+    configs[4] Monte-Carlo 1e8 x 256 (sharded, one exchange), configs[3] 4K image batch B=64 (sharded by images, one exchange per
+    batch), and at N=1: configs[2] matmul 8192^3, image_normalize / imfilter on the per-GPU share, mldivide."""
     out = {}
-    # Monte-Carlo: paths sharded in contiguous ranges; RNG addressing is global, result independent of `world`
+    peak_hbm, _ = measured_peaks()
+    dev = f"cuda:{local_rank}"
+
+    def max_over_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    def host_sync():
+        p.synchronize()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    # ---- Monte-Carlo: paths sharded in contiguous ranges; RNG addressing is global, result independent of `world` ----------
     M, T = 100_000_000, 256
     lo, hi = rank * M // world, (rank + 1) * M // world
     drift, scale = (0.05 - 0.5 * 0.2 ** 2) / 252.0, 0.2 * math.sqrt(1.0 / 252.0)
     hS0 = p.fill((hi - lo, 1), 100.0)
-    p.set_rng_state(0)
-    for it in range(2):
+    hScr = p.fill((1, 1), 0.0)
+    ms = price = None
+    for it in range(3):
         p.set_rng_state(0)
-        p.synchronize()
-        if world > 1:
-            dist.barrier()
+        host_sync()
+        ex.align(hScr)                       # device-side rendezvous: ranks start within microseconds
         p.timer_begin()
         hS = p.stochastic_evolution_sharded(hS0, drift, scale, T, lo, M)
         hP = p.payoff_partial_sum(hS, 100.0)
-        if world > 1:
-            p.synchronize()
-            ptr, n = p.device_ptr(hP)
-            dist.all_reduce(torch.as_tensor(CudaArray(ptr, n), device=f"cuda:{local_rank}"))
-            torch.cuda.synchronize()
+        hG = ex.allreduce(hP)                # the path's only exchange: 1 f64 (stream-ordered, no host wait)
+        ex.fence()
         ms = p.timer_end_ms()
-        price = p.read_scalar(hP, 0) / M * math.exp(-0.05 * T / 252.0)
+        price = (ex.last_value(hG) if world > 1 else p.read_scalar(hG, 0)) / M * math.exp(-0.05 * T / 252.0)
         p.free(hS)
-        p.free(hP)
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+        p.free(hG)
+    ms = max_over_ranks(ms)
     p.free(hS0)
-    out["monte_carlo"] = {"paths": M, "steps": T, "ms": ms, "path_steps_per_s": M * T / (ms * 1e-3), "price": price, "scaling": "strong",
-                          "collective": "one NCCL all-reduce of 1 f64" if world > 1 else None}
-    if world == 1:
-        # configs[3] per-GPU share: [8,2160,3840] f32 normalise pipeline (image_normalize) + 5x5 imfilter on one 4K RGB frame
-        from runmat_b200 import B200Provider, ImageNormalizeDescriptor
+    p.free(hScr)
+    # work model: one path-step = 1/2 Box-Muller pair (log, sqrt, sincos for two paths) + one exp + the S *= e multiply + the LCG hop
+    psps = M * T / (ms * 1e-3)
+    fp64_per_step = MC_FP64_INSTR_PER_PATH_STEP
+    pipe_rate = 148 * 64 * 1.965e9 * world  # FP64 lane-instructions/s the SMs can issue (64 lanes/SM/clk)
+    out["monte_carlo"] = {"paths": M, "steps": T, "ms": ms, "path_steps_per_s": psps, "price": price, "scaling": "strong",
+                          "exchange": ex.describe() if world > 1 else None,
+                          "roofline": {"bound": "fp64 pipe (ALU/issue; HBM traffic is 16 B/path total)", "work_model": f"{fp64_per_step} FP64 arithmetic instructions (DFMA+DMUL+DADD) per path-step, measured with ncu SASS opcode counters; peak = 148 SM x 64 lanes x 1.965 GHz per GPU",
+                                       "achieved": psps * fp64_per_step / 1e12, "peak": pipe_rate / 1e12, "unit": "T FP64-instr/s",
+                                       "frac": psps * fp64_per_step / pipe_rate}}
 
-        with B200Provider(local_rank, device_id=rank + 1000, precision="f32") as p32:
-            Bi, H, W = 8, 2160, 3840
-            img = np.random.default_rng(3).random(Bi * H * W, dtype=np.float32)
-            hI = p32.upload(img, (Bi, H, W))
-            d = ImageNormalizeDescriptor(Bi, H, W, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
-            for _ in range(2):
-                p32.free(p32.image_normalize(hI, d))
-            p32.synchronize()
-            p32.timer_begin()
-            for _ in range(5):
-                p32.free(p32.image_normalize(hI, d))
-            ms = p32.timer_end_ms() / 5
-            px = Bi * H * W
-            out["image_normalize_8x4k_f32"] = {"ms": ms, "gb_per_s_at_12B_per_px": 12 * px / (ms * 1e-3) / 1e9,
-                                               "gb_per_s_at_8B_per_px_algorithmic": 8 * px / (ms * 1e-3) / 1e9}
-            for _ in range(2):
-                p32.free(p32.reduce_mean_nd(hI, [1, 2]))
-            p32.synchronize()
-            p32.timer_begin()
-            for _ in range(5):
-                p32.free(p32.reduce_mean_nd(hI, [1, 2]))
-            ms = p32.timer_end_ms() / 5
-            out["mean_dims23_8x4k_f32"] = {"ms": ms, "gb_per_s": 4 * px / (ms * 1e-3) / 1e9, "kernel": "rm_fused_red (Strided layout, 8 slices)"}
-            p32.free(hI)
-            frame = np.random.default_rng(4).random(H * W * 3, dtype=np.float32)
-            g = np.exp(-((np.arange(5) - 2)[:, None] ** 2 + (np.arange(5) - 2)[None, :] ** 2) / 2.0)
-            hF, hK = p32.upload(frame, (H, W, 3)), p32.upload((g / g.sum()).astype(np.float32))
-            for _ in range(2):
-                p32.free(p32.imfilter(hF, hK, padding="replicate"))
-            p32.synchronize()
-            p32.timer_begin()
-            for _ in range(5):
-                p32.free(p32.imfilter(hF, hK, padding="replicate"))
-            ms = p32.timer_end_ms() / 5
-            out["imfilter_5x5_4k_rgb_f32"] = {"ms": ms, "gb_per_s_at_8B_per_sample": 8 * H * W * 3 / (ms * 1e-3) / 1e9}
-        n = 8192
-        rng = np.random.default_rng(7)
-        hA = p.upload(rng.uniform(-1, 1, n * n), (n, n))
-        hB = p.upload(rng.uniform(-1, 1, n * n), (n, n))
-        hC = p.matmul(hA, hB)
-        p.free(hC)
-        p.synchronize()
-        p.timer_begin()
-        reps = 2
-        for _ in range(reps):
-            p.free(p.matmul(hA, hB))
-        ms = p.timer_end_ms() / reps
-        out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9,
-                                  "engine": "auto -> tcgen05 (Ozaki int8 split, 7 slices = 28 exact int8 GEMMs, TMEM int32 accumulate, f64 recombine)"}
-        p.set_matmul_engine(1)
-        p.free(p.matmul(hA, hB))
-        p.synchronize()
-        p.timer_begin()
-        p.free(p.matmul(hA, hB))
-        ms1 = p.timer_end_ms()
-        p.set_matmul_engine(0)
-        out["matmul_8192_f64_dmma"] = {"ms": ms1, "gflops": 2.0 * n ** 3 / (ms1 * 1e-3) / 1e9, "engine": "FP64 DMMA mma.sync.m8n8k4"}
-        p.free(hA)
-        p.free(hB)
-        # mldivide: 4096 x 4096 system, 64 right-hand sides (device LU with partial pivoting)
-        ns = 4096
-        hM = p.upload(rng.uniform(-1, 1, ns * ns) + np.eye(ns).reshape(-1) * 4.0, (ns, ns))
-        hR = p.upload(rng.uniform(-1, 1, ns * 64), (ns, 64))
-        p.free(p.mldivide(hM, hR))
-        p.synchronize()
+    # ---- configs[3]: 4K image batch, B = 64 images sharded by image (batch is the stride-1 axis: each rank owns its own
+    #      [B/N, H, W] tensor), per batch: image_normalize -> squared error vs input -> ONE scalar exchange (MSE) ------------------
+    out["image_batch_64x4k_f32"] = image_batch_leg(p, rank, world, local_rank, dist, torch, peak_hbm)
+
+    if world == 1:
+        out.update(single_gpu_kernels(p, rank, local_rank, peak_hbm))
+    return out
+
+
+# FP64 arithmetic instructions (DFMA + DMUL + DADD, thread-level, predicated-on) evolve_kernel executes per path-step, MEASURED
+# with ncu's SASS opcode counters on the 1e8 x 256 run (profiles/r04_summary.md, r04_gemm_mc.ncu-rep: 3625.8 + 1059.8 + 725.2
+# thread-instr/clk over 116.89 ms at 1.965 GHz = 1.243e12 instructions / 2.56e10 path-steps). It is the dynamic count of
+# 1/2 (log + sqrt + sincos) + exp + the state update; the pipe issues 64 such instructions per SM per clock.
+MC_FP64_INSTR_PER_PATH_STEP = 48.5
+
+
+def image_batch_leg(p, rank, world, local_rank, dist, torch, peak_hbm):
+    from runmat_b200 import B200Provider, ImageNormalizeDescriptor, fusion_text as ft
+    from runmat_b200.sharding import batch_slices_for_rank, lcg_image_shard
+
+    Bt, H, W = 64, 2160, 3840
+    b0, b1 = batch_slices_for_rank(Bt, rank, world)
+    Bl = b1 - b0
+    dev = f"cuda:{local_rank}"
+    with B200Provider(local_rank, device_id=rank + 1000, precision="f32") as p32:
+        ex32 = Exchange(p32, rank, world, local_rank, dist, torch, label=" image")
         t0 = time.perf_counter()
-        hX = p.mldivide(hM, hR)
-        p.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3
-        out["mldivide_4096_x64"] = {"ms": ms, "gflops_lu": (2.0 / 3.0) * ns ** 3 / (ms * 1e-3) / 1e9}
-        for h in (hM, hR, hX):
-            p.free(h)
+        imgs = lcg_image_shard(Bt, H, W, b0, Bl)          # runmat_lcg.m:59-79, generated directly in this rank's layout
+        gen_s = time.perf_counter() - t0
+        hI = p32.upload(imgs, (Bl, H, W))
+        del imgs
+        d = ImageNormalizeDescriptor(Bl, H, W, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+        O, I, T0, T1 = 0, 1, 10, 11
+        mse_shader = ft.reduction_wgsl([O, I], [ft.FusionOp("primitive", "Sub", [O, I], T0), ft.FusionOp("primitive", "ElemMul", [T0, T0], T1)], T1,
+                                       axis=0, scalar_ty="f32")
+        n = Bl * H * W
+        hScr = p32.fill((1, 1), 0.0)
+
+        def batch_step():
+            hO = p32.image_normalize(hI, d)
+            hE = p32.fused_reduction(mse_shader, [hO, hI], (1, 1), n, 1)
+            p32.free(hO)
+            return ex32.allreduce(hE) if world > 1 else hE
+
+        for _ in range(2):
+            p32.free(batch_step())
+        p32.synchronize()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+        ex32.align(hScr)
+        K = 5
+        p32.timer_begin()
+        hG = None
+        for _ in range(K):
+            if hG is not None:
+                p32.free(hG)
+            hG = batch_step()
+        ex32.fence()
+        ms = p32.timer_end_ms() / K
+        sq = ex32.last_value(hG) if world > 1 else float(p32.download(hG)[0, 0])
+        p32.free(hG)
+        p32.free(hI)
+        p32.free(hScr)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        px = Bt * H * W
+        alg = 20 * px  # normalise: 2 reads + 1 write (12 B/px, the second read cannot come from L2 at this size); MSE: 2 reads (8 B/px)
+        return {"batch": Bt, "images_per_rank": Bl, "ms_per_batch": ms, "images_per_s": Bt / (ms * 1e-3), "mse": sq / px, "scaling": "strong",
+                "exchange": ex32.describe() if world > 1 else None, "host_generate_s_per_rank": gen_s,
+                "roofline": {"bound": "hbm", "work_model": "20 B/px: image_normalize 12 B/px (moments read + normalise read + write) + fused squared-error reduction 8 B/px",
+                             "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak_hbm * world, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / (peak_hbm * world)}}
+
+
+def single_gpu_kernels(p, rank, local_rank, peak_hbm):
+    out = {}
+    from runmat_b200 import B200Provider, ImageNormalizeDescriptor
+
+    def timed(pp, fn, reps):
+        for _ in range(2):
+            pp.free(fn())
+        pp.synchronize()
+        pp.timer_begin()
+        for _ in range(reps):
+            pp.free(fn())
+        return pp.timer_end_ms() / reps
+
+    with B200Provider(local_rank, device_id=rank + 2000, precision="f32") as p32:
+        Bi, H, W = 8, 2160, 3840
+        img = np.random.default_rng(3).random(Bi * H * W, dtype=np.float32)
+        hI = p32.upload(img, (Bi, H, W))
+        d = ImageNormalizeDescriptor(Bi, H, W, 1e-6, gain=1.0123, bias=-0.02, gamma=1.8)
+        ms = timed(p32, lambda: p32.image_normalize(hI, d), 5)
+        px = Bi * H * W
+        out["image_normalize_8x4k_f32"] = {"ms": ms, "roofline": {"bound": "hbm", "work_model": "12 B/px (2 reads + 1 write; 8 B/px would need the batch to stay in L2)",
+                                                                   "achieved": 12 * px / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s", "frac": 12 * px / (ms * 1e-3) / 1e9 / peak_hbm,
+                                                                   "frac_at_8B_per_px": 8 * px / (ms * 1e-3) / 1e9 / peak_hbm}}
+        ms = timed(p32, lambda: p32.reduce_mean_nd(hI, [1, 2]), 5)
+        out["mean_dims23_8x4k_f32"] = {"ms": ms, "kernel": "rm_fused_red (Strided layout, 8 slices)",
+                                       "roofline": {"bound": "hbm", "work_model": "4 B/px", "achieved": 4 * px / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                                                    "frac": 4 * px / (ms * 1e-3) / 1e9 / peak_hbm}}
+        p32.free(hI)
+        frame = np.random.default_rng(4).random(H * W * 3, dtype=np.float32)
+        g = np.exp(-((np.arange(5) - 2)[:, None] ** 2 + (np.arange(5) - 2)[None, :] ** 2) / 2.0)
+        hF, hK = p32.upload(frame, (H, W, 3)), p32.upload((g / g.sum()).astype(np.float32))
+        ms = timed(p32, lambda: p32.imfilter(hF, hK, padding="replicate"), 5)
+        smp = H * W * 3
+        out["imfilter_5x5_4k_rgb_f32"] = {"ms": ms, "roofline": {"bound": "hbm (8 B/sample) / FP32 issue (25 unfused mul + 25 add per sample, bit-exact with the host order)",
+                                                                  "work_model": "8 B/sample", "achieved": 8 * smp / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                                                                  "frac": 8 * smp / (ms * 1e-3) / 1e9 / peak_hbm}}
+    n = 8192
+    rng = np.random.default_rng(7)
+    hA = p.upload(rng.uniform(-1, 1, n * n), (n, n))
+    hB = p.upload(rng.uniform(-1, 1, n * n), (n, n))
+    ms = timed(p, lambda: p.matmul(hA, hB), 3)
+    st = p.ozaki_stats()
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    bf16 = float(peaks.get("bf16_tflops", 2250.0 * 0.76))
+    int8_ops = 29 * 2.0 * n ** 3  # 28 digit products + the accuracy guard's magnitude product, all exact int8 GEMMs
+    out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "fp64_fallback_tiles": st["fp64_tiles"],
+                              "engine": "auto -> tcgen05 (Ozaki int8 split, 7 slices = 28 exact int8 GEMMs + 1 guard GEMM, TMEM int32 accumulate, f64 recombine; "
+                                        "device-side accuracy guard, no host sync)",
+                              "roofline": {"bound": "tensor", "work_model": "29 int8 GEMMs of 2*8192^3 op; peak = 2 x the measured bf16 burst (int8 rate = 2 x bf16 on tcgen05)",
+                                           "achieved": int8_ops / (ms * 1e-3) / 1e12, "peak": 2 * bf16, "unit": "TOP/s", "frac": int8_ops / (ms * 1e-3) / 1e12 / (2 * bf16),
+                                           "f64_equivalent_tflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e12}}
+    p.set_matmul_engine(1)
+    ms1 = timed(p, lambda: p.matmul(hA, hB), 1)
+    p.set_matmul_engine(0)
+    out["matmul_8192_f64_dmma"] = {"ms": ms1, "gflops": 2.0 * n ** 3 / (ms1 * 1e-3) / 1e9, "engine": "FP64 DMMA mma.sync.m8n8k4",
+                                   "roofline": {"bound": "fp64 tensor pipe", "work_model": "2*8192^3 flop", "achieved": 2.0 * n ** 3 / (ms1 * 1e-3) / 1e12, "peak": fp64_peak_tflops(),
+                                                "unit": "TFLOP/s", "frac": 2.0 * n ** 3 / (ms1 * 1e-3) / 1e12 / fp64_peak_tflops(), "peak_source": "stated: 148 SM x 64 FMA/clk x 1.965 GHz"}}
+    p.free(hA)
+    p.free(hB)
+    # mldivide: 4096 x 4096 system, 64 right-hand sides (device LU with partial pivoting)
+    ns = 4096
+    hM = p.upload(rng.uniform(-1, 1, ns * ns) + np.eye(ns).reshape(-1) * 4.0, (ns, ns))
+    hR = p.upload(rng.uniform(-1, 1, ns * 64), (ns, 64))
+    p.free(p.mldivide(hM, hR))
+    p.synchronize()
+    t0 = time.perf_counter()
+    hX = p.mldivide(hM, hR)
+    p.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    flop = (2.0 / 3.0) * ns ** 3 + 2.0 * ns * ns * 64
+    out["mldivide_4096_x64"] = {"ms": ms, "gflops_lu": (2.0 / 3.0) * ns ** 3 / (ms * 1e-3) / 1e9,
+                                "roofline": {"bound": "fp64 tensor pipe (updates) + latency (panel)", "work_model": "2/3 n^3 + 2 n^2 nrhs flop", "achieved": flop / (ms * 1e-3) / 1e12,
+                                             "peak": fp64_peak_tflops(), "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / fp64_peak_tflops()}}
+    for h in (hM, hR, hX):
+        p.free(h)
     return out
 
 

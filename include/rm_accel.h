@@ -22,8 +22,12 @@
  *    `diag_output` of `rm_matmul_epilogue` (written in place, lib.rs:3520-3522).
  *  - The provider is `Send + Sync`: all entry points are thread-safe (one mutex around the buffer
  *    table, stream-ordered allocation); `rm_free` may arrive from a GC finalizer thread.
- *  - Work is enqueued on the provider's CUDA stream; only `rm_download`, `rm_read_scalar` and
- *    `rm_synchronize` wait for the device.
+ *  - Work is enqueued on the provider's CUDA stream. The calls that wait for the device are the ones whose
+ *    return value lives on it: `rm_download*`, `rm_read_scalar`, `rm_synchronize`, `rm_timer_end_ms`,
+ *    `rm_warmup`, `rm_find` (data-dependent output size), `rm_sub2ind`/`rm_ind2sub` (the host raises on a bad
+ *    subscript) and `rm_mldivide`/`rm_mrdivide`/`rm_linsolve` (the conditioning gate decides between a result
+ *    and `RM_UNSUPPORTED`). Everything else — including `rm_matmul` on either engine — only enqueues;
+ *    `rm_host_sync_count` counts the waits so a caller (and the tests) can verify that.
  *  - There is NO CPU fallback inside the library: without a usable CUDA device
  *    `rm_provider_create` fails with `RM_NO_DEVICE`.
  */
@@ -114,11 +118,22 @@ rm_status rm_comm_init(rm_provider* p, const uint8_t* unique_id, uint32_t len, u
 uint32_t rm_comm_world_size(rm_provider* p);
 rm_status rm_comm_allreduce_sum(rm_provider* p, const rm_handle* in, rm_handle* out);
 rm_status rm_comm_fence(rm_provider* p);
+/* Peer-memory exchange for the scalar of a sharded reduction (NVLink/NVSwitch peer stores; comm.cu). Every rank calls
+ * rm_comm_p2p_export (allocates its slot buffer, returns the 64-byte CUDA IPC handle), the host gathers the handles of all
+ * ranks in rank order, every rank calls rm_comm_p2p_connect. Afterwards rm_comm_allreduce_sum of a 1-element f64 tensor and
+ * rm_fused_reduction_allreduce use peer stores instead of a NCCL launch; results are bit-identical on every rank (fixed rank
+ * order). world == 1 connects a rank to itself. */
+#define RM_COMM_P2P_HANDLE_BYTES 64
+rm_status rm_comm_p2p_export(rm_provider* p, uint8_t* handle_out, uint32_t len);
+rm_status rm_comm_p2p_connect(rm_provider* p, const uint8_t* all_handles, uint32_t len, uint32_t rank, uint32_t world);
+int rm_comm_p2p_connected(rm_provider* p);
+rm_status rm_comm_p2p_error(rm_provider* p, int32_t* err); /* 1 if a combine's bounded wait expired (a peer never published) */
 /* PCI bus id ("0000:1b:00.0") of the provider's device: lets the host place its threads and pinned buffers on the GPU's NUMA node. */
 rm_status rm_device_pci_bus_id(rm_provider* p, char* buf, uint32_t buflen);
 uint32_t rm_device_id(rm_provider* p);                                     /* :1391 */
 rm_precision rm_provider_precision(rm_provider* p);                        /* precision() :1458 */
 rm_status rm_synchronize(rm_provider* p);
+uint64_t rm_host_sync_count(rm_provider* p); /* number of entry-point calls that blocked the host on the device so far */
 /* export_context (lib.rs:1406): share the CUDA stream / raw device pointer with other CUDA code. */
 rm_status rm_get_stream(rm_provider* p, void** cuda_stream_out);
 rm_status rm_set_stream(rm_provider* p, void* cuda_stream);
@@ -255,6 +270,10 @@ rm_status rm_fused_reduction(rm_provider* p, const char* shader, const rm_handle
                              uint64_t reduce_len, uint64_t num_slices, uint32_t workgroup_size,
                              rm_reduction_flavor flavor, double custom_scale, rm_handle* out);
 void rm_fused_cache_counters(rm_provider* p, uint64_t* hits, uint64_t* misses); /* :3013 */
+/* sharded 'all' reduction: per-rank fused reduction to one scalar + sum over the ranks of the peer-memory exchange;
+ * the publish is the tail of the reduction kernel's last block. `out` is 1x1 and holds the GLOBAL value. */
+rm_status rm_fused_reduction_allreduce(rm_provider* p, const char* shader, const rm_handle* inputs, uint32_t n_inputs,
+                                       uint64_t reduce_len, rm_reduction_flavor flavor, double custom_scale, rm_handle* out);
 
 /* ---- a6: reductions (lib.rs:2709-2882) ----------------------------------------------------------- */
 typedef enum rm_nan_mode { RM_NAN_INCLUDE = 0, RM_NAN_OMIT = 1 } rm_nan_mode;
@@ -295,8 +314,12 @@ rm_status rm_syrk(rm_provider* p, const rm_handle* a, rm_handle* out); /* A' * A
 rm_status rm_matmul_power_step(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, double epsilon, rm_handle* out); /* lib.rs:2414 */
 rm_status rm_covariance(rm_provider* p, const rm_handle* matrix, int normalization_biased, rm_handle* out); /* lib.rs:2857, rows=All, unweighted */
 rm_status rm_diag_extract(rm_provider* p, const rm_handle* matrix, int64_t offset, rm_handle* out);         /* lib.rs:1626 */
-/* selects the GEMM engine: 0 = auto, 1 = FP64 DMMA (mma.sync m8n8k4), 2 = Ozaki split on tcgen05 i8 */
+/* selects the GEMM engine: 0 = auto, 1 = FP64 DMMA (mma.sync m8n8k4), 2 = Ozaki split on tcgen05 i8.
+ * The tcgen05 engine is element-wise safe on every input: entries whose terms hide under the row/column maximum, and
+ * non-finite inputs, are detected on the device and recomputed by the FP64 kernel in the same stream (gemm_ozaki.cu). */
 rm_status rm_set_matmul_engine(rm_provider* p, int engine);
+/* test/debug: waits for the stream; out4 = {non-finite input seen, pipeline error, tiles recomputed in FP64, 0} of the last tcgen05 product */
+rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4);
 
 /* ---- a9: mldivide core (lib.rs:2477-2489): square systems by device LU with partial pivoting; non-square,
  *      singular or badly conditioned inputs return RM_UNSUPPORTED (host SVD fallback, as with wgpu today) ---- */

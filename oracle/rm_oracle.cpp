@@ -287,7 +287,7 @@ void image_normalize_t(const T* data, T* out, uint64_t batch, uint64_t height, u
         T v = (data[idx] - mean) * inv_sigma;
         if (has_gain) v *= gain;
         if (has_bias) v += bias;
-        if (clamp_zero) v = std::max(v, (T)0);  // f64::max(NaN,0)=0: v.max(0.0)
+        if (clamp_zero) v = std::fmax(v, (T)0);  // Rust `value.max(0.0)` (simple_provider.rs:7982): NaN.max(0.0) == 0.0, i.e. fmax, not std::max
         if (has_gamma) v = std::pow(v, gamma);
         out[idx] = v;
       }
@@ -459,9 +459,10 @@ ORC_API void orc_image_normalize_f32(const float* data, float* out, uint64_t bat
 // image/filters/imfilter.rs:476-745. 2-D/3-D images with a 2-D kernel (rank <= 3). padding: 0 const,
 // 1 replicate, 2 symmetric, 3 circular. shape: 0 same, 1 full, 2 valid. mode: 0 corr, 1 conv.
 // Returns the output dims in out_shape[3]; `out` may be NULL to query the shape only.
-ORC_API int orc_imfilter(const double* img, const uint64_t* ishape, int irank, const double* ker,
-                         const uint64_t* kshape, int krank, int padding, double cval, int shape, int mode,
-                         double* out, uint64_t* out_shape) {
+template <typename T>
+static int imfilter_t(const T* img, const uint64_t* ishape, int irank, const T* ker,
+                      const uint64_t* kshape, int krank, int padding, T cval, int shape, int mode,
+                      T* out, uint64_t* out_shape) {
   int rank = std::max(irank, krank);
   if (rank > 3) return -1;
   uint64_t ie[3] = {1, 1, 1}, ke[3] = {1, 1, 1};
@@ -484,13 +485,13 @@ ORC_API int orc_imfilter(const double* img, const uint64_t* ishape, int irank, c
     for (uint64_t o1 = 0; o1 < oe[1]; ++o1)
       for (uint64_t o0 = 0; o0 < oe[0]; ++o0, ++oi) {
         int64_t ob[3] = {(int64_t)o0, (int64_t)o1, (int64_t)o2};
-        double sum = 0.0;
+        T sum = (T)0;
         uint64_t kidx[3] = {0, 0, 0};
         for (uint64_t kp = 0; kp < ktotal; ++kp) {  // kernel points in column-major order (:655-690)
           uint64_t lin = kidx[0] * kstr[0] + kidx[1] * kstr[1] + kidx[2] * kstr[2];
           uint64_t flin = (ke[0] - 1 - kidx[0]) * kstr[0] + (ke[1] - 1 - kidx[1]) * kstr[1] + (ke[2] - 1 - kidx[2]) * kstr[2];
-          double kv = mode == 0 ? ker[lin] : ker[flin];
-          double sample; bool constant = false; uint64_t ilin = 0;
+          T kv = mode == 0 ? ker[lin] : ker[flin];
+          T sample; bool constant = false; uint64_t ilin = 0;
           for (int d = 0; d < 3; ++d) {
             int64_t coord = ob[d] + base[d] + ((int64_t)kidx[d] - origin[d]);
             int64_t len = (int64_t)ie[d];
@@ -507,6 +508,20 @@ ORC_API int orc_imfilter(const double* img, const uint64_t* ishape, int irank, c
         out[oi] = sum;
       }
   return rank;
+}
+
+ORC_API int orc_imfilter(const double* img, const uint64_t* ishape, int irank, const double* ker,
+                         const uint64_t* kshape, int krank, int padding, double cval, int shape, int mode,
+                         double* out, uint64_t* out_shape) {
+  return imfilter_t<double>(img, ishape, irank, ker, kshape, krank, padding, cval, shape, mode, out, out_shape);
+}
+// The same loop in f32 storage arithmetic: what a provider running at ProviderPrecision::F32 computes (the wgpu default,
+// backend/wgpu/provider/init.rs:145-172): per-tap `sum += k * sample` rounded to f32 after the multiply and after the add,
+// host tap order (imfilter.rs:655-690). Checker for the f32 image config (BASELINE configs[3]).
+ORC_API int orc_imfilter_f32(const float* img, const uint64_t* ishape, int irank, const float* ker,
+                             const uint64_t* kshape, int krank, int padding, float cval, int shape, int mode,
+                             float* out, uint64_t* out_shape) {
+  return imfilter_t<float>(img, ishape, irank, ker, kshape, krank, padding, cval, shape, mode, out, out_shape);
 }
 
 // conv2d: simple_provider.rs:1845-1876 (conv2d_full_real: scatter over the signal in column-major order, zero
@@ -610,6 +625,28 @@ ORC_API uint64_t orc_stochastic_evolution(uint64_t rng_state, double* data, uint
     }
   }
   return rng_state;
+}
+
+// The same host algorithm replayed for a SAMPLE of paths (full-size parity of the 1e8 x 256 run: the whole vector would be
+// 2.56e10 sequential draws). In pass t the host's generate_normal consumes 2 draws per Box-Muller pair, pair j = path/2 first
+// (random.rs:530-543), so path p's normal of pass t starts at stream offset t*2*ceil(len/2) + 2*(p/2); orc_advance_state
+// (random.rs:238-257, pinned against n sequential steps in tests/test_oracle_kats.py) jumps there. Element 2j takes
+// r*cos, element 2j+1 takes r*sin; value *= exp(drift + scale*z) with a rounding after every operation, as in :25-27.
+ORC_API void orc_stochastic_evolution_sampled(uint64_t rng_state, double s0, uint64_t len, double drift, double scale, uint32_t steps,
+                                              const uint64_t* paths, uint64_t n_paths, double* out) {
+  const uint64_t draws_per_pass = 2 * ((len + 1) / 2);
+  for (uint64_t k = 0; k < n_paths; ++k) {
+    const uint64_t p = paths[k];
+    double v = s0;
+    for (uint32_t t = 0; t < steps; ++t) {
+      uint64_t st = orc_advance_state(rng_state, (uint64_t)t * draws_per_pass + 2 * (p / 2));
+      double z0, z1;
+      next_normal_pair(&st, &z0, &z1);
+      double term = drift + scale * ((p & 1) ? z1 : z0);
+      v *= std::exp(term);
+    }
+    out[k] = v;
+  }
 }
 
 // simple_provider.rs:3488-3512 (linspace; last element forced to `stop`)

@@ -103,6 +103,7 @@ lib.rm_device_id.restype = C.c_uint32
 lib.rm_live_buffers.restype = C.c_uint64
 lib.rm_comm_world_size.restype = C.c_uint32
 lib.rm_live_bytes.restype = C.c_uint64
+lib.rm_host_sync_count.restype = C.c_uint64
 lib.rm_two_pass_threshold.restype = C.c_uint64
 lib.rm_default_reduction_workgroup_size.restype = C.c_uint32
 

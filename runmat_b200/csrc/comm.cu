@@ -6,6 +6,19 @@
 // only when the value is used (the same lazy mechanism uploads use), so the next step's kernels run under the collective.
 // NCCL is bound at run time (dlopen of the libnccl the process already carries, e.g. torch's), never at link time: a
 // single-GPU user of librm_accel_b200.so needs no NCCL at all.
+//
+// Peer-memory exchange (rm_comm_p2p_*). The scalar exchange above is latency-, not bandwidth-bound: a NCCL all-reduce of 8
+// bytes is a kernel launch + a multi-hop LL protocol whose CTAs must become co-resident on every rank (measured r1: +175 us
+// at N=4, +280 us at N=8 on a 123 us step). Over NVSwitch every GPU can store straight into every peer's memory, so the
+// exchange becomes: PUBLISH = rank r stores its partial into slot [bank][r] of EVERY rank's slot buffer (CUDA IPC mapping of
+// a cudaMalloc'ed 2 KB buffer) followed by a system-scope release store of the step number; COMBINE = each rank waits
+// (acquire loads on its OWN memory, bounded) until all N flags of the bank carry the step, then folds the N values in rank
+// order, so every rank gets the bit-identical sum independent of arrival order. The publish is fused into the tail of the
+// producing kernel (the generated reduction's last block: rm_fused_reduction_allreduce; rm_payoff_partial_sum feeds the
+// stand-alone publish kernel), the combine runs on the communication stream and its result is waited for lazily like an
+// upload. Bank reuse: 8 banks; publish(t) is ordered after this rank's combine(t-4), and a peer's publish(t) therefore proves
+// its combine(t-4) is done, so when rank r overwrites bank (t mod 8) with step t every peer has already folded step t-8
+// (r's publish(t) follows r's combine(t-4), which saw the peer's publish(t-4), which followed the peer's combine(t-8)).
 #include <dlfcn.h>
 
 #include "common.h"
@@ -68,10 +81,146 @@ void give_event(rm_provider* p, cudaEvent_t ev) {
   p->event_pool.push_back(ev);
 }
 
+// ---- peer-memory exchange ---------------------------------------------------------------------------------------------
+constexpr int P2P_MAXR = 16, P2P_BANKS = 8, P2P_LAG = 4;
+struct P2PSlots {
+  double vals[P2P_BANKS][P2P_MAXR];
+  unsigned long long flags[P2P_BANKS][P2P_MAXR];
+};
+struct P2PState {
+  P2PSlots* mine = nullptr;           // cudaMalloc (IPC-exportable; pool memory is not)
+  P2PSlots* peers[P2P_MAXR] = {};     // peers[rank] == mine
+  P2PSlots** d_peers = nullptr;       // device copy of `peers` (what the kernels index)
+  int* d_err = nullptr;               // set by a combine whose bounded wait ran out
+  int world = 1, rank = 0;
+  bool connected = false;
+  uint64_t step = 0;
+  cudaEvent_t combine_done[P2P_BANKS] = {};
+  bool recorded[P2P_BANKS] = {};
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* addr, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* addr) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+  return v;
+}
+// stand-alone publish (for partials produced by a kernel that does not carry the fused tail)
+template <typename T>
+__global__ void p2p_publish_kernel(P2PSlots* const* __restrict__ peers, int n, int rank, unsigned long long step, const T* __restrict__ value) {
+  const int q = threadIdx.x;
+  if (q >= n) return;
+  const int b = (int)(step % P2P_BANKS);
+  P2PSlots* dst = peers[q];
+  dst->vals[b][rank] = (double)*value;
+  st_release_sys(&dst->flags[b][rank], step + 1);
+}
+template <typename T>
+__global__ void p2p_combine_kernel(const P2PSlots* __restrict__ mine, int n, unsigned long long step, T* __restrict__ out, int* __restrict__ err) {
+  __shared__ double v[P2P_MAXR];
+  __shared__ int bad;
+  const int q = threadIdx.x;
+  const int b = (int)(step % P2P_BANKS);
+  if (q == 0) bad = 0;
+  __syncthreads();
+  if (q < n) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flags[b][q]) < step + 1) {
+      if (clock64() - t0 > 20000000000LL) { bad = 1; break; }  // ~10 s: a dead peer raises the error flag, never hangs the GPU
+      __nanosleep(200);
+    }
+    v[q] = *(volatile const double*)&mine->vals[b][q];
+  }
+  __syncthreads();
+  if (q == 0) {
+    if (bad) atomicExch(err, 1);
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += v[r];  // rank order: bit-identical on every rank
+    *out = (T)(bad ? __longlong_as_double(0x7ff8000000000000LL) : s);  // exchanged and folded in f64 whatever the storage type
+  }
+}
+
+P2PState* p2p_state(rm_provider* p) { return (P2PState*)p->p2p; }
+
+}  // namespace
+
+// Publish context handed to the generated reduction kernel (fused.cu): returns false when no peer exchange is connected.
+// The caller holds p->comm_mu from this call until p2p_finish().
+bool p2p_begin(rm_provider* p, P2PPublish* pub) {
+  P2PState* s = p2p_state(p);
+  if (!s || !s->connected) return false;
+  const uint64_t t = s->step;
+  // bank reuse rule: publish(t) is ordered after this rank's combine(t - LAG)
+  if (t >= (uint64_t)P2P_LAG) {
+    const int b = (int)((t - P2P_LAG) % P2P_BANKS);
+    if (s->recorded[b]) cudaStreamWaitEvent(p->stream, s->combine_done[b], 0);
+  }
+  pub->peers = (void* const*)s->d_peers;
+  pub->n = (uint32_t)s->world;
+  pub->rank = (uint32_t)s->rank;
+  pub->step = t;
+  return true;
+}
+// After the producer (with its fused or stand-alone publish) has been enqueued on the compute stream: enqueue the combine on
+// the communication stream into a fresh 1x1 handle whose ready event the compute stream waits on at first use.
+rm_status p2p_finish(rm_provider* p, rm_handle* out) {
+  P2PState* s = p2p_state(p);
+  const uint64_t t = s->step++;
+  uint64_t shp[2] = {1, 1};
+  void* dst;
+  RM_TRY(alloc_tensor(p, shp, 2, out, &dst));
+  cudaEvent_t produced = take_event(p), done = take_event(p);
+  cudaError_t e = cudaEventRecord(produced, p->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->comm_stream, produced, 0);
+  give_event(p, produced);
+  if (e == cudaSuccess) {
+    if (p->precision == RM_F64) p2p_combine_kernel<double><<<1, 32, 0, p->comm_stream>>>(s->mine, s->world, t, (double*)dst, s->d_err);
+    else p2p_combine_kernel<float><<<1, 32, 0, p->comm_stream>>>(s->mine, s->world, t, (float*)dst, s->d_err);
+    e = cudaGetLastError();
+  }
+  const int b = (int)(t % P2P_BANKS);
+  if (e == cudaSuccess) e = cudaEventRecord(s->combine_done[b], p->comm_stream);
+  if (e == cudaSuccess) { s->recorded[b] = true; e = cudaEventRecord(done, p->comm_stream); }
+  if (e != cudaSuccess) { give_event(p, done); rm_free(p, out); return fail(RM_ERROR, "p2p exchange: %s", cudaGetErrorString(e)); }
+  count_launch(p);
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = p->buffers.find(out->buffer_id);
+  if (it != p->buffers.end()) it->second.ready = done; else cudaStreamWaitEvent(p->stream, done, 0);
+  return RM_OK;
+}
+
+namespace {
+
+void p2p_destroy(rm_provider* p) {
+  P2PState* s = p2p_state(p);
+  if (!s) return;
+  for (int q = 0; q < s->world; ++q)
+    if (s->peers[q] && s->peers[q] != s->mine) cudaIpcCloseMemHandle(s->peers[q]);
+  for (int b = 0; b < P2P_BANKS; ++b) if (s->combine_done[b]) cudaEventDestroy(s->combine_done[b]);
+  if (s->d_peers) cudaFree(s->d_peers);
+  if (s->d_err) cudaFree(s->d_err);
+  if (s->mine) cudaFree(s->mine);
+  cudaGetLastError();
+  delete s;
+  p->p2p = nullptr;
+}
+
+rm_status ensure_comm_stream(rm_provider* p) {
+  if (p->comm_stream) return RM_OK;
+  // Highest priority: the exchange's few CTAs must get an SM slot as soon as any compute CTA retires.
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  RM_CUDA(cudaStreamCreateWithPriority(&p->comm_stream, cudaStreamNonBlocking, prio_greatest));
+  return RM_OK;
+}
+
 }  // namespace
 
 void comm_destroy(rm_provider* p) {
   if (p->comm_stream) cudaStreamSynchronize(p->comm_stream);
+  p2p_destroy(p);
   if (p->nccl_comm && nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)p->nccl_comm);
   p->nccl_comm = nullptr;
   if (p->comm_stream) { cudaStreamDestroy(p->comm_stream); p->comm_stream = nullptr; }
@@ -103,30 +252,112 @@ RM_EXPORT rm_status rm_comm_init(rm_provider* p, const uint8_t* unique_id, uint3
   ncclComm_t comm = nullptr;
   const int r = nccl().CommInitRank(&comm, (int)world, id, (int)rank);
   RM_REQUIRE(r == 0 && comm, RM_ERROR, "ncclCommInitRank(rank %u of %u): %s", rank, world, nccl().GetErrorString(r));
-  // Highest priority: the collective's few CTAs must get SM slots as soon as any compute CTA retires. At default priority the
-  // all-reduce queued behind a resident 592-CTA reduction / 8192-CTA elementwise kernel only starts ~a kernel later, which eats
-  // the one-step slack of a pipelined caller (r04: +25 us/step at N >= 2).
-  int prio_least = 0, prio_greatest = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-  cudaError_t e = cudaStreamCreateWithPriority(&p->comm_stream, cudaStreamNonBlocking, prio_greatest);
-  if (e != cudaSuccess) { nccl().CommDestroy(comm); return fail(RM_ERROR, "comm_init: stream: %s", cudaGetErrorString(e)); }
+  if (ensure_comm_stream(p) != RM_OK) { std::string m = last_error(); nccl().CommDestroy(comm); return fail(RM_ERROR, "comm_init: stream: %s", m.c_str()); }
   p->nccl_comm = comm;
   p->comm_rank = (int)rank;
   p->comm_world = (int)world;
   return RM_OK;
 }
 
-RM_EXPORT uint32_t rm_comm_world_size(rm_provider* p) { return p && p->nccl_comm ? (uint32_t)p->comm_world : 1u; }
+RM_EXPORT uint32_t rm_comm_world_size(rm_provider* p) {
+  if (!p) return 1u;
+  if (p->nccl_comm) return (uint32_t)p->comm_world;
+  P2PState* s = p2p_state(p);
+  return s && s->connected ? (uint32_t)s->world : 1u;
+}
+
+// Allocates this rank's slot buffer and returns its CUDA IPC handle (64 bytes) for the host to ship to every rank.
+RM_EXPORT rm_status rm_comm_p2p_export(rm_provider* p, uint8_t* handle_out, uint32_t len) {
+  RM_REQUIRE(p && handle_out && len >= RM_COMM_P2P_HANDLE_BYTES, RM_INVALID_ARG, "comm_p2p_export: need a %d-byte buffer", RM_COMM_P2P_HANDLE_BYTES);
+  static_assert(sizeof(cudaIpcMemHandle_t) == RM_COMM_P2P_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(p->ordinal);
+  std::lock_guard<std::mutex> lk(p->comm_mu);
+  RM_REQUIRE(!p->p2p, RM_ERROR, "comm_p2p_export: already exported");
+  std::unique_ptr<P2PState> s(new P2PState());
+  RM_CUDA(cudaMalloc((void**)&s->mine, sizeof(P2PSlots)));
+  RM_CUDA(cudaMemset(s->mine, 0, sizeof(P2PSlots)));
+  RM_CUDA(cudaMalloc((void**)&s->d_peers, sizeof(P2PSlots*) * P2P_MAXR));
+  RM_CUDA(cudaMalloc((void**)&s->d_err, sizeof(int)));
+  RM_CUDA(cudaMemset(s->d_err, 0, sizeof(int)));
+  RM_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  RM_CUDA(cudaIpcGetMemHandle(&h, s->mine));
+  memcpy(handle_out, &h, sizeof h);
+  p->p2p = s.release();
+  return RM_OK;
+}
+
+// `all_handles` = world x 64 bytes in rank order (this rank's own entry is ignored). world == 1 connects the rank to itself
+// (the full protocol on one GPU: used by the single-GPU tests).
+RM_EXPORT rm_status rm_comm_p2p_connect(rm_provider* p, const uint8_t* all_handles, uint32_t len, uint32_t rank, uint32_t world) {
+  RM_REQUIRE(p && all_handles && world >= 1 && world <= (uint32_t)P2P_MAXR && rank < world && len >= world * RM_COMM_P2P_HANDLE_BYTES, RM_INVALID_ARG,
+             "comm_p2p_connect: bad arguments (world <= %d)", P2P_MAXR);
+  DeviceGuard g(p->ordinal);
+  std::lock_guard<std::mutex> lk(p->comm_mu);
+  P2PState* s = p2p_state(p);
+  RM_REQUIRE(s && s->mine, RM_ERROR, "comm_p2p_connect: call rm_comm_p2p_export first");
+  RM_REQUIRE(!s->connected, RM_ERROR, "comm_p2p_connect: already connected");
+  RM_TRY(ensure_comm_stream(p));
+  for (uint32_t q = 0; q < world; ++q) {
+    if (q == rank) { s->peers[q] = s->mine; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + (size_t)q * RM_COMM_P2P_HANDLE_BYTES, sizeof h);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (uint32_t k = 0; k < q; ++k) if (k != rank && s->peers[k]) { cudaIpcCloseMemHandle(s->peers[k]); s->peers[k] = nullptr; }
+      return fail(RM_UNSUPPORTED, "comm_p2p_connect: cudaIpcOpenMemHandle(rank %u): %s", q, cudaGetErrorString(e));
+    }
+    s->peers[q] = (P2PSlots*)ptr;
+  }
+  RM_CUDA(cudaMemcpy(s->d_peers, s->peers, sizeof(P2PSlots*) * P2P_MAXR, cudaMemcpyHostToDevice));
+  for (int b = 0; b < P2P_BANKS; ++b) RM_CUDA(cudaEventCreateWithFlags(&s->combine_done[b], cudaEventDisableTiming));
+  s->world = (int)world;
+  s->rank = (int)rank;
+  s->connected = true;
+  return RM_OK;
+}
+RM_EXPORT int rm_comm_p2p_connected(rm_provider* p) {
+  P2PState* s = p ? p2p_state(p) : nullptr;
+  return s && s->connected ? 1 : 0;
+}
+// 1 when a combine's bounded wait ran out (a peer never published): waits for the communication stream.
+RM_EXPORT rm_status rm_comm_p2p_error(rm_provider* p, int32_t* err) {
+  RM_REQUIRE(p && err, RM_INVALID_ARG, "comm_p2p_error: bad arguments");
+  *err = 0;
+  P2PState* s = p2p_state(p);
+  if (!s || !s->connected) return RM_OK;
+  DeviceGuard g(p->ordinal);
+  RM_CUDA(cudaStreamSynchronize(p->comm_stream));
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
+  int h = 0;
+  RM_CUDA(cudaMemcpy(&h, s->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  *err = h;
+  return RM_OK;
+}
 
 // out = sum over ranks of `in` (element-wise, same shape on every rank). The copy of `in` is ordered on the compute stream, the
 // collective runs in place on that copy on the communication stream, and `out` becomes usable through its ready event.
 RM_EXPORT rm_status rm_comm_allreduce_sum(rm_provider* p, const rm_handle* in, rm_handle* out) {
   RM_REQUIRE(p && in && out, RM_INVALID_ARG, "comm_allreduce_sum: bad arguments");
-  RM_REQUIRE(p->nccl_comm, RM_ERROR, "comm_allreduce_sum: rm_comm_init has not been called");
   DeviceGuard g(p->ordinal);
   void *src, *dst;
   uint64_t n;
   RM_TRY(resolve(p, in, &src, &n));
+  if (n == 1) {
+    // scalar exchange over peer memory (the sharded paths' final sum): publish into every peer's slot, lazy combine
+    std::lock_guard<std::mutex> lk(p->comm_mu);
+    P2PPublish pub;
+    if (p2p_begin(p, &pub)) {
+      if (p->precision == RM_F64) p2p_publish_kernel<double><<<1, 32, 0, p->stream>>>((P2PSlots* const*)pub.peers, (int)pub.n, (int)pub.rank, pub.step, (const double*)src);
+      else p2p_publish_kernel<float><<<1, 32, 0, p->stream>>>((P2PSlots* const*)pub.peers, (int)pub.n, (int)pub.rank, pub.step, (const float*)src);
+      RM_LAUNCH_CHECK();
+      count_launch(p);
+      return p2p_finish(p, out);
+    }
+  }
+  RM_REQUIRE(p->nccl_comm, RM_ERROR, "comm_allreduce_sum: neither rm_comm_init nor rm_comm_p2p_connect has been called");
   RM_TRY(alloc_tensor(p, in->shape, in->rank, out, &dst));
   if (n == 0) return RM_OK;
   cudaEvent_t copied = take_event(p), done = take_event(p);

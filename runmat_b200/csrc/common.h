@@ -105,9 +105,16 @@ struct rm_provider {
   rm::DispatchCounter t_fused_elementwise, t_fused_reduction, t_matmul, t_linsolve, t_mldivide, t_mrdivide;
   std::atomic<uint64_t> upload_bytes{0}, download_bytes{0}, cache_hits{0}, cache_misses{0}, kernel_launches{0};
 
-  // scratch
+  // scratch. `scratch_mu` is held from ensure_scratch() through pointer capture to the launch that uses the scratch, so a
+  // concurrent caller cannot re-allocate it underneath an enqueue (the stream then orders the kernels themselves).
+  std::mutex scratch_mu;
   void* reduce_scratch = nullptr;   // partial sums + tickets for two-stage reductions
   size_t reduce_scratch_bytes = 0;
+  // gemm_ozaki.cu workspace (slices, exponents, device flags, tensor maps); oz_mu is held across one product's enqueues
+  std::mutex oz_mu;
+  void* oz_ws = nullptr;
+  // number of times an entry point blocked the host on the device (download, read_scalar, synchronize, find, mldivide's gate ...)
+  std::atomic<uint64_t> host_syncs{0};
   void* l2_flush = nullptr;
   size_t l2_flush_bytes = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -120,6 +127,8 @@ struct rm_provider {
   void* nccl_comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   int comm_rank = 0, comm_world = 1;
+  std::mutex comm_mu;   // one exchange (publish + combine enqueue) at a time
+  void* p2p = nullptr;  // comm.cu: peer-memory slot exchange state
 
   rm::FusedCache* fused = nullptr;
 
@@ -148,6 +157,14 @@ inline uint64_t handle_elems(const rm_handle* h) { return shape_elems(h->shape, 
 // Allocates a device buffer of `elems` elements (provider precision) and fills `out` with a fresh handle.
 rm_status alloc_tensor(rm_provider* p, const uint64_t* shape, uint32_t rank, rm_handle* out, void** dptr);
 void comm_destroy(rm_provider* p);
+// comm.cu peer-memory exchange: parameters of the publish tail fused into a producing kernel
+struct P2PPublish {
+  void* const* peers = nullptr;  // device array of per-rank slot buffers
+  uint32_t n = 0, rank = 0;
+  uint64_t step = 0;
+};
+bool p2p_begin(rm_provider* p, P2PPublish* pub);     // caller holds p->comm_mu until p2p_finish()
+rm_status p2p_finish(rm_provider* p, rm_handle* out);
 // Resolves a handle to its device pointer, validating device_id and element count.
 rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* elems);
 rm_status ensure_scratch(rm_provider* p, size_t bytes);
@@ -202,16 +219,26 @@ rm_status run_elementwise_program(rm_provider* p, const ElementwiseProgram& prog
 rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, const std::string& key, RedOp op,
                                 RedLayout layout, const rm_handle* inputs, uint32_t n_inputs,
                                 const uint64_t* out_shape, uint32_t rank, uint64_t reduce_len,
-                                uint64_t num_slices, uint64_t inner, int use_div, double factor, rm_handle* out);
+                                uint64_t num_slices, uint64_t inner, int use_div, double factor, rm_handle* out,
+                                const struct P2PPublish* publish = nullptr, double param0 = 0.0);
 // NVRTC-only compile (no device needed): used by CPU tests of the lowering and by rm_warmup.
 rm_status compile_cuda_to_cubin(const std::string& src, const char* name, std::vector<char>* cubin, std::string* log);
 
 // ---- other translation units ---------------------------------------------------------------------------------
 rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, const rm_matmul_epilogue* ep, rm_handle* out);
-// gemm_ozaki.cu: f64 GEMM on tcgen05 (int8 Ozaki split). *used=false => caller must run the DMMA engine.
+// gemm_ozaki.cu: f64 GEMM on tcgen05 (int8 Ozaki split). *used=false => shape outside the engine's range, caller runs the
+// DMMA engine unconditionally; *used=true => caller enqueues the DMMA kernel CONDITIONALLY on `guard` (device flags: non-finite
+// inputs or tiles that failed the element-wise accuracy guard), while still holding p->oz_mu.
+struct OzGuard {
+  const int* flags = nullptr;      // flags[0] != 0: recompute every tile
+  const int* tileflags = nullptr;  // per 128x256 Ozaki tile, m fastest
+  int tiles_m = 0;
+};
 rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double* C, uint64_t m, uint64_t n, uint64_t k,
-                       const rm_matmul_epilogue* epd, const void* prow, const void* pcol, void* pdiag, bool ep_active, bool* used);
+                       const rm_matmul_epilogue* epd, const void* prow, const void* pcol, void* pdiag, bool ep_active, bool* used, OzGuard* guard);
 int ozaki_default_slices();
+void ozaki_workspace_destroy(rm_provider* p);
+rm_status ozaki_last_stats(rm_provider* p, int out[4]);
 rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const double* B, uint64_t ldb, double* C, uint64_t ldc,
                             uint64_t m, uint64_t n, uint64_t k);
 

@@ -318,7 +318,7 @@ rm_status run_elementwise_program(rm_provider* p, const ElementwiseProgram& prog
 rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, const std::string& key, RedOp op,
                                 RedLayout layout, const rm_handle* inputs, uint32_t n_inputs,
                                 const uint64_t* out_shape, uint32_t rank, uint64_t reduce_len,
-                                uint64_t num_slices, uint64_t inner, int use_div, double factor, rm_handle* out) {
+                                uint64_t num_slices, uint64_t inner, int use_div, double factor, rm_handle* out, const P2PPublish* publish, double param0) {
   RM_REQUIRE(n_inputs == prog.n_inputs, RM_INVALID_ARG, "fused_reduction: shader declares %u inputs, got %u", prog.n_inputs, n_inputs);
   RM_REQUIRE((p->precision == RM_F64) == (prog.scalar_ty == "f64"), RM_INVALID_ARG,
              "fused_reduction: shader scalar type %s does not match provider precision", prog.scalar_ty.c_str());
@@ -333,6 +333,7 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
                (unsigned long long)elems, (unsigned long long)reduce_len, (unsigned long long)num_slices);
   }
   if (num_slices == 1) layout = RedLayout::Contig;
+  RM_REQUIRE(!publish || num_slices == 1, RM_INVALID_ARG, "fused_reduction_allreduce: only scalar ('all') reductions are exchanged");
   void* out_ptr = nullptr;
   RM_TRY(alloc_tensor(p, out_shape, rank, out, &out_ptr));
 
@@ -374,6 +375,8 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       block = dim3(256);
       partial_elems = chunks > 1 ? chunks * num_slices : 0;
     }
+    // held across ensure -> pointer capture -> launch: a concurrent host thread may not re-allocate the scratch in between
+    std::lock_guard<std::mutex> scratch_lock(p->scratch_mu);
     st = ensure_scratch(p, partial_elems * (sizeof(double) + sizeof(uint32_t)) + 256);
     if (st == RM_OK) {
       double* partial = (double*)p->reduce_scratch;
@@ -394,6 +397,15 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       args.push_back(&bps);
       args.push_back(&inner_arg);
       args.push_back(&sl);
+      // fused peer-memory publish of the scalar result (comm.cu); n == 0 disables the tail
+      void* const* pub_peers = publish ? publish->peers : nullptr;
+      uint32_t pub_n = publish ? publish->n : 0, pub_rank = publish ? publish->rank : 0;
+      unsigned long long pub_step = publish ? publish->step : 0;
+      args.push_back(&pub_peers);
+      args.push_back(&pub_n);
+      args.push_back(&pub_rank);
+      args.push_back(&pub_step);
+      args.push_back(&param0);  // free scalar of the value expression (`p0`), e.g. the strike of the payoff reduction
       st = launch(p, kern, grid, block, args.data());
     }
   }

@@ -329,7 +329,9 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return dflt;
 }
 int red_unroll() { return env_int("RUNMAT_B200_RED_UNROLL", 2, 1, 8); }
-int red_minblocks() { return env_int("RUNMAT_B200_RED_MINB", 0, 0, 8); }
+// 4 resident CTAs/SM (<= 64 registers) + two independent accumulators: 49.2 us vs 53.9 us for the r01 structure on the headline
+// reduction (profiles/r04_harness_results.txt: occupancy is the lever, a third/fourth accumulator costs registers and loses)
+int red_minblocks() { return env_int("RUNMAT_B200_RED_MINB", 4, 0, 8); }
 
 std::string input_params(uint32_t n_inputs) {
   std::string s;
@@ -424,9 +426,12 @@ std::string emit_reduction_cuda(const ReductionProgram& prog, RedOp op, RedLayou
   o << R"CUDA(
 // canonical NaN, as the reference's reduction shader writes it (fusion.rs:1958-1962)
 #define CANON_NAN __longlong_as_double(0x7ff8000000000000LL)
-__device__ __forceinline__ void accumulate(double& acc, bool& saw_nan, T val) {
-#if TRACK_NAN
-  if (val != val) { if (!OMITNAN) saw_nan = true; } else { acc = COMBINE(acc, (double)val); }
+// NaN handling without per-element bookkeeping: in include mode a NaN term poisons the accumulator by itself (x + NaN,
+// x * NaN) and finish() canonicalises; in omit mode NaN terms are replaced by the identity (branch-free select);
+// max/min use fmax/fmin, which ignore NaN like f64::max (simple_provider.rs:7375).
+__device__ __forceinline__ void accumulate(double& acc, T val) {
+#if TRACK_NAN && OMITNAN
+  acc = COMBINE(acc, (val != val) ? IDENT : (double)val);
 #else
   acc = COMBINE(acc, (double)val);
 #endif
@@ -447,10 +452,24 @@ __device__ __forceinline__ double block_reduce(double v, double* smem) {
   if (warp == 0) { r = lane < nwarp ? smem[lane] : IDENT; r = warp_reduce(r); }
   return r;  // valid in warp 0
 }
-__device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, double factor) {
+__device__ __forceinline__ T finish(double acc, int use_div, double factor) {
   double r = use_div ? acc / factor : acc * factor;
-  if (saw_nan) r = CANON_NAN;
+  if (r != r) r = CANON_NAN;
   return (T)r;
+}
+// Fused exchange tail (comm.cu protocol): the block that produced the final scalar stores it into slot [bank][rank] of every
+// rank's peer-mapped slot buffer and releases the step flag (system scope), one thread per destination rank. Peer stores go
+// over NVLink; nothing waits here, the fold happens in the consumer's combine.
+#define P2P_BANKS 8
+#define P2P_MAXR 16
+__device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 rank, u64 step, double value) {
+  if (threadIdx.x < n) {
+    char* base = (char*)peers[threadIdx.x];
+    const u64 slot = (step % P2P_BANKS) * P2P_MAXR + rank;
+    *(double*)(base + slot * 8) = value;
+    unsigned long long* flag = (unsigned long long*)(base + (u64)P2P_BANKS * P2P_MAXR * 8 + slot * 8);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(step + 1) : "memory");
+  }
 }
 )CUDA";
 
@@ -461,12 +480,14 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     else o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(";
     o << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
-         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl) {\n";
+         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n";
     o << "  __shared__ double smem[32];\n  __shared__ bool is_last;\n";
     o << "  const u64 slice = blockIdx.x / bps;\n  const u32 bidx = blockIdx.x % bps;\n  const u64 base = slice * len;\n";
     o << "  const u64 nvec = vec_ok ? len / VEC : 0;\n";
     o << "  const u64 tid = (u64)bidx * blockDim.x + threadIdx.x;\n  const u64 nthr = (u64)bps * blockDim.x;\n";
-    o << "  double acc = IDENT; bool saw_nan = false;\n";
+    // two independent accumulators (even / odd vector lanes): halves the dependent DADD chain, fixed fold order at the end
+    o << "  double acc0 = IDENT, acc1 = IDENT;\n";
     o << "  u64 i = tid;\n";
     // U 256-bit vectors per input in flight per thread per iteration (all loads issued before any math)
     o << "  for (; i + (u64)(RED_U - 1) * nthr < nvec; i += (u64)RED_U * nthr) {\n";
@@ -478,26 +499,25 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     o << "    }\n";
     o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n      #pragma unroll\n      for (int l = 0; l < VEC; ++l) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = a" << k << "[u].x[l];\n";
-    o << "        accumulate(acc, saw_nan, " << prog.val_expr << ");\n      }\n    }\n  }\n";
+    o << "        if (l & 1) accumulate(acc1, " << prog.val_expr << "); else accumulate(acc0, " << prog.val_expr << ");\n      }\n    }\n  }\n";
     o << "  for (; i < nvec; i += nthr) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "    const vec_t a" << k << " = ldv(in" << k << " + base + i * VEC);\n";
     o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = a" << k << ".x[l];\n";
-    o << "      accumulate(acc, saw_nan, " << prog.val_expr << ");\n    }\n  }\n";
+    o << "      if (l & 1) accumulate(acc1, " << prog.val_expr << "); else accumulate(acc0, " << prog.val_expr << ");\n    }\n  }\n";
     o << "  for (u64 g = nvec * VEC + tid; g < len; g += nthr) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "    const T v" << k << " = in" << k << "[base + g];\n";
-    o << "    accumulate(acc, saw_nan, " << prog.val_expr << ");\n  }\n";
+    o << "    accumulate(acc0, " << prog.val_expr << ");\n  }\n";
     o << R"CUDA(
-  const int any_nan = __syncthreads_or(saw_nan ? 1 : 0);
-  double total = block_reduce(acc, smem);
+  double total = block_reduce(COMBINE(acc0, acc1), smem);
   if (bps == 1) {
-    if (threadIdx.x == 0) out[slice] = finish(total, any_nan != 0, use_div, factor);
+    if (threadIdx.x == 0) { const T r = finish(total, use_div, factor); out[slice] = r; smem[0] = (double)r; }
+    if (pub_n) { __syncthreads(); publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]); }
     return;
   }
   // two-stage, atomic-free on the data path: partials are combined by the LAST block in a fixed order
   if (threadIdx.x == 0) {
     partial[slice * bps + bidx] = total;
-    pflags[slice * bps + bidx] = (u32)any_nan;
     __threadfence();
     const u32 t = atomicAdd(&tickets[slice], 1u);
     is_last = (t == bps - 1);
@@ -505,14 +525,11 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  double acc2 = IDENT; int nan2 = 0;
-  for (u32 b = threadIdx.x; b < bps; b += blockDim.x) {
-    acc2 = COMBINE(acc2, __ldcg(&partial[slice * bps + b]));
-    nan2 |= (int)__ldcg(&pflags[slice * bps + b]);
-  }
-  nan2 = __syncthreads_or(nan2);
+  double acc2 = IDENT;
+  for (u32 b = threadIdx.x; b < bps; b += blockDim.x) acc2 = COMBINE(acc2, __ldcg(&partial[slice * bps + b]));
   double total2 = block_reduce(acc2, smem);
-  if (threadIdx.x == 0) { out[slice] = finish(total2, nan2 != 0, use_div, factor); tickets[slice] = 0; }
+  if (threadIdx.x == 0) { const T r = finish(total2, use_div, factor); out[slice] = r; tickets[slice] = 0; smem[0] = (double)r; }
+  if (pub_n) { __syncthreads(); publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]); }
 }
 )CUDA";
   } else {
@@ -522,13 +539,14 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     // same deterministic last-block finish as the contiguous layout.
     o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(" << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
-         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl) {\n";
-    o << "  __shared__ bool is_last;\n  __shared__ double sacc[256];\n  __shared__ u32 snan[256];\n";
+         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n";
+    o << "  __shared__ bool is_last;\n  __shared__ double sacc[256];\n";
     o << "  const u32 sloc = threadIdx.x % sl, lane = threadIdx.x / sl, rl = blockDim.x / sl;\n";
     o << "  const u64 s = (u64)blockIdx.x * sl + sloc;\n";
     o << "  const u64 chunk = (len + gridDim.y - 1) / gridDim.y;\n";
     o << "  const u64 r0 = (u64)blockIdx.y * chunk; const u64 r1 = r0 + chunk < len ? r0 + chunk : len;\n";
-    o << "  double acc = IDENT; bool saw_nan = false;\n";
+    o << "  double acc = IDENT, accb = IDENT;\n";
     o << "  const u64 sbase = (s % inner) + (s / inner) * inner * len;\n";
     o << "  if (s < num_slices) {\n    u64 r = r0 + lane;\n";
     o << "    for (; r + 3 * (u64)rl < r1; r += 4 * (u64)rl) {\n";
@@ -537,25 +555,24 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     for (int u = 0; u < 4; ++u) {
       o << "      {\n";
       for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = w" << u << "_" << k << ";\n";
-      o << "        accumulate(acc, saw_nan, " << prog.val_expr << ");\n      }\n";
+      o << "        accumulate(" << ((u & 1) ? "accb" : "acc") << ", " << prog.val_expr << ");\n      }\n";
     }
     o << "    }\n    for (; r < r1; r += rl) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = in" << k << "[sbase + r * inner];\n";
-    o << "      accumulate(acc, saw_nan, " << prog.val_expr << ");\n    }\n  }\n";
+    o << "      accumulate(acc, " << prog.val_expr << ");\n    }\n  }\n";
     o << R"CUDA(
+  acc = COMBINE(acc, accb);
   sacc[threadIdx.x] = acc;
-  snan[threadIdx.x] = saw_nan ? 1u : 0u;
   __syncthreads();
-  u32 nanf = saw_nan ? 1u : 0u;
   if (lane == 0) {
-    for (u32 l = 1; l < rl; ++l) { acc = COMBINE(acc, sacc[l * sl + sloc]); nanf |= snan[l * sl + sloc]; }
+    for (u32 l = 1; l < rl; ++l) acc = COMBINE(acc, sacc[l * sl + sloc]);
   }
   const bool owner = lane == 0 && s < num_slices;
   if (gridDim.y == 1) {
-    if (owner) out[s] = finish(acc, nanf != 0, use_div, factor);
+    if (owner) out[s] = finish(acc, use_div, factor);
     return;
   }
-  if (owner) { partial[(u64)blockIdx.y * num_slices + s] = acc; pflags[(u64)blockIdx.y * num_slices + s] = nanf; }
+  if (owner) partial[(u64)blockIdx.y * num_slices + s] = acc;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) { const u32 t = atomicAdd(&tickets[blockIdx.x], 1u); is_last = (t == gridDim.y - 1); }
@@ -569,15 +586,15 @@ __device__ __forceinline__ T finish(double acc, bool saw_nan, int use_div, doubl
     const u32 W = 256 / sl;
     const u32 fs = threadIdx.x % sl, fy = threadIdx.x / sl;
     const u64 gs = (u64)blockIdx.x * sl + fs;
-    double acc2 = IDENT; u32 nan2 = 0;
+    double acc2 = IDENT;
     if (gs < num_slices)
-      for (u32 y = fy; y < gridDim.y; y += W) { acc2 = COMBINE(acc2, __ldcg(&partial[(u64)y * num_slices + gs])); nan2 |= __ldcg(&pflags[(u64)y * num_slices + gs]); }
+      for (u32 y = fy; y < gridDim.y; y += W) acc2 = COMBINE(acc2, __ldcg(&partial[(u64)y * num_slices + gs]));
+    __syncthreads();  // every thread has finished reading sacc from the first fold
     sacc[threadIdx.x] = acc2;
-    snan[threadIdx.x] = nan2;
     __syncthreads();
     if (threadIdx.x < sl && gs < num_slices) {
-      for (u32 w = 1; w < W; ++w) { acc2 = COMBINE(acc2, sacc[w * sl + fs]); nan2 |= snan[w * sl + fs]; }
-      out[gs] = finish(acc2, nan2 != 0, use_div, factor);
+      for (u32 w = 1; w < W; ++w) acc2 = COMBINE(acc2, sacc[w * sl + fs]);
+      out[gs] = finish(acc2, use_div, factor);
     }
   }
   if (threadIdx.x == 0) tickets[blockIdx.x] = 0;

@@ -71,8 +71,10 @@ template <bool ALIGNED2>
 __global__ void __launch_bounds__(256, 1)
 dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                   uint64_t m, uint64_t n, uint64_t k, uint64_t lda, uint64_t ldb, uint64_t ldc, int subtract,
-                  const __grid_constant__ Epilogue ep) {
+                  const __grid_constant__ Epilogue ep, const __grid_constant__ OzGuard guard) {
   extern __shared__ __align__(16) double smem[];
+  // conditional mode (behind the tcgen05 engine): only tiles its accuracy guard / non-finite scan handed over are computed
+  if (guard.flags && !(guard.flags[0] | guard.tileflags[blockIdx.x + (blockIdx.y >> 1) * guard.tiles_m])) return;
   double* As = smem;                              // [STAGES][BK][LDA_S]
   double* Bs = smem + (size_t)STAGES * A_STAGE;   // [STAGES][BN][LDB_S]
 
@@ -278,11 +280,16 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
     // engine selection: 1 = DMMA, 2 = Ozaki/tcgen05, 0 = auto (tcgen05 once the 128x256 tile grid can fill the SMs)
     const uint64_t oz_tiles = ((m + 127) / 128) * ((n + 255) / 256);
     const bool want_ozaki = p->matmul_engine == 2 || (p->matmul_engine == 0 && oz_tiles >= 96 && k >= 512 && !getenv("RUNMAT_B200_DISABLE_OZAKI"));
+    OzGuard guard{};
+    std::unique_lock<std::mutex> oz_lock(p->oz_mu, std::defer_lock);
     if (want_ozaki) {
+      // The tcgen05 engine never blocks the host: what it cannot do (Inf/NaN, entries whose terms hide under the row/column
+      // maximum) is marked in device flags, and the DMMA kernel below runs conditionally on them in the same stream.
+      oz_lock.lock();
       bool used = false;
-      st = ozaki_matmul(p, (const double*)pa, (const double*)pb, (double*)pc, m, n, k, epd, prow, pcol, pdiag, active, &used);
-      if (st != RM_OK) { std::string msg = last_error(); rm_free(p, out); set_error("%s", msg.c_str()); return st; }
-      if (used) return RM_OK;
+      st = ozaki_matmul(p, (const double*)pa, (const double*)pb, (double*)pc, m, n, k, epd, prow, pcol, pdiag, active, &used, &guard);
+      if (st != RM_OK) { std::string msg = last_error(); oz_lock.unlock(); rm_free(p, out); set_error("%s", msg.c_str()); return st; }
+      if (!used) { guard = OzGuard{}; oz_lock.unlock(); }
     }
     Epilogue ep{};
     ep.alpha = 1.0;
@@ -295,10 +302,10 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
     const bool aligned = (m % 2 == 0) && (k % 2 == 0);
     if (aligned) {
       cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-      dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, m, k, m, 0, ep);
+      dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, m, k, m, 0, ep, guard);
     } else {
       cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-      dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, m, k, m, 0, ep);
+      dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>((const double*)pa, (const double*)pb, (double*)pc, m, n, k, m, k, m, 0, ep, guard);
     }
   } else {
     EpilogueF ep{};
@@ -327,10 +334,10 @@ rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const
   const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A) % 16 == 0) && (((uintptr_t)B) % 16 == 0);
   if (aligned) {
     cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep);
+    dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
   } else {
     cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep);
+    dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
   }
   RM_LAUNCH_CHECK();
   count_launch(p);

@@ -190,8 +190,11 @@ struct NormParams {
 // f32 storage: pow as WGSL defines it, exp2(y * log2(x)) with the full-precision (non-approximate) log2f/exp2f — the
 // accuracy class of the reference's own f32 shader (shaders/image_normalize.rs) at a fraction of powf's cost
 // (powf carries double-float internals; ncu r02: the normalise sweep was compute-bound on it, SM throughput 81 %).
+// The shortcut is only taken for a >= 0 (what clamp_zero guarantees); a negative base (gamma without the clamp) goes
+// through powf so that e.g. (-x)^2 is x^2 and not NaN, like the host's f32::powf and the generic kernel below.
 __device__ __forceinline__ float rm_powT(float a, float b) {
   if (b == 0.0f) return 1.0f;
+  if (a < 0.0f) return powf(a, b);
   return exp2f(b * log2f(a));
 }
 __device__ __forceinline__ double rm_powT(double a, double b) { return pow(a, b); }
@@ -255,7 +258,7 @@ normalize_kernel(const T* __restrict__ x, T* __restrict__ y, uint64_t B, uint64_
       if (np.has_gain) val *= (T)np.gain;
       if (np.has_bias) val += (T)np.bias;
       if (np.clamp_zero) val = val > (T)0 ? val : (T)0;  // f64::max(v, 0.0): NaN -> 0
-      if (np.has_gamma) val = sizeof(T) == 4 ? (T)powf((float)val, (float)np.gamma) : (T)pow((double)val, np.gamma);
+      if (np.has_gamma) val = rm_powT(val, (T)np.gamma);  // the same pow as the fixed-lane kernel: the result must not depend on the path taken
       v[l] = val;
       if (++b == B) b = 0;
     }
@@ -539,6 +542,7 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   uint32_t nblocks = fast_blocks ? fast_blocks : (uint32_t)std::min<uint64_t>((uint64_t)sms * 2, std::max<uint64_t>(1, P / (lanes * 4ull)));
   const size_t partial_bytes = (size_t)nblocks * 2 * B * sizeof(double);
   const size_t stats_off = ((partial_bytes + 255) / 256) * 256;
+  std::lock_guard<std::mutex> scratch_lock(p->scratch_mu);  // held until the kernels that use the scratch are enqueued
   rm_status st = ensure_scratch(p, stats_off + 2 * B * sizeof(double));
   if (st != RM_OK) { rm_free(p, out); return st; }
   double* partial = (double*)p->reduce_scratch;
@@ -731,6 +735,6 @@ RM_EXPORT rm_status rm_warmup(rm_provider* p) {
   if (st == RM_OK) { rm_free(p, &b); st = rm_reduce_sum(p, &a, &c); }
   if (st == RM_OK) rm_free(p, &c);
   rm_free(p, &a);
-  if (st == RM_OK) RM_CUDA(cudaStreamSynchronize(p->stream));
+  if (st == RM_OK) { RM_CUDA(cudaStreamSynchronize(p->stream)); p->host_syncs.fetch_add(1, std::memory_order_relaxed); }
   return st;
 }

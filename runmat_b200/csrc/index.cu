@@ -143,6 +143,7 @@ rm_status find_impl(rm_provider* p, const rm_handle* a, int has_limit, uint64_t 
     find_count_kernel<T><<<wblocks, 256, 0, st>>>((const T*)src, n, counts, nseg);
     scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, nseg, dtotal);
     cudaMemcpyAsync(&found, dtotal, 8, cudaMemcpyDeviceToHost, st);
+    p->host_syncs.fetch_add(1, std::memory_order_relaxed);
     cudaStreamSynchronize(st);  // the output size is data-dependent: one 8-byte read
     count_launch(p, 2);
     if (found > 0) {
@@ -267,6 +268,7 @@ RM_EXPORT rm_status rm_sub2ind(rm_provider* p, const uint64_t* dims, const uint6
   count_launch(p);
   int herr = 0;
   cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, p->stream);
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   cudaStreamSynchronize(p->stream);  // the host raises on a bad subscript, so the call must know before returning
   cudaFreeAsync(derr, p->stream);
   RM_LAUNCH_CHECK();
@@ -305,6 +307,7 @@ RM_EXPORT rm_status rm_ind2sub(rm_provider* p, const uint64_t* dims, const uint6
   count_launch(p);
   int herr = 0;
   cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, p->stream);
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   cudaStreamSynchronize(p->stream);
   cudaFreeAsync(derr, p->stream);
   if (herr) { drop(); return index_error("ind2sub", herr); }

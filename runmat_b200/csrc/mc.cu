@@ -225,11 +225,10 @@ RM_EXPORT rm_status rm_payoff_partial_sum(rm_provider* p, const rm_handle* state
   ReductionProgram prog;
   prog.scalar_ty = p->precision == RM_F64 ? "f64" : "f32";
   prog.n_inputs = 1;
-  char expr[96];
-  snprintf(expr, sizeof expr, "fmax((v0 - (T)%.17g), (T)0)", strike);
-  prog.val_expr = expr;
+  // the strike rides in as the kernel's free scalar p0: one cached kernel serves every strike (and non-finite strikes)
+  prog.val_expr = "fmax((v0 - (T)p0), (T)0)";
   uint64_t one[2] = {1, 1};
   const uint64_t n = handle_elems(state);
   if (n == 0) return rm_fill(p, one, 2, 0.0, out);
-  return run_reduction_program(p, prog, std::string("payoff:") + expr, RedOp::Sum, RedLayout::Contig, state, 1, one, 2, n, 1, 1, 0, 1.0, out);
+  return run_reduction_program(p, prog, "payoff", RedOp::Sum, RedLayout::Contig, state, 1, one, 2, n, 1, 1, 0, 1.0, out, nullptr, strike);
 }

@@ -134,32 +134,44 @@ uint64_t text_hash(const char* s, size_t* len_out) {
   *len_out = n;
   return h;
 }
+// The cache is keyed by the FULL shader text (a 64-bit hash alone could silently run the wrong kernel on a collision); the
+// short key handed to the kernel cache is hash:len, made unique with a suffix if two different texts ever share it.
 template <typename Prog>
 struct ParsedCache {
+  struct Entry { std::shared_ptr<Prog> prog; std::string key; };
   std::mutex mu;
-  std::unordered_map<std::string, std::shared_ptr<Prog>> map;
+  std::unordered_map<std::string, Entry> map;            // shader text -> parsed program + short key
+  std::unordered_map<std::string, uint32_t> short_keys;  // hash:len -> number of distinct texts seen with it
+  static constexpr size_t kMaxEntries = 4096;            // bounded: a caller streaming unique shaders cannot grow it forever
 };
 ParsedCache<ElementwiseProgram> g_ew_cache;
 ParsedCache<ReductionProgram> g_red_cache;
 
 template <typename Prog, typename ParseFn>
 rm_status parsed(ParsedCache<Prog>& cache, const char* shader, ParseFn parse, std::shared_ptr<Prog>* out, std::string* key) {
-  size_t len;
-  const uint64_t h = text_hash(shader, &len);
-  char buf[48];
-  snprintf(buf, sizeof buf, "%016llx:%zu", (unsigned long long)h, len);
-  *key = buf;
+  const std::string text(shader);
   {
     std::lock_guard<std::mutex> lk(cache.mu);
-    auto it = cache.map.find(*key);
-    if (it != cache.map.end()) { *out = it->second; return RM_OK; }
+    auto it = cache.map.find(text);
+    if (it != cache.map.end()) { *out = it->second.prog; *key = it->second.key; return RM_OK; }
   }
   auto prog = std::make_shared<Prog>();
   std::string err;
   if (!parse(shader, prog.get(), &err)) return fail(RM_COMPILE_ERROR, "%s", err.c_str());
+  size_t len;
+  const uint64_t h = text_hash(shader, &len);
+  char buf[64];
+  snprintf(buf, sizeof buf, "%016llx:%zu", (unsigned long long)h, len);
   std::lock_guard<std::mutex> lk(cache.mu);
-  cache.map[*key] = prog;
+  auto it = cache.map.find(text);  // another thread may have parsed the same text meanwhile
+  if (it != cache.map.end()) { *out = it->second.prog; *key = it->second.key; return RM_OK; }
+  if (cache.map.size() >= ParsedCache<Prog>::kMaxEntries) cache.map.clear();  // short_keys is kept: suffixes stay unique
+  const uint32_t dup = cache.short_keys[buf]++;
+  std::string k = buf;
+  if (dup) k += "#" + std::to_string(dup);
+  cache.map[text] = {prog, k};
   *out = prog;
+  *key = k;
   return RM_OK;
 }
 
@@ -275,6 +287,7 @@ RM_EXPORT rm_status rm_fused_reduction(rm_provider* p, const char* shader, const
                                        uint32_t /*workgroup_size: a wgpu tuning hint; CUDA geometry is chosen here*/,
                                        rm_reduction_flavor flavor, double custom_scale, rm_handle* out) {
   RM_REQUIRE(p && shader && inputs && out, RM_INVALID_ARG, "fused_reduction: bad arguments");
+  RM_REQUIRE(reduce_len > 0, RM_ERROR, "fused_reduction: zero reduce_len");  // fusion_exec.rs: the executor rejects it before dispatch
   DeviceGuard g(p->ordinal);
   ScopedWall wall(p->t_fused_reduction);
   std::shared_ptr<ReductionProgram> progp;
@@ -289,6 +302,36 @@ RM_EXPORT rm_status rm_fused_reduction(rm_provider* p, const char* shader, const
   const RedLayout layout = prog.axis == 0 ? RedLayout::Contig : RedLayout::Strided;
   return run_reduction_program(p, prog, "wgsl:" + key, RedOp::Sum, layout, inputs, n_inputs, output_shape, rank,
                                reduce_len, num_slices, /*inner=*/num_slices, use_div, factor, out);
+}
+
+// Sharded form: every rank reduces its own inputs to ONE scalar and the scalars are summed over the ranks of the
+// peer-memory exchange (rm_comm_p2p_connect). The publish into the peers' slots is the tail of the reduction kernel's last
+// block; `out` (1x1) holds the global sum once the lazy combine has run (waited for at first use, like an upload).
+RM_EXPORT rm_status rm_fused_reduction_allreduce(rm_provider* p, const char* shader, const rm_handle* inputs, uint32_t n_inputs, uint64_t reduce_len,
+                                                 rm_reduction_flavor flavor, double custom_scale, rm_handle* out) {
+  RM_REQUIRE(p && shader && inputs && out, RM_INVALID_ARG, "fused_reduction_allreduce: bad arguments");
+  RM_REQUIRE(reduce_len > 0, RM_ERROR, "fused_reduction: zero reduce_len");
+  RM_REQUIRE(p->precision == RM_F64, RM_UNSUPPORTED, "fused_reduction_allreduce: f64 providers only");
+  DeviceGuard g(p->ordinal);
+  ScopedWall wall(p->t_fused_reduction);
+  std::shared_ptr<ReductionProgram> progp;
+  std::string key;
+  RM_TRY(parsed(g_red_cache, shader, parse_reduction_wgsl, &progp, &key));
+  int use_div = 0;
+  double factor = 1.0;
+  if (flavor == RM_FLAVOR_MEAN) { use_div = 1; factor = (double)reduce_len; }
+  else if (flavor == RM_FLAVOR_CUSTOM) factor = custom_scale;
+  std::lock_guard<std::mutex> lk(p->comm_mu);
+  P2PPublish pub;
+  RM_REQUIRE(p2p_begin(p, &pub), RM_ERROR, "fused_reduction_allreduce: rm_comm_p2p_connect has not been called");
+  uint64_t one[2] = {1, 1};
+  rm_handle local;
+  RM_TRY(run_reduction_program(p, *progp, "wgsl:" + key, RedOp::Sum, RedLayout::Contig, inputs, n_inputs, one, 2, reduce_len, 1, 1, use_div, factor, &local, &pub));
+  rm_status st = p2p_finish(p, out);
+  std::string msg = st == RM_OK ? "" : last_error();
+  rm_free(p, &local);
+  if (st != RM_OK) set_error("%s", msg.c_str());
+  return st;
 }
 
 // =============================================================================================================

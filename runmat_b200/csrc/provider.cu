@@ -86,6 +86,7 @@ rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* ele
   return RM_OK;
 }
 
+// Caller holds p->scratch_mu from this call until the launch that consumes the scratch has been enqueued.
 rm_status ensure_scratch(rm_provider* p, size_t bytes) {
   if (bytes <= p->reduce_scratch_bytes) return RM_OK;
   size_t want = std::max<size_t>(bytes, 1 << 20);
@@ -242,6 +243,7 @@ RM_EXPORT rm_status rm_provider_destroy(rm_provider* p) {
   p->buffers.clear();
   if (p->reduce_scratch) cudaFreeAsync(p->reduce_scratch, p->stream);
   if (p->l2_flush) cudaFreeAsync(p->l2_flush, p->stream);
+  ozaki_workspace_destroy(p);
   cudaStreamSynchronize(p->stream);
   comm_destroy(p);
   fused_cache_destroy(p);
@@ -285,6 +287,16 @@ RM_EXPORT rm_status rm_synchronize(rm_provider* p) {
   RM_REQUIRE(p, RM_INVALID_ARG, "null provider");
   DeviceGuard g(p->ordinal);
   RM_CUDA(cudaStreamSynchronize(p->stream));
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
+  return RM_OK;
+}
+RM_EXPORT uint64_t rm_host_sync_count(rm_provider* p) { return p ? p->host_syncs.load() : 0; }
+RM_EXPORT rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4) {
+  RM_REQUIRE(p && out4, RM_INVALID_ARG, "rm_debug_ozaki_stats: bad arguments");
+  DeviceGuard g(p->ordinal);
+  int tmp[4];
+  RM_TRY(ozaki_last_stats(p, tmp));
+  for (int i = 0; i < 4; ++i) out4[i] = tmp[i];
   return RM_OK;
 }
 RM_EXPORT rm_status rm_get_stream(rm_provider* p, void** s) {
@@ -413,6 +425,7 @@ static rm_status download_impl(rm_provider* p, const rm_handle* h, HostT* out, u
     RM_CUDA(cudaFreeAsync(stage, p->stream));
   }
   RM_CUDA(cudaStreamSynchronize(p->stream));
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   p->download_bytes.fetch_add(n * sizeof(HostT), std::memory_order_relaxed);
   return RM_OK;
 }
@@ -473,6 +486,7 @@ RM_EXPORT rm_status rm_read_scalar(rm_provider* p, const rm_handle* h, uint64_t 
     RM_CUDA(cudaStreamSynchronize(p->stream));
     *out = (double)f;
   }
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   p->download_bytes.fetch_add(p->elem_size(), std::memory_order_relaxed);
   return RM_OK;
 }
@@ -781,6 +795,7 @@ RM_EXPORT rm_status rm_timer_end_ms(rm_provider* p, double* ms) {
   DeviceGuard g(p->ordinal);
   RM_CUDA(cudaEventRecord(p->ev_end, p->stream));
   RM_CUDA(cudaEventSynchronize(p->ev_end));
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   float f = 0;
   RM_CUDA(cudaEventElapsedTime(&f, p->ev_begin, p->ev_end));
   *ms = (double)f;
@@ -790,6 +805,7 @@ RM_EXPORT rm_status rm_flush_l2(rm_provider* p) {
   RM_REQUIRE(p, RM_INVALID_ARG, "null provider");
   DeviceGuard g(p->ordinal);
   const size_t bytes = 256ull << 20;  // > 126 MB L2
+  std::lock_guard<std::mutex> lk(p->scratch_mu);
   if (!p->l2_flush) {
     RM_CUDA(cudaMallocAsync(&p->l2_flush, bytes, p->stream));
     p->l2_flush_bytes = bytes;

@@ -571,6 +571,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   SV_CUDA(cudaMemcpyAsync(h_mm, pivmm, 16, cudaMemcpyDeviceToHost, st));
   SV_CUDA(cudaMemcpyAsync(&h_amax, amax, 8, cudaMemcpyDeviceToHost, st));
   SV_CUDA(cudaStreamSynchronize(st));
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   double amaxv;
   memcpy(&amaxv, &h_amax, 8);
   if (h_info[1]) { cleanup(true); return fail(RM_UNSUPPORTED, "mldivide: non-finite input not supported by provider"); }

@@ -120,6 +120,33 @@ class B200Provider:
     def comm_fence(self) -> None:
         _check(lib.rm_comm_fence(self._p))
 
+    def comm_p2p_export(self) -> bytes:
+        """Allocates this rank's peer-exchange slot buffer; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_uint8 * 64)()
+        _check(lib.rm_comm_p2p_export(self._p, buf, 64))
+        return bytes(buf)
+
+    def comm_p2p_connect(self, all_handles: Sequence[bytes], rank: int, world: int) -> None:
+        blob = b"".join(h[:64].ljust(64, b"\0") for h in all_handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(lib.rm_comm_p2p_connect(self._p, buf, len(blob), C.c_uint32(rank), C.c_uint32(world)))
+
+    def comm_p2p_connected(self) -> bool:
+        return bool(lib.rm_comm_p2p_connected(self._p))
+
+    def comm_p2p_error(self) -> int:
+        e = C.c_int32()
+        _check(lib.rm_comm_p2p_error(self._p, C.byref(e)))
+        return int(e.value)
+
+    def fused_reduction_allreduce(self, shader: str, inputs: Sequence[Handle], reduce_len: int, flavor: str = "sum", custom_scale: float = 1.0) -> Handle:
+        """Per-rank fused 'all' reduction + sum over the ranks of the peer-memory exchange (publish fused into the kernel tail)."""
+        arr = (Handle * len(inputs))(*inputs)
+        out = Handle()
+        fl = {"sum": 0, "mean": 1, "custom": 2}[flavor]
+        _check(lib.rm_fused_reduction_allreduce(self._p, shader.encode(), arr, len(inputs), C.c_uint64(reduce_len), fl, C.c_double(custom_scale), C.byref(out)))
+        return out
+
     def pci_bus_id(self) -> str:
         buf = C.create_string_buffer(32)
         _check(lib.rm_device_pci_bus_id(self._p, buf, 32))
@@ -456,6 +483,16 @@ class B200Provider:
         h = Handle()
         _check(lib.rm_diag_extract(self._p, C.byref(matrix), C.c_int64(offset), C.byref(h)))
         return h
+
+    def host_sync_count(self) -> int:
+        """How many entry-point calls have blocked the host on the device so far (rm_host_sync_count)."""
+        return int(lib.rm_host_sync_count(self._p))
+
+    def ozaki_stats(self) -> dict:
+        """Device flags of the last tcgen05 product (waits for the stream): test/debug hook."""
+        out = (C.c_int32 * 4)()
+        _check(lib.rm_debug_ozaki_stats(self._p, out))
+        return {"nonfinite": int(out[0]), "pipeline_error": int(out[1]), "fp64_tiles": int(out[2])}
 
     def set_matmul_engine(self, engine: int) -> None:
         _check(lib.rm_set_matmul_engine(self._p, int(engine)))

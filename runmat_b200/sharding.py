@@ -39,6 +39,37 @@ def batch_slices_for_rank(batch: int, rank: int, world: int) -> Tuple[int, int]:
     return shard_range(batch, rank, world)
 
 
+def split_batch_strided(imgs, rank: int, world: int):
+    """The strided host split of a `[B,H,W]` batch-fastest tensor (element (b,h,w) at b + B*(h + H*w),
+    simple_provider.rs:7937-7938): rank r's images [b0,b1) become their own dense column-major `[b1-b0,H,W]` tensor.
+    `imgs` is a numpy array of shape (B,H,W) in Fortran order (or anything reshapeable to it); returns an F-ordered copy."""
+    import numpy as np
+
+    B = imgs.shape[0]
+    b0, b1 = batch_slices_for_rank(B, rank, world)
+    return np.asfortranarray(imgs[b0:b1, ...])
+
+
+def lcg_image_shard(B: int, H: int, W: int, b0: int, bcount: int, seed: float = 0.0):
+    """Images [b0, b0+bcount) of the deterministic batch of benchmarks/4k-image-processing/runmat_lcg.m:59-79, generated directly
+    in the rank's own `[bcount,H,W]` layout (no global tensor is ever materialised on a rank):
+        idx = (b-1)*H*W + seed + y*W + x;  state = mod(1664525*idx + 1013904223, 2^32);  pixel = single(state)/single(2^32).
+    All products stay below 2^53 for B*H*W < 5.4e9, so integer arithmetic reproduces MATLAB's doubles exactly.
+    Returns float32, Fortran order."""
+    import numpy as np
+
+    if (B * H * W + int(seed)) * 1664525 + 1013904223 >= 2 ** 53:
+        raise ValueError("index range exceeds exact double arithmetic; the script's mod() would round")
+    out = np.empty((bcount, H, W), dtype=np.float32, order="F")
+    yx = (np.arange(H, dtype=np.uint64)[:, None] * np.uint64(W) + np.arange(W, dtype=np.uint64)[None, :])  # [H,W]: y*W + x
+    for k in range(bcount):
+        idx = yx + np.uint64((b0 + k) * H * W + int(seed))
+        state = (np.uint64(1664525) * idx + np.uint64(1013904223)) & np.uint64(0xFFFFFFFF)
+        # single(state) ./ single(2^32): round the integer to f32 first, then divide in f32 (exact: power of two)
+        out[k, :, :] = state.astype(np.float32) / np.float32(4294967296.0)
+    return out
+
+
 def bind_process_to_gpu_numa(pci_bus_id: str):
     """One process per GPU: run this process (and first-touch its pinned host buffers) on the NUMA node the GPU hangs off, so
     H2D/D2H copies do not cross the inter-socket link. Returns {"node": n, "cpus": k} or None when the topology is not exposed

@@ -158,7 +158,9 @@ class Oracle:
                                          int(gamma is not None), C.c_double(gamma or 0), int(clamp_zero))
         return out.reshape((B, H, W), order="F")
 
-    def imfilter(self, img, ker, padding="constant", cval=0.0, shape="same", mode="corr"):
+    def imfilter(self, img, ker, padding="constant", cval=0.0, shape="same", mode="corr", f32=False):
+        if f32:
+            return self._imfilter_f32(img, ker, padding, cval, shape, mode)
         img, ker = np.asarray(img, dtype=np.float64), np.asarray(ker, dtype=np.float64)
         pad = ["constant", "replicate", "symmetric", "circular"].index(padding)
         shp = ["same", "full", "valid"].index(shape)
@@ -170,6 +172,24 @@ class Oracle:
         dims = [oshape[0], oshape[1], oshape[2]]
         out = np.empty(int(np.prod(dims)))
         self.lib.orc_imfilter(_dp(fi), _shape(img.shape), img.ndim, _dp(fk), _shape(ker.shape), ker.ndim, pad, C.c_double(cval), shp, md, _dp(out), oshape)
+        while len(dims) > max(img.ndim, 2) and dims[-1] == 1:
+            dims.pop()
+        return out.reshape(dims, order="F")
+
+    def _imfilter_f32(self, img, ker, padding, cval, shape, mode):
+        img, ker = np.asarray(img, dtype=np.float32), np.asarray(ker, dtype=np.float32)
+        pad = ["constant", "replicate", "symmetric", "circular"].index(padding)
+        shp = ["same", "full", "valid"].index(shape)
+        md = ["corr", "conv"].index(mode)
+        oshape = (C.c_uint64 * 3)()
+        fi = np.ascontiguousarray(img.reshape(-1, order="F"))
+        fk = np.ascontiguousarray(ker.reshape(-1, order="F"))
+        fn = self.lib.orc_imfilter_f32
+        r = fn(fi.ctypes.data_as(_f), _shape(img.shape), img.ndim, fk.ctypes.data_as(_f), _shape(ker.shape), ker.ndim, pad, C.c_float(cval), shp, md, None, oshape)
+        assert r >= 0
+        dims = [oshape[0], oshape[1], oshape[2]]
+        out = np.empty(int(np.prod(dims)), dtype=np.float32)
+        fn(fi.ctypes.data_as(_f), _shape(img.shape), img.ndim, fk.ctypes.data_as(_f), _shape(ker.shape), ker.ndim, pad, C.c_float(cval), shp, md, out.ctypes.data_as(_f), oshape)
         while len(dims) > max(img.ndim, 2) and dims[-1] == 1:
             dims.pop()
         return out.reshape(dims, order="F")
@@ -188,6 +208,13 @@ class Oracle:
         out = np.empty(n)
         new = self.lib.orc_generate_normal(C.c_uint64(state), C.c_uint64(n), _dp(out))
         return out, new
+
+    def stochastic_evolution_sampled(self, rng_state, s0, length, drift, scale, steps, paths):
+        paths = np.ascontiguousarray(paths, dtype=np.uint64)
+        out = np.empty(paths.size)
+        self.lib.orc_stochastic_evolution_sampled(C.c_uint64(rng_state), C.c_double(s0), C.c_uint64(length), C.c_double(drift), C.c_double(scale),
+                                                  C.c_uint32(steps), paths.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(paths.size), _dp(out))
+        return out
 
     def stochastic_evolution(self, rng_state, data, drift, scale, steps):
         d = f64(data).copy()

@@ -131,6 +131,29 @@ def test_normals_are_box_muller_pairs(orc):
     assert abs(big.mean()) < 0.01 and abs(big.std() - 1.0) < 0.01  # runmat-runtime/tests/rng.rs:21-62 style moments
 
 
+def test_sampled_evolution_equals_the_sequential_host_loop(orc):
+    """The sampled replay used for the full-size Monte-Carlo parity check is the sequential host loop, bit for bit, for odd and
+    even lengths (a trailing unpaired element still consumes a whole Box-Muller pair)."""
+    drift, scale = 1.2e-4, 0.0126
+    for n, steps in ((1, 3), (2, 2), (7, 5), (1000, 9), (1001, 4)):
+        s0 = np.full((n, 1), 100.0)
+        want, _ = orc.stochastic_evolution(4242, s0, drift, scale, steps)
+        got = orc.stochastic_evolution_sampled(4242, 100.0, n, drift, scale, steps, np.arange(n))
+        assert np.array_equal(got, want[:, 0])
+    # NaN pixels: Rust's value.max(0.0) maps NaN to 0 (simple_provider.rs:7982); the restatement must too
+    x = np.random.default_rng(1).uniform(0, 1, (2, 4, 4))
+    x[1, 2, 3] = np.nan
+    out = orc.image_normalize(x, 1e-6, gain=1.5, bias=0.1, gamma=None, clamp_zero=True)
+    assert np.all(out[1] == 0.0) and np.all(np.isfinite(out[0]))     # a NaN pixel poisons its image's statistics -> every pixel clamps to 0
+    out = orc.image_normalize(x, 1e-6, gain=1.5, bias=0.1, gamma=None, clamp_zero=False)
+    assert np.all(np.isnan(out[1])) and np.all(np.isfinite(out[0]))
+    # f32 imfilter oracle: same tap order, f32 arithmetic; equal to the f64 one on dyadic data
+    img = np.random.default_rng(2).integers(0, 64, (9, 7, 2)).astype(np.float64) / 64.0
+    ker = np.random.default_rng(3).integers(-8, 8, (3, 3)).astype(np.float64) / 8.0
+    for padding in ("constant", "replicate", "symmetric", "circular"):
+        assert np.array_equal(orc.imfilter(img, ker, padding=padding, f32=True).astype(np.float64), orc.imfilter(img, ker, padding=padding))
+
+
 def test_unary_and_scalar_tables(orc):
     x = np.array([[-2.5, -0.0, 0.0, 0.5, 2.5, np.nan, np.inf]])
     assert_same(orc.unary("round", x), np.array([[-3.0, -0.0, 0.0, 1.0, 3.0, np.nan, np.inf]]))  # half away from zero
