@@ -325,6 +325,17 @@ rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4);
  *      singular or badly conditioned inputs return RM_UNSUPPORTED (host SVD fallback, as with wgpu today) ---- */
 rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_handle* b, rm_handle* out);
 rm_status rm_mrdivide(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, rm_handle* out); /* lhs / rhs, lib.rs:2484 */
+/* linsolve (lib.rs:2422-2429), ProviderLinsolveOptions (lib.rs:681-691), ProviderLinsolveResult (lib.rs:694-697).
+ * On the device: LT / UT triangular systems (TRANSA included; rcond = min|diag|/max|diag| like the host's diagonal_rcond,
+ * zero diagonal and opts.rcond violations raise the host's "singular to working precision" error) and, when no reciprocal
+ * condition number is requested, square general / SYM / POSDEF systems through the LU of rm_mldivide (rcond = NaN).
+ * RECT, and general solves that need the singular-value rcond, return RM_UNSUPPORTED (host fallback). */
+typedef struct rm_linsolve_options {
+  int lower, upper, rectangular, transposed, conjugate, symmetric, posdef, need_rcond;
+  int has_rcond; double rcond; /* Option<f64> */
+} rm_linsolve_options;
+rm_status rm_linsolve(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, const rm_linsolve_options* opt,
+                      rm_handle* solution, double* reciprocal_condition);
 
 /* ---- a10/a11: Monte-Carlo evolution + RNG (lib.rs:1713-1775) -------------------------------------- */
 rm_status rm_set_rng_state(rm_provider* p, uint64_t state);                                     /* :1772 */

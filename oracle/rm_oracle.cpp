@@ -649,6 +649,29 @@ ORC_API void orc_stochastic_evolution_sampled(uint64_t rng_state, double s0, uin
   }
 }
 
+// builtins/math/linalg/solve/linsolve.rs:769-833 (forward_substitution_real / backward_substitution_real): per right-hand
+// side, accum = sum_j T[i,j]*x[j] in ascending j, x[i] = (b[i] - accum) / T[i,i]; rcond = min|diag| / max|diag|
+// (diagonal_rcond, common/linalg.rs:232-238). Returns -1 on a zero diagonal entry ("singular to working precision").
+ORC_API int orc_linsolve_triangular(const double* t, uint64_t n, const double* rhs, uint64_t nrhs, int lower, double* out, double* rcond) {
+  double min_diag = INFINITY, max_diag = 0.0;
+  for (uint64_t i = 0; i < n * nrhs; ++i) out[i] = rhs[i];
+  for (uint64_t col = 0; col < nrhs; ++col) {
+    for (uint64_t step = 0; step < n; ++step) {
+      const uint64_t i = lower ? step : n - 1 - step;
+      const double diag = t[i + i * n], diag_abs = std::fabs(diag);
+      min_diag = std::fmin(min_diag, diag_abs);
+      max_diag = std::fmax(max_diag, diag_abs);
+      if (diag_abs == 0.0) return -1;
+      double accum = 0.0;
+      if (lower) { for (uint64_t j = 0; j < i; ++j) accum += t[i + j * n] * out[j + col * n]; }
+      else { for (uint64_t j = i + 1; j < n; ++j) accum += t[i + j * n] * out[j + col * n]; }
+      out[i + col * n] = (out[i + col * n] - accum) / diag;
+    }
+  }
+  *rcond = max_diag == 0.0 ? 0.0 : min_diag / max_diag;
+  return 0;
+}
+
 // simple_provider.rs:3488-3512 (linspace; last element forced to `stop`)
 ORC_API void orc_linspace(double start, double stop, uint64_t count, double* out) {
   if (count == 0) return;

@@ -80,6 +80,13 @@ class ImageNormalizeDesc(C.Structure):
                 ("has_gamma", C.c_int), ("gamma", C.c_double), ("clamp_zero", C.c_int)]
 
 
+class LinsolveOptions(C.Structure):
+    """ProviderLinsolveOptions (accelerate-api/src/lib.rs:681-691)."""
+
+    _fields_ = [("lower", C.c_int), ("upper", C.c_int), ("rectangular", C.c_int), ("transposed", C.c_int), ("conjugate", C.c_int),
+                ("symmetric", C.c_int), ("posdef", C.c_int), ("need_rcond", C.c_int), ("has_rcond", C.c_int), ("rcond", C.c_double)]
+
+
 class ImfilterOptions(C.Structure):
     _fields_ = [("padding", C.c_int), ("constant_value", C.c_double), ("shape", C.c_int), ("mode", C.c_int)]
 

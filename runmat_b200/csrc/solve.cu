@@ -350,9 +350,11 @@ __global__ void __launch_bounds__(2 * NB) perm_apply_kernel(double* __restrict__
 }
 
 // Solve T * X = Bm in place for a jb x jb triangular block T (ldt) and jb x ncols right-hand sides Bm (ldb).
-// LOWER_UNIT: forward substitution with implicit unit diagonal; otherwise backward substitution with the stored diagonal.
-// One CTA handles 32 columns; T and the column tile live in shared memory.
-template <bool LOWER_UNIT>
+// MODE 1 (TRSM_LOWER_UNIT): forward substitution with implicit unit diagonal (the L of the LU); MODE 0 (TRSM_UPPER): backward
+// substitution with the stored diagonal; MODE 2 (TRSM_LOWER): forward substitution with the stored diagonal (linsolve's
+// general lower-triangular systems). One CTA handles 32 columns; T and the column tile live in shared memory.
+constexpr int TRSM_UPPER = 0, TRSM_LOWER_UNIT = 1, TRSM_LOWER = 2;
+template <int MODE>
 __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restrict__ T, uint64_t ldt, int jb, double* __restrict__ Bm, uint64_t ldb, uint64_t ncols) {
   extern __shared__ double trsm_smem[];
   double (*sT)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem);                    // [NB][NB+1]
@@ -365,8 +367,16 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
   }
   __syncthreads();
   const int col = threadIdx.x & 31, part = threadIdx.x >> 5;  // 8 row-parts per column
-  if (LOWER_UNIT) {
+  if (MODE == TRSM_LOWER_UNIT) {
     for (int i = 0; i < jb; ++i) {
+      const double xi = sB[col][i];
+      for (int k = i + 1 + part; k < jb; k += 8) sB[col][k] -= sT[k][i] * xi;
+      __syncthreads();
+    }
+  } else if (MODE == TRSM_LOWER) {
+    for (int i = 0; i < jb; ++i) {
+      if (part == 0) sB[col][i] = sB[col][i] / sT[i][i];
+      __syncthreads();
       const double xi = sB[col][i];
       for (int k = i + 1 + part; k < jb; k += 8) sB[col][k] -= sT[k][i] * xi;
       __syncthreads();
@@ -398,11 +408,134 @@ __global__ void absmax_kernel(const double* __restrict__ x, uint64_t n, unsigned
   atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 
+// min / max of |diag(T)| (forward/backward_substitution_real track exactly these, linsolve.rs:769-833) as IEEE bit patterns
+__global__ void diag_minmax_kernel(const double* __restrict__ T, uint64_t n, unsigned long long* __restrict__ mm) {
+  double mn = 1.7976931348623157e308 * 2.0, mx = 0.0;  // +inf, 0
+  bool nan = false;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double d = fabs(T[i + i * n]);
+    nan |= d != d;
+    mn = fmin(mn, d);
+    mx = fmax(mx, d);
+  }
+  atomicMin(&mm[0], (unsigned long long)__double_as_longlong(mn));
+  atomicMax(&mm[1], (unsigned long long)__double_as_longlong(mx));
+  if (nan) atomicExch(&mm[2], 1ull);
+}
+
 }  // namespace
 
 }  // namespace rm
 
 using namespace rm;
+
+// linsolve (lib.rs:2422-2476; host semantics: builtins/math/linalg/solve/linsolve.rs:691-726). Device paths, mirroring what
+// the wgpu provider keeps on the device (backend/wgpu/provider/ops/solve.rs:869-950):
+//  * LT / UT (exactly one): blocked forward / backward substitution (64x64 diagonal blocks in shared memory + DMMA updates).
+//    TRANSA solves with A' (one device transpose; the triangle hint flips, linsolve.rs:698-705). A zero diagonal entry is
+//    the host's "singular to working precision" error; rcond = min|diag| / max|diag| (diagonal_rcond, common/linalg.rs:232)
+//    is always returned, and enforced against opts.rcond like enforce_rcond (:1000-1009).
+//  * no structure hint, SYM or POSDEF: square systems go through the LU of rm_mldivide when the caller does not need the
+//    reciprocal condition number (the host derives it from singular values, which an LU cannot reproduce): rcond = NaN, as the
+//    wgpu provider reports when it was not asked for one. Otherwise RM_UNSUPPORTED -> host fallback.
+//  * RECT: RM_UNSUPPORTED.
+RM_EXPORT rm_status rm_linsolve(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, const rm_linsolve_options* opt, rm_handle* solution,
+                                double* reciprocal_condition) {
+  RM_REQUIRE(p && lhs && rhs && opt && solution && reciprocal_condition, RM_INVALID_ARG, "linsolve: bad arguments");
+  RM_REQUIRE(lhs->rank <= 2 && rhs->rank <= 2, RM_ERROR, "linsolve: inputs must be 2-D matrices or vectors");
+  RM_REQUIRE(p->precision == RM_F64, RM_UNSUPPORTED, "linsolve: f32 storage not supported by provider");
+  RM_REQUIRE(!opt->rectangular, RM_UNSUPPORTED, "linsolve: RECT (least-squares) solve not supported by provider");
+  DeviceGuard g(p->ordinal);
+  ScopedWall wall(p->t_linsolve);
+  *reciprocal_condition = NAN;
+  const bool needs_rcond = opt->need_rcond || opt->has_rcond;
+  auto dim = [](const rm_handle* h, int d) -> uint64_t { return d < (int)h->rank ? h->shape[d] : 1; };
+  const uint64_t arows = opt->transposed ? dim(lhs, 1) : dim(lhs, 0), acols = opt->transposed ? dim(lhs, 0) : dim(lhs, 1);
+  const uint64_t brows = dim(rhs, 0), nrhs = dim(rhs, 1);
+  const bool tri = (opt->lower != 0) != (opt->upper != 0) && !opt->symmetric && !opt->posdef;
+  rm_handle a_eff = *lhs;
+  bool own_a = false;
+  auto drop_a = [&]() { if (own_a) rm_free(p, &a_eff); };
+  if (!tri) {
+    RM_REQUIRE(!needs_rcond, RM_UNSUPPORTED, "linsolve: singular-value reciprocal condition estimate not supported by provider");
+    RM_REQUIRE(arows == acols, RM_UNSUPPORTED, "linsolve: non-square general solve not supported by provider");
+    RM_REQUIRE(brows == arows, RM_ERROR, "Matrix dimensions must agree.");  // normalize_rhs_tensor, linsolve.rs:972-984
+    if (opt->transposed) { RM_TRY(rm_transpose(p, lhs, &a_eff)); own_a = true; }
+    rm_handle a2 = a_eff, b2 = *rhs;
+    a2.rank = 2; a2.shape[0] = arows; a2.shape[1] = acols;
+    b2.rank = 2; b2.shape[0] = brows; b2.shape[1] = nrhs;
+    rm_status st = rm_mldivide(p, &a2, &b2, solution);
+    std::string msg = st == RM_OK ? "" : last_error();
+    drop_a();
+    if (st != RM_OK) set_error("%s", msg.c_str());
+    return st;
+  }
+  RM_REQUIRE(arows == acols, RM_ERROR, "linsolve: triangular solves require a square coefficient matrix.");  // ensure_square, :1057-1065
+  const uint64_t n = arows;
+  RM_REQUIRE(brows == n, RM_ERROR, "Matrix dimensions must agree.");
+  uint64_t oshape[2] = {n, nrhs};
+  if (n == 0 || nrhs == 0) return rm_zeros(p, oshape, 2, solution);
+  const bool eff_lower = opt->transposed ? opt->upper != 0 : opt->lower != 0;  // the hint describes A; A' flips it
+  if (opt->transposed) { RM_TRY(rm_transpose(p, lhs, &a_eff)); own_a = true; }
+  void *pa, *pb, *px;
+  rm_status st = resolve(p, &a_eff, &pa, nullptr);
+  if (st == RM_OK) st = resolve(p, rhs, &pb, nullptr);
+  if (st != RM_OK) { std::string m = last_error(); drop_a(); set_error("%s", m.c_str()); return st; }
+  cudaStream_t stream = p->stream;
+  unsigned long long* mm = nullptr;
+  auto bail = [&](rm_status code, const char* msg) { if (mm) cudaFreeAsync(mm, stream); drop_a(); return fail(code, "%s", msg); };
+  if (cudaMallocAsync((void**)&mm, 24, stream) != cudaSuccess) { cudaGetLastError(); return bail(RM_OOM, "linsolve: allocation failed"); }
+  const unsigned long long init[3] = {0x7ff0000000000000ull, 0ull, 0ull};
+  cudaMemcpyAsync(mm, init, 24, cudaMemcpyHostToDevice, stream);
+  diag_minmax_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, stream>>>((const double*)pa, n, mm);
+  count_launch(p);
+  unsigned long long h_mm[3];
+  cudaMemcpyAsync(h_mm, mm, 24, cudaMemcpyDeviceToHost, stream);
+  if (cudaStreamSynchronize(stream) != cudaSuccess) { cudaGetLastError(); return bail(RM_ERROR, "linsolve: device error while scanning the diagonal"); }
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
+  double dmin, dmax;
+  memcpy(&dmin, &h_mm[0], 8);
+  memcpy(&dmax, &h_mm[1], 8);
+  if (dmin == 0.0) return bail(RM_ERROR, "linsolve: matrix is singular to working precision.");
+  const double rcond = h_mm[2] ? NAN : (dmax == 0.0 ? 0.0 : dmin / dmax);  // diagonal_rcond
+  if (opt->has_rcond && rcond < opt->rcond) return bail(RM_ERROR, "linsolve: matrix is singular to working precision.");  // enforce_rcond
+  cudaFreeAsync(mm, stream);
+  mm = nullptr;
+  st = alloc_tensor(p, oshape, 2, solution, &px);
+  if (st != RM_OK) { std::string m = last_error(); drop_a(); set_error("%s", m.c_str()); return st; }
+  const double* T = (const double*)pa;
+  double* X = (double*)px;
+  cudaMemcpyAsync(X, pb, n * nrhs * 8, cudaMemcpyDeviceToDevice, stream);
+  constexpr size_t TRSM_SMEM = (size_t)(NB + 32) * (NB + 1) * sizeof(double);
+  cudaFuncSetAttribute(trsm_block_kernel<TRSM_LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
+  cudaFuncSetAttribute(trsm_block_kernel<TRSM_UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
+  const unsigned tgrid = (unsigned)((nrhs + 31) / 32);
+  if (eff_lower) {
+    for (uint64_t j0 = 0; j0 < n && st == RM_OK; j0 += NB) {
+      const int jb = (int)std::min<uint64_t>(NB, n - j0);
+      trsm_block_kernel<TRSM_LOWER><<<tgrid, 256, TRSM_SMEM, stream>>>(T + j0 + j0 * n, n, jb, X + j0, n, nrhs);
+      count_launch(p);
+      const uint64_t rest = n - j0 - jb;
+      if (rest > 0) st = dgemm_sub_strided(p, T + (j0 + jb) + j0 * n, n, X + j0, n, X + j0 + jb, n, rest, nrhs, (uint64_t)jb);
+    }
+  } else {
+    for (uint64_t jend = n; jend > 0 && st == RM_OK;) {
+      const uint64_t j0 = ((jend - 1) / NB) * NB;
+      const int jb = (int)(jend - j0);
+      trsm_block_kernel<TRSM_UPPER><<<tgrid, 256, TRSM_SMEM, stream>>>(T + j0 + j0 * n, n, jb, X + j0, n, nrhs);
+      count_launch(p);
+      if (j0 > 0) st = dgemm_sub_strided(p, T + j0 * n, n, X + j0, n, X, n, j0, nrhs, (uint64_t)jb);
+      jend = j0;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (st == RM_OK && e != cudaSuccess) st = fail(RM_ERROR, "linsolve launch failed: %s", cudaGetErrorString(e));
+  std::string msg = st == RM_OK ? "" : last_error();
+  drop_a();
+  if (st != RM_OK) { rm_free(p, solution); set_error("%s", msg.c_str()); return st; }
+  *reciprocal_condition = rcond;
+  return RM_OK;
+}
 
 RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_handle* b, rm_handle* out) {
   RM_REQUIRE(p && a && b && out, RM_INVALID_ARG, "mldivide: bad arguments");
@@ -453,8 +586,8 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
 #define SV_TRY(expr) do { rm_status _s = (expr); if (_s != RM_OK) { std::string _m = last_error(); cleanup(true); set_error("%s", _m.c_str()); return _s; } } while (0)
 
   constexpr size_t TRSM_SMEM = (size_t)(NB + 32) * (NB + 1) * sizeof(double);
-  cudaFuncSetAttribute(trsm_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
-  cudaFuncSetAttribute(trsm_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
+  cudaFuncSetAttribute(trsm_block_kernel<TRSM_LOWER_UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
+  cudaFuncSetAttribute(trsm_block_kernel<TRSM_UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->ordinal);
   RM_REQUIRE(coop, RM_UNSUPPORTED, "mldivide: cooperative launch not supported on this device");
@@ -545,7 +678,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     const uint64_t rest_in = Jend - (j0 + jb);  // columns of the outer block still to factor
     if (rest_in > 0) {
       // inside the outer block: A12 <- L11^-1 A12 ; A22 -= A21 * A12
-      trsm_block_kernel<true><<<(unsigned)((rest_in + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest_in);
+      trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((rest_in + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest_in);
       count_launch(p);
       SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, LU + j0 + (j0 + jb) * n, n, LU + (j0 + jb) + (j0 + jb) * n, n, rest, rest_in, (uint64_t)jb));
     } else if (Jend < n) {
@@ -553,7 +686,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
       const uint64_t right = n - Jend;
       for (uint64_t i0 = J0; i0 < Jend; i0 += NB) {
         const int ib = (int)std::min<uint64_t>(NB, Jend - i0);
-        trsm_block_kernel<true><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, st>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
+        trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, st>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
         count_launch(p);
         const uint64_t below = Jend - (i0 + ib);
         if (below > 0) SV_TRY(dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, LU + i0 + Jend * n, n, LU + (i0 + ib) + Jend * n, n, below, right, (uint64_t)ib));
@@ -583,7 +716,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   // forward substitution: L y = P b
   for (uint64_t j0 = 0; j0 < n; j0 += NB) {
     const int jb = (int)std::min<uint64_t>(NB, n - j0);
-    trsm_block_kernel<true><<<(unsigned)((nrhs + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, X + j0, n, nrhs);
+    trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((nrhs + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, X + j0, n, nrhs);
     count_launch(p);
     const uint64_t rest = n - j0 - jb;
     if (rest > 0) SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, X + j0, n, X + j0 + jb, n, rest, nrhs, (uint64_t)jb));
@@ -592,7 +725,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   for (uint64_t jend = n; jend > 0;) {
     const uint64_t j0 = ((jend - 1) / NB) * NB;
     const int jb = (int)(jend - j0);
-    trsm_block_kernel<false><<<(unsigned)((nrhs + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, X + j0, n, nrhs);
+    trsm_block_kernel<TRSM_UPPER><<<(unsigned)((nrhs + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, X + j0, n, nrhs);
     count_launch(p);
     if (j0 > 0) SV_TRY(dgemm_sub_strided(p, LU + j0 * n, n, X + j0, n, X, n, j0, nrhs, (uint64_t)jb));
     jend = j0;

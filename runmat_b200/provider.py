@@ -458,6 +458,15 @@ class B200Provider:
 
     def mrdivide(self, lhs, rhs): return self._named2(lib.rm_mrdivide, lhs, rhs)
 
+    def linsolve(self, lhs: Handle, rhs: Handle, lower=False, upper=False, rectangular=False, transposed=False, conjugate=False, symmetric=False,
+                 posdef=False, need_rcond=False, rcond: Optional[float] = None) -> tuple[Handle, float]:
+        """ProviderLinsolveResult{solution, reciprocal_condition} (lib.rs:2422-2429, 694-697)."""
+        o = _capi.LinsolveOptions(int(lower), int(upper), int(rectangular), int(transposed), int(conjugate), int(symmetric), int(posdef), int(need_rcond),
+                                  int(rcond is not None), float(rcond or 0.0))
+        out, rc = Handle(), C.c_double()
+        _check(lib.rm_linsolve(self._p, C.byref(lhs), C.byref(rhs), C.byref(o), C.byref(out), C.byref(rc)))
+        return out, rc.value
+
     def conv2d(self, signal: Handle, kernel: Handle, mode: str = "full") -> Handle:
         h = Handle()
         _check(lib.rm_conv2d(self._p, C.byref(signal), C.byref(kernel), ["full", "same", "valid"].index(mode), C.byref(h)))

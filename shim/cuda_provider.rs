@@ -5,14 +5,16 @@
 //! `cargo`/`rustc`, so it is not compiled or tested here (INTEGRATION.md says how it slots into the reference).
 //! Every method is a 1:1 forward; anything the C library reports as RM_UNSUPPORTED keeps the trait's default
 //! ("... not supported by provider"), so callers fall back to host exactly as they do today.
+//! `tests/test_shim_coverage.py` parses this file, include/rm_accel.h and (when present) the reference trait, and fails when an
+//! exported entry point with a trait counterpart is not forwarded here or a forwarded method's arity differs from the trait's.
 
 use anyhow::{anyhow, Result};
 use runmat_accelerate_api::{
     AccelDownloadFuture, AccelProvider, AccelProviderFuture, ApiDeviceInfo, GpuTensorHandle, GpuTensorStorage,
     CovNormalization, CovRows, CovarianceOptions, FindDirection, HostTensorOwned, HostTensorView, ImageNormalizeDescriptor,
     ImfilterMode, ImfilterOptions, ImfilterPadding, ImfilterShape, MatmulEpilogue, PowerStepEpilogue, ProviderConvMode,
-    ProviderDispatchStats, ProviderFindResult, ProviderMoments2, ProviderPrecision, ProviderTelemetry, ReduceDimResult,
-    ReductionFlavor, ScaleOp,
+    ProviderDispatchStats, ProviderFindResult, ProviderLinsolveOptions, ProviderLinsolveResult, ProviderMoments2, ProviderPrecision,
+    ProviderTelemetry, ReduceDimResult, ReductionFlavor, ScaleOp, SpawnHandleConcurrency,
 };
 use std::ffi::{c_char, c_int, c_void, CStr, CString};
 
@@ -65,6 +67,20 @@ pub struct RmImfilterOptions {
     pub constant_value: f64,
     pub shape: c_int,          // rm_imfilter_shape: same, full, valid
     pub mode: c_int,           // rm_imfilter_mode: correlation, convolution
+}
+
+#[repr(C)]
+pub struct RmLinsolveOptions {
+    pub lower: c_int,
+    pub upper: c_int,
+    pub rectangular: c_int,
+    pub transposed: c_int,
+    pub conjugate: c_int,
+    pub symmetric: c_int,
+    pub posdef: c_int,
+    pub need_rcond: c_int,
+    pub has_rcond: c_int,
+    pub rcond: f64,
 }
 
 #[repr(C)]
@@ -150,6 +166,16 @@ extern "C" {
     fn rm_reduce_mean_nd(p: *mut c_void, a: *const RmHandle, dims: *const u32, n: u32, out: *mut RmHandle) -> c_int;
     fn rm_reduce_moments_nd(p: *mut c_void, a: *const RmHandle, dims: *const u32, n: u32, mean: *mut RmHandle, ex2: *mut RmHandle) -> c_int;
     fn rm_warmup(p: *mut c_void) -> c_int;
+    fn rm_ones(p: *mut c_void, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_reshape(p: *mut c_void, h: *const RmHandle, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_random_uniform(p: *mut c_void, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_random_normal(p: *mut c_void, shape: *const u64, rank: u32, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_max(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_min(p: *mut c_void, a: *const RmHandle, out: *mut RmHandle) -> c_int;
+    fn rm_reduce_min_dim(p: *mut c_void, a: *const RmHandle, dim: u32, vals: *mut RmHandle, idx: *mut RmHandle) -> c_int;
+    fn rm_linsolve(p: *mut c_void, lhs: *const RmHandle, rhs: *const RmHandle, opt: *const RmLinsolveOptions, solution: *mut RmHandle, rcond: *mut f64) -> c_int;
+    fn rm_default_reduction_workgroup_size(p: *mut c_void) -> u32;
+    fn rm_two_pass_threshold(p: *mut c_void) -> u64;
 }
 
 pub struct CudaProvider {
@@ -208,6 +234,12 @@ impl CudaProvider {
     fn unary(&self, op: c_int, a: &GpuTensorHandle) -> Result<GpuTensorHandle> {
         let (ra, mut out) = (to_raw(a)?, empty_raw());
         check(unsafe { rm_unary(self.raw, op, &ra, &mut out) })?;
+        Ok(from_raw(&out))
+    }
+    fn ctor(&self, f: unsafe extern "C" fn(*mut c_void, *const u64, u32, *mut RmHandle) -> c_int, shape: &[usize]) -> Result<GpuTensorHandle> {
+        let s: Vec<u64> = shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { f(self.raw, s.as_ptr(), s.len() as u32, &mut out) })?;
         Ok(from_raw(&out))
     }
     fn scalar(&self, op: c_int, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> {
@@ -276,6 +308,25 @@ impl AccelProvider for CudaProvider {
         check(unsafe { rm_fill(self.raw, s.as_ptr(), s.len() as u32, value, &mut out) })?;
         Ok(from_raw(&out))
     }
+    fn ones(&self, shape: &[usize]) -> Result<GpuTensorHandle> { self.ctor(rm_ones, shape) }
+    fn zeros_like(&self, prototype: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.zeros(&prototype.shape) }
+    fn ones_like(&self, prototype: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.ctor(rm_ones, &prototype.shape) }
+    fn fill_like(&self, prototype: &GpuTensorHandle, value: f64) -> Result<GpuTensorHandle> { self.fill(&prototype.shape, value) }
+    fn random_uniform(&self, shape: &[usize]) -> Result<GpuTensorHandle> { self.ctor(rm_random_uniform, shape) }
+    fn random_uniform_like(&self, prototype: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.ctor(rm_random_uniform, &prototype.shape) }
+    fn random_normal(&self, shape: &[usize]) -> Result<GpuTensorHandle> { self.ctor(rm_random_normal, shape) }
+    fn random_normal_like(&self, prototype: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.ctor(rm_random_normal, &prototype.shape) }
+    fn reshape(&self, handle: &GpuTensorHandle, new_shape: &[usize]) -> Result<GpuTensorHandle> {
+        // metadata-only, like the trait default (lib.rs:2676-2684); the library additionally rejects element-count changes
+        let s: Vec<u64> = new_shape.iter().map(|&d| d as u64).collect();
+        let mut out = empty_raw();
+        check(unsafe { rm_reshape(self.raw, &to_raw(handle)?, s.as_ptr(), s.len() as u32, &mut out) })?;
+        Ok(GpuTensorHandle { shape: new_shape.to_vec(), device_id: handle.device_id, buffer_id: handle.buffer_id })
+    }
+    fn spawn_handle_concurrency(&self) -> SpawnHandleConcurrency {
+        // handles are immutable ids into a mutex-guarded table; every result is a new buffer except scatter_linear / diag_output
+        SpawnHandleConcurrency::ImmutableShare
+    }
     fn linspace(&self, start: f64, stop: f64, count: usize) -> Result<GpuTensorHandle> {
         let mut out = empty_raw();
         check(unsafe { rm_linspace(self.raw, start, stop, count as u64, &mut out) })?;
@@ -311,7 +362,44 @@ impl AccelProvider for CudaProvider {
     fn unary_log<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(14, a)) }
     fn unary_sqrt<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(18, a)) }
     fn unary_abs<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(19, a)) }
-    // ... the remaining unary_* methods forward the same way with their rm_unary_op code.
+    fn unary_tan<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(2, a)) }
+    fn unary_asin<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(3, a)) }
+    fn unary_acos<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(4, a)) }
+    fn unary_atan<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(5, a)) }
+    fn unary_sinh<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(6, a)) }
+    fn unary_cosh<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(7, a)) }
+    fn unary_asinh<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(9, a)) }
+    fn unary_acosh<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(10, a)) }
+    fn unary_atanh<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(11, a)) }
+    fn unary_expm1<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(13, a)) }
+    fn unary_log2<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(15, a)) }
+    fn unary_log10<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(16, a)) }
+    fn unary_log1p<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(17, a)) }
+    fn unary_sign<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(20, a)) }
+    fn unary_floor<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(21, a)) }
+    fn unary_ceil<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(22, a)) }
+    fn unary_round<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(23, a)) }
+    fn unary_fix<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(24, a)) }
+    fn unary_pow2<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(26, a)) }
+    fn unary_heaviside<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(27, a)) }
+    fn unary_single<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(28, a)) }
+    fn unary_double<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(29, a)) }
+    fn unary_erf<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(35, a)) }
+    fn unary_gamma<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(36, a)) }
+    fn unary_gammaln<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.unary(37, a)) }
+    fn logical_isnan(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.unary(30, a) }
+    fn logical_isinf(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.unary(31, a) }
+    fn logical_isfinite(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.unary(32, a) }
+    fn map_nan_to_zero(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.unary(33, a) }
+    fn not_nan_mask(&self, a: &GpuTensorHandle) -> Result<GpuTensorHandle> { self.unary(34, a) }
+    fn elem_hypot<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(7, a, b)) }
+    fn elem_atan2<'a>(&'a self, y: &'a GpuTensorHandle, x: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(8, y, x)) }
+    fn elem_ge<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(11, a, b)) }
+    fn elem_le<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(12, a, b)) }
+    fn elem_lt<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(13, a, b)) }
+    fn elem_gt<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(14, a, b)) }
+    fn elem_eq<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(15, a, b)) }
+    fn elem_ne<'a>(&'a self, a: &'a GpuTensorHandle, b: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> { ready!(self.binary(16, a, b)) }
     fn scalar_add(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(0, a, s) }
     fn scalar_sub(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(1, a, s) }
     fn scalar_mul(&self, a: &GpuTensorHandle, s: f64) -> Result<GpuTensorHandle> { self.scalar(2, a, s) }
@@ -362,6 +450,21 @@ impl AccelProvider for CudaProvider {
     fn reduce_mean<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
         ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_mean(self.raw, &to_raw(a)?, &mut out) })?; Ok(from_raw(&out)) })
     }
+    fn reduce_max<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_max(self.raw, &to_raw(a)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_min<'a>(&'a self, a: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
+        ready!({ let mut out = empty_raw(); check(unsafe { rm_reduce_min(self.raw, &to_raw(a)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn reduce_min_dim<'a>(&'a self, a: &'a GpuTensorHandle, dim: usize) -> AccelProviderFuture<'a, ReduceDimResult> {
+        ready!({
+            let (mut v, mut i) = (empty_raw(), empty_raw());
+            check(unsafe { rm_reduce_min_dim(self.raw, &to_raw(a)?, dim as u32, &mut v, &mut i) })?;
+            Ok(ReduceDimResult { values: from_raw(&v), indices: from_raw(&i) })
+        })
+    }
+    fn default_reduction_workgroup_size(&self) -> u32 { unsafe { rm_default_reduction_workgroup_size(self.raw) } }
+    fn two_pass_threshold(&self) -> usize { unsafe { rm_two_pass_threshold(self.raw) as usize } }
     fn reduce_max_dim<'a>(&'a self, a: &'a GpuTensorHandle, dim: usize) -> AccelProviderFuture<'a, ReduceDimResult> {
         ready!({
             let (mut v, mut i) = (empty_raw(), empty_raw());
@@ -416,6 +519,19 @@ impl AccelProvider for CudaProvider {
     fn mldivide<'a>(&'a self, lhs: &'a GpuTensorHandle, rhs: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
         // RM_UNSUPPORTED (least-squares / singular / ill-conditioned) surfaces as Err => host SVD path, as with wgpu today
         ready!({ let mut out = empty_raw(); check(unsafe { rm_mldivide(self.raw, &to_raw(lhs)?, &to_raw(rhs)?, &mut out) })?; Ok(from_raw(&out)) })
+    }
+    fn linsolve<'a>(&'a self, lhs: &'a GpuTensorHandle, rhs: &'a GpuTensorHandle, o: &'a ProviderLinsolveOptions) -> AccelProviderFuture<'a, ProviderLinsolveResult> {
+        // triangular systems and (without an rcond request) square general systems stay on the device; everything else is Err => host
+        ready!({
+            let raw = RmLinsolveOptions {
+                lower: o.lower as c_int, upper: o.upper as c_int, rectangular: o.rectangular as c_int, transposed: o.transposed as c_int,
+                conjugate: o.conjugate as c_int, symmetric: o.symmetric as c_int, posdef: o.posdef as c_int, need_rcond: o.need_rcond as c_int,
+                has_rcond: o.rcond.is_some() as c_int, rcond: o.rcond.unwrap_or(0.0),
+            };
+            let (mut out, mut rcond) = (empty_raw(), f64::NAN);
+            check(unsafe { rm_linsolve(self.raw, &to_raw(lhs)?, &to_raw(rhs)?, &raw, &mut out, &mut rcond) })?;
+            Ok(ProviderLinsolveResult { solution: from_raw(&out), reciprocal_condition: rcond })
+        })
     }
     fn mrdivide<'a>(&'a self, lhs: &'a GpuTensorHandle, rhs: &'a GpuTensorHandle) -> AccelProviderFuture<'a, GpuTensorHandle> {
         ready!({ let mut out = empty_raw(); check(unsafe { rm_mrdivide(self.raw, &to_raw(lhs)?, &to_raw(rhs)?, &mut out) })?; Ok(from_raw(&out)) })

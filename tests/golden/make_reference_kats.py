@@ -150,6 +150,20 @@ kats = {
         {"src": "runmat-runtime/src/builtins/stats/random/stochastic_evolution.rs:40-51 cpu_fallback_handles_zero_scale (tol 1e-12): S*exp(drift*steps)",
          "state": [1.0, 2.0], "drift": 0.1, "scale": 0.0, "steps": 3},
     ],
+    # runmat-runtime/src/builtins/math/linalg/solve/linsolve.rs tests (tolerance 1e-7, approx_eq :1111-1113)
+    "linsolve": [
+        {"src": "linsolve.rs:1209-1220 linsolve_basic_square", "a": {"shape": [2, 2], "data": [2, 1, 1, 2]}, "b": {"shape": [2, 1], "data": [4, 5]},
+         "opts": {}, "out": {"shape": [2, 1], "data": [1, 2]}},
+        {"src": "linsolve.rs:1224-1246 linsolve_lower_triangular_hint", "a": {"shape": [3, 3], "data": [3, -1, 4, 0, 2, 1, 0, 0, 5]},
+         "b": {"shape": [3, 1], "data": [9, 1, 19]}, "opts": {"lower": True}, "out": {"shape": [3, 1], "data": [3, 2, 1]}},
+        # linsolve_transposed_triangular_hint (:1250-1282) asserts equality with the general solve of A' x = b; A' = [3 1 0; 0 4 2; 0 0 5],
+        # b = [5 14 23]'  ->  x3 = 4.6, x2 = (14 - 9.2)/4 = 1.2, x1 = (5 - 1.2)/3
+        {"src": "linsolve.rs:1250-1282 linsolve_transposed_triangular_hint", "a": {"shape": [3, 3], "data": [3, 1, 0, 0, 4, 2, 0, 0, 5]},
+         "b": {"shape": [3, 1], "data": [5, 14, 23]}, "opts": {"lower": True, "transposed": True},
+         "out": {"shape": [3, 1], "data": [(5 - 1.2) / 3, 1.2, 4.6]}},
+        {"src": "linsolve.rs:1434-1465 linsolve_recovers_rcond_output (identity, LT hint added: rcond = 1)", "a": {"shape": [2, 2], "data": [1, 0, 0, 1]},
+         "b": {"shape": [2, 1], "data": [1, 2]}, "opts": {"lower": True, "need_rcond": True}, "out": {"shape": [2, 1], "data": [1, 2]}, "rcond": 1.0},
+    ],
     "linspace": [
         {"src": "runmat-accelerate/src/simple_provider.rs:3488-3512 (last element forced to stop)", "start": 0.0, "stop": 1.0, "count": 5,
          "out": [0.0, 0.25, 0.5, 0.75, 1.0]},

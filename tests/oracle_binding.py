@@ -221,6 +221,18 @@ class Oracle:
         new = self.lib.orc_stochastic_evolution(C.c_uint64(rng_state), _dp(d), C.c_uint64(d.size), C.c_double(drift), C.c_double(scale), C.c_uint32(steps))
         return d.reshape(np.asarray(data).shape, order="F"), new
 
+    def linsolve_triangular(self, t, rhs, lower: bool):
+        """Returns (solution, rcond) or raises ValueError('singular') like the host's error."""
+        t, rhs = np.asarray(t, dtype=np.float64), np.asarray(rhs, dtype=np.float64)
+        n, nrhs = t.shape[0], rhs.shape[1]
+        ft_, fr = f64(t), f64(rhs)
+        out = np.empty(n * nrhs)
+        rc = C.c_double()
+        r = self.lib.orc_linsolve_triangular(_dp(ft_), C.c_uint64(n), _dp(fr), C.c_uint64(nrhs), int(lower), _dp(out), C.byref(rc))
+        if r != 0:
+            raise ValueError("singular")
+        return out.reshape((n, nrhs), order="F"), rc.value
+
     def conv2d(self, sig, ker, mode):
         sig, ker = np.asarray(sig, dtype=np.float64), np.asarray(ker, dtype=np.float64)
         m = ["full", "same", "valid"].index(mode)

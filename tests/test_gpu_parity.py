@@ -908,6 +908,62 @@ def test_matmul_8192_properties(prov, orc):
 # ---------------------------------------------------------------------------------------------------------------
 # a9: mldivide (device LU; the reference pins this path by residual only: mldivide.rs:662-676)
 # ---------------------------------------------------------------------------------------------------------------
+def test_linsolve_kats_triangular_and_general(prov, orc):
+    """linsolve (lib.rs:2422-2476): the reference's own literals, then larger triangular systems against the oracle's restatement of
+    forward/backward_substitution_real (blocked device TRSM vs the sequential host loop: 1e-10 relative to the solve's conditioning),
+    TRANSA, rcond reporting / enforcement, the singular error, and the LU route for unstructured systems."""
+    for k in KATS["linsolve"]:
+        o = k["opts"]
+        x, rc = prov.linsolve(prov.upload(arr(k["a"])), prov.upload(arr(k["b"])), **o)
+        assert_same(prov.download(x), arr(k["out"]), tol=1e-7)    # the reference's approx_eq (linsolve.rs:1111-1113)
+        if "rcond" in k:
+            assert abs(rc - k["rcond"]) < 1e-7
+    rng = np.random.default_rng(606)
+    for n, nrhs in ((5, 1), (64, 3), (65, 33), (300, 70), (1000, 17)):
+        full = rng.uniform(-1, 1, (n, n)) + np.eye(n) * rng.uniform(2, 6, n) * np.sqrt(n)   # the other triangle holds garbage on purpose
+        b = rng.uniform(-1, 1, (n, nrhs))
+        for lower in (True, False):
+            tri = np.tril(full) if lower else np.triu(full)
+            want, want_rc = orc.linsolve_triangular(full, b, lower)
+            x, rc = prov.linsolve(prov.upload(full), prov.upload(b), lower=lower, upper=not lower, need_rcond=True)
+            got = prov.download(x)
+            scale = np.abs(np.linalg.inv(tri)) @ (np.abs(tri) @ np.abs(want) + np.abs(b))   # componentwise forward-error bound of a triangular solve
+            assert np.all(np.abs(got - want) <= 1e-10 * scale), (n, nrhs, lower, np.max(np.abs(got - want) / scale))
+            assert rc == want_rc
+            # TRANSA: solve with A' -- the hint describes A, so the effective triangle flips
+            xt, rct = prov.linsolve(prov.upload(np.asfortranarray(full.T)), prov.upload(b), lower=not lower, upper=lower, transposed=True)
+            assert np.all(np.abs(prov.download(xt) - want) <= 1e-10 * scale) and rct == want_rc
+    # singular / rcond enforcement: the host's message (linsolve.rs:783-786, 1000-1009)
+    t = np.diag([1.0, 0.0, 3.0]) + np.tril(np.ones((3, 3)), -1)
+    with pytest.raises(ProviderError, match="singular to working precision"):
+        prov.linsolve(prov.upload(t), prov.upload(np.ones((3, 1))), lower=True)
+    t = np.diag([1.0, 1e-6, 3.0])
+    with pytest.raises(ProviderError, match="singular to working precision"):
+        prov.linsolve(prov.upload(t), prov.upload(np.ones((3, 1))), upper=True, rcond=1e-3)
+    x, rc = prov.linsolve(prov.upload(t), prov.upload(np.ones((3, 1))), upper=True, rcond=1e-9)
+    assert abs(rc - 1e-6 / 3.0) < 1e-18
+    with pytest.raises(ProviderError, match="square"):
+        prov.linsolve(prov.upload(np.ones((3, 2))), prov.upload(np.ones((3, 1))), lower=True)
+    with pytest.raises(ProviderError, match="dimensions must agree"):
+        prov.linsolve(prov.upload(np.eye(3)), prov.upload(np.ones((2, 1))), lower=True)
+    # unstructured / SYM / POSDEF systems: the LU of mldivide when no rcond is requested; otherwise "not supported" -> host fallback
+    n = 200
+    a = rng.uniform(-1, 1, (n, n)) + np.eye(n) * 8
+    b = rng.uniform(-1, 1, (n, 5))
+    for kw in ({}, {"transposed": True}, {"symmetric": True}, {"posdef": True}, {"lower": True, "upper": True}):
+        aa = a @ a.T if (kw.get("posdef") or kw.get("symmetric")) else a
+        x, rc = prov.linsolve(prov.upload(aa), prov.upload(b), **kw)
+        eff = aa.T if kw.get("transposed") else aa
+        got = prov.download(x)
+        assert np.isnan(rc)
+        assert np.max(np.abs(eff @ got - b)) <= 1e-10 * (np.max(np.abs(eff)) * np.max(np.abs(got)) * n)
+    for kw in ({"need_rcond": True}, {"rcond": 1e-3}, {"rectangular": True}):
+        with pytest.raises(ProviderError) as ei:
+            prov.linsolve(prov.upload(a), prov.upload(b), **kw)
+        assert ei.value.status == 2   # RM_UNSUPPORTED
+    assert prov.telemetry_snapshot().linsolve.count > 0
+
+
 def test_mldivide_kat_and_scalar(prov):
     from svd_solve import mldivide as oracle_mldivide
 

@@ -154,6 +154,27 @@ def test_sampled_evolution_equals_the_sequential_host_loop(orc):
         assert np.array_equal(orc.imfilter(img, ker, padding=padding, f32=True).astype(np.float64), orc.imfilter(img, ker, padding=padding))
 
 
+def test_linsolve_triangular_kats(orc):
+    for k in KATS["linsolve"]:
+        o = k["opts"]
+        if not (o.get("lower") or o.get("upper")):
+            continue
+        a = arr(k["a"])
+        lower = bool(o.get("lower"))
+        if o.get("transposed"):
+            a, lower = np.asfortranarray(a.T), not lower          # linsolve.rs:698-705: transpose, then the triangle hint flips
+        x, rc = orc.linsolve_triangular(a, arr(k["b"]), lower)
+        assert_same(x, arr(k["out"]), tol=1e-7)                     # the reference's approx_eq
+        if "rcond" in k:
+            assert abs(rc - k["rcond"]) < 1e-7
+    with pytest.raises(ValueError):
+        orc.linsolve_triangular(np.array([[1.0, 0.0], [2.0, 0.0]]), np.ones((2, 1)), True)
+    # the untouched triangle is ignored, like the host loops
+    t = np.array([[2.0, 99.0], [1.0, 4.0]])
+    x, rc = orc.linsolve_triangular(t, np.array([[2.0], [9.0]]), True)
+    assert np.array_equal(x, [[1.0], [2.0]]) and rc == 0.5
+
+
 def test_unary_and_scalar_tables(orc):
     x = np.array([[-2.5, -0.0, 0.0, 0.5, 2.5, np.nan, np.inf]])
     assert_same(orc.unary("round", x), np.array([[-3.0, -0.0, 0.0, 1.0, 3.0, np.nan, np.inf]]))  # half away from zero
