@@ -285,6 +285,10 @@ struct FilterParams {
   int64_t origin[3], base[3];
   int padding, mode;
   double cval;
+  // 1.0f, but only known at run time: the packed f32 kernel accumulates with fma.rn.f32x2(acc, one, product), which is
+  // bit-identical to add.rn (x*1 is exact) and which ptxas cannot contract with the preceding mul.rn.f32x2 into an FFMA2 the
+  // way it contracts mul.rn.f32x2 + add.rn.f32x2 (even under -fmad=false) or a literal 1.0f (it folds that back to an add).
+  float one = 1.0f;
 };
 __device__ __forceinline__ int64_t clamp_index(int64_t c, int64_t len) { return (len <= 0 || c <= 0) ? 0 : (c >= len ? len - 1 : c); }
 __device__ __forceinline__ int64_t wrap_index(int64_t c, int64_t len) { if (len <= 0) return 0; c %= len; if (c < 0) c += len; return c; }
@@ -463,6 +467,109 @@ imfilter_regblock_kernel(const T* __restrict__ img, const T* __restrict__ ker, T
       if (o < nvalid) *dst = acc[o];
   }
 }
+// f32 specialisation with packed arithmetic. Each thread owns TWO strips of RB2 outputs along dim 1, 32 columns apart in
+// dim 0 (A = column lx, B = column lx + 32), and processes them as f32x2 lanes: per staged value pair (tA, tB) and tap weight w
+//     FMUL2  p   = (w, w) * (tA, tB)          one rounding per lane, like the host's multiply
+//     FFMA2  acc = acc * (1, 1) + p           exact times-one, then ONE rounding: the host's add
+// i.e. one instruction per tap and output pair instead of the scalar kernel's FMUL + FADD per tap and output (r04: the 5x5 f32
+// filter was FP32-issue-bound at 200 FMUL + 200 FADD per 8 outputs). Pairing across the two strips (instead of adjacent
+// outputs) means a staged value always meets the same partner, so ptxas allocates each (tA, tB) in an aligned register pair
+// straight from the two shared-memory loads: no MOVs. Tap order per output is unchanged (k1 ascending, k0 ascending inside:
+// the host's column-major kernel walk, imfilter.rs:731-745), so the result stays bit-identical to the reference loop.
+constexpr int RB2 = 4;  // 8 strips x 4 rows = the CTA's 32 output rows
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+template <int K0, int K1>
+__global__ void __launch_bounds__(256)
+imfilter_packed_f32_kernel(const float* __restrict__ img, const float* __restrict__ ker, float* __restrict__ out, const __grid_constant__ FilterParams fp) {
+  constexpr int SX = FX + K0 - 1, SY = FY + K1 - 1;
+  __shared__ float tile[SY][SX];
+  __shared__ int map0[SX], map1[SY];
+  const int64_t t0 = (int64_t)blockIdx.x * FX, t1 = (int64_t)blockIdx.y * FY;
+  const uint64_t plane = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto remap = [&](int64_t c, int64_t len) -> int {
+    if (c >= 0 && c < len) return (int)c;
+    if (fp.padding == 0) return -1;
+    return (int)(fp.padding == 1 ? clamp_index(c, len) : (fp.padding == 3 ? wrap_index(c, len) : reflect_index(c, len)));
+  };
+  const int64_t h0 = t0 + fp.base[0] - fp.origin[0], h1 = t1 + fp.base[1] - fp.origin[1];
+  const bool interior = h0 >= 0 && h1 >= 0 && h0 + SX <= (int64_t)fp.ie[0] && h1 + SY <= (int64_t)fp.ie[1];
+  if (!interior) {
+    for (int i = tid; i < SX; i += 256) map0[i] = remap(h0 + i, (int64_t)fp.ie[0]);
+    for (int i = tid; i < SY; i += 256) map1[i] = remap(h1 + i, (int64_t)fp.ie[1]);
+  }
+  float w[K0 * K1];  // application order (already flipped for convolution)
+#pragma unroll
+  for (int i = 0; i < K0 * K1; ++i) {
+    const int k0 = i % K0, k1 = i / K0;
+    w[i] = __ldg(ker + (fp.mode == 0 ? k0 + k1 * K0 : (K0 - 1 - k0) + (K1 - 1 - k1) * K0));
+  }
+  const float* src = img + plane * fp.ie[0] * fp.ie[1];
+  if (interior) {
+    const float* col = src + (uint64_t)h0 + (uint64_t)(h1 + warp) * fp.ie[0];
+    const uint64_t step = 8 * fp.ie[0];
+    for (int sy = warp; sy < SY; sy += 8, col += step) {
+#pragma unroll
+      for (int sx = lane; sx < SX; sx += 32) tile[sy][sx] = col[sx];
+    }
+  } else {
+    __syncthreads();
+    for (int sy = warp; sy < SY; sy += 8) {
+      const int c = map1[sy];
+      for (int sx = lane; sx < SX; sx += 32) {
+        const int r = map0[sx];
+        tile[sy][sx] = (r < 0 || c < 0) ? (float)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+      }
+    }
+  }
+  __syncthreads();
+  const int ly0 = warp * RB2;
+  const unsigned long long one2 = pack_f32x2(fp.one, fp.one);
+  unsigned long long acc[RB2];
+#pragma unroll
+  for (int o = 0; o < RB2; ++o) acc[o] = pack_f32x2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < RB2 + K1 - 1; ++j) {
+#pragma unroll
+    for (int k0 = 0; k0 < K0; ++k0) {
+      const unsigned long long v = pack_f32x2(tile[ly0 + j][lane + k0], tile[ly0 + j][lane + 32 + k0]);
+#pragma unroll
+      for (int k1 = 0; k1 < K1; ++k1) {
+        const int o = j - k1;
+        if (o >= 0 && o < RB2) {
+          const float wk = w[k0 + k1 * K0];
+          unsigned long long prod;
+          asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod) : "l"(pack_f32x2(wk, wk)), "l"(v));
+          asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[o]) : "l"(acc[o]), "l"(one2), "l"(prod));
+        }
+      }
+    }
+  }
+  const uint64_t oA = (uint64_t)t0 + lane, oB = oA + 32, o1 = (uint64_t)t1 + ly0;
+  float* dst = out + o1 * fp.oe[0] + plane * fp.oe[0] * fp.oe[1];
+  const int nvalid = o1 + RB2 <= fp.oe[1] ? RB2 : (o1 < fp.oe[1] ? (int)(fp.oe[1] - o1) : 0);
+#pragma unroll
+  for (int o = 0; o < RB2; ++o, dst += fp.oe[0]) {
+    if (o < nvalid) {
+      float a, b;
+      unpack_f32x2(acc[o], a, b);
+      if (oA < fp.oe[0]) dst[oA] = a;
+      if (oB < fp.oe[0]) dst[oB] = b;
+    }
+  }
+}
+template <typename T, int K>
+static void launch_regblock_k(rm_provider* p, dim3 grid, const T* a, const T* k, T* o, const FilterParams& fp) {
+  if constexpr (std::is_same<T, float>::value) {
+    if (!getenv("RUNMAT_B200_IMFILTER_SCALAR")) { imfilter_packed_f32_kernel<K, K><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return; }
+  }
+  imfilter_regblock_kernel<T, K, K><<<grid, 256, 0, p->stream>>>(a, k, o, fp);
+}
 template <typename T>
 static bool launch_regblock(rm_provider* p, const void* pi, const void* pk, void* po, const FilterParams& fp) {
   if (fp.ke[2] != 1 || fp.ke[0] != fp.ke[1]) return false;
@@ -470,9 +577,9 @@ static bool launch_regblock(rm_provider* p, const void* pi, const void* pk, void
   if (grid.y > 65535 || grid.z > 65535) return false;
   const T* a = (const T*)pi; const T* k = (const T*)pk; T* o = (T*)po;
   switch (fp.ke[0]) {
-    case 3: imfilter_regblock_kernel<T, 3, 3><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return true;
-    case 5: imfilter_regblock_kernel<T, 5, 5><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return true;
-    case 7: imfilter_regblock_kernel<T, 7, 7><<<grid, 256, 0, p->stream>>>(a, k, o, fp); return true;
+    case 3: launch_regblock_k<T, 3>(p, grid, a, k, o, fp); return true;
+    case 5: launch_regblock_k<T, 5>(p, grid, a, k, o, fp); return true;
+    case 7: launch_regblock_k<T, 7>(p, grid, a, k, o, fp); return true;
     default: return false;
   }
 }

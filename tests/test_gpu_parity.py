@@ -1108,13 +1108,15 @@ def test_monte_carlo_full_size_sampled_vs_oracle(prov, orc):
     M, T = 100_000_000, 256
     drift, scale = (0.05 - 0.5 * 0.2 ** 2) / 252.0, 0.2 * math.sqrt(1.0 / 252.0)
     h = prov.fill((M, 1), 100.0)
-    prov.set_rng_state(0)
+    prov.set_rng_state(0)                     # rng(0) -> the default seed (simple_provider.rs:3627-3640), like the host
+    state0 = prov.get_rng_state()
+    assert state0 == orc.default_seed()
     out = prov.stochastic_evolution(h, drift, scale, T)
     paths = np.unique(np.concatenate([np.random.default_rng(99).integers(0, M, 1000), [0, 1, 2, 3, M - 2, M - 1, M // 2, M // 2 + 1]])).astype(np.uint32)
     got = prov.download(prov.gather_linear(out, paths, (len(paths), 1)))[:, 0]
-    want = orc.stochastic_evolution_sampled(0, 100.0, M, drift, scale, T, paths)
+    want = orc.stochastic_evolution_sampled(state0, 100.0, M, drift, scale, T, paths)
     assert np.all(np.abs(got - want) <= 1e-10 * np.abs(want)), f"worst {np.max(np.abs(got - want) / np.abs(want))}"
-    assert prov.get_rng_state() == orc.advance_state(0, T * M)   # the provider's RNG advanced exactly like the host's
+    assert prov.get_rng_state() == orc.advance_state(state0, T * M)   # the provider's RNG advanced exactly like the host's
     prov.free(out)
     prov.free(h)
 
