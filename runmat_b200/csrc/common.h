@@ -205,7 +205,10 @@ enum class EwVariant { Flat = 0, Broadcast = 1 };
 // scalar_mask bit k set => input k is a 1-element tensor (hoisted scalar load) in the Flat variant.
 std::string emit_elementwise_cuda(const ElementwiseProgram& prog, EwVariant variant, uint32_t scalar_mask);
 enum class RedOp { Sum = 0, Prod = 1, Max = 2, Min = 3 };
-enum class RedLayout { Contig = 0, Strided = 1 };  // Contig: slice s at [s*len, (s+1)*len); Strided: elem r of slice s at s + r*num_slices
+// Contig: slice s at [s*len, (s+1)*len); Strided: elem r of slice s at s + r*num_slices; Interleaved: the Strided addressing
+// for a small power-of-two `inner`, swept as ONE flat 256-bit vector stream per [inner x len] block (vector lane l of a
+// thread always belongs to the same slice, so the per-slice accumulators live in registers).
+enum class RedLayout { Contig = 0, Strided = 1, Interleaved = 2 };
 std::string emit_reduction_cuda(const ReductionProgram& prog, RedOp op, RedLayout layout);
 
 // ---- fused module cache / launch (fused.cu) -----------------------------------------------------------------

@@ -22,14 +22,14 @@ RM_EXPORT rm_status rm_debug_lower_elementwise(const char* shader, int variant, 
   if (!parse_elementwise_wgsl(shader, &prog, &err)) return fail(RM_COMPILE_ERROR, "%s", err.c_str());
   return copy_out(emit_elementwise_cuda(prog, variant ? EwVariant::Broadcast : EwVariant::Flat, scalar_mask), buf, buflen, needed);
 }
-// op: 0 sum, 1 prod, 2 max, 3 min; layout: -1 = from shader axis, 0 contiguous, 1 strided
+// op: 0 sum, 1 prod, 2 max, 3 min; layout: -1 = from shader axis, 0 contiguous, 1 strided, 2 interleaved
 RM_EXPORT rm_status rm_debug_lower_reduction(const char* shader, int op, int layout, char* buf, size_t buflen, size_t* needed, int* axis, int* omit_nan) {
   ReductionProgram prog;
   std::string err;
   if (!parse_reduction_wgsl(shader, &prog, &err)) return fail(RM_COMPILE_ERROR, "%s", err.c_str());
   if (axis) *axis = prog.axis;
   if (omit_nan) *omit_nan = prog.omit_nan ? 1 : 0;
-  RedLayout l = layout < 0 ? (prog.axis == 0 ? RedLayout::Contig : RedLayout::Strided) : (layout ? RedLayout::Strided : RedLayout::Contig);
+  RedLayout l = layout < 0 ? (prog.axis == 0 ? RedLayout::Contig : RedLayout::Strided) : layout == 2 ? RedLayout::Interleaved : (layout ? RedLayout::Strided : RedLayout::Contig);
   return copy_out(emit_reduction_cuda(prog, (RedOp)op, l), buf, buflen, needed);
 }
 RM_EXPORT rm_status rm_debug_translate_expr(const char* wgsl_expr, const char* scalar_ty, char* buf, size_t buflen) {

@@ -333,14 +333,17 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
                (unsigned long long)elems, (unsigned long long)reduce_len, (unsigned long long)num_slices);
   }
   if (num_slices == 1) layout = RedLayout::Contig;
+  const uint64_t vec = p->precision == RM_F64 ? 4 : 8;
+  if (layout == RedLayout::Strided && inner >= 2 && (inner & (inner - 1)) == 0 && inner <= 32 * vec && num_slices % inner == 0 &&
+      (inner * reduce_len) % vec == 0 && inner * reduce_len >= 256 * vec * 8 && num_slices / inner <= 65535 && !getenv("RUNMAT_B200_RED_NO_INTERLEAVED"))
+    layout = RedLayout::Interleaved;
   RM_REQUIRE(!publish || num_slices == 1, RM_INVALID_ARG, "fused_reduction_allreduce: only scalar ('all') reductions are exchanged");
   void* out_ptr = nullptr;
   RM_TRY(alloc_tensor(p, out_shape, rank, out, &out_ptr));
 
-  const uint64_t vec = p->precision == RM_F64 ? 4 : 8;
   const uint64_t sms = (uint64_t)p->prop.multiProcessorCount;
   Kernel kern;
-  const std::string k2 = std::string(layout == RedLayout::Contig ? "redC|" : "redS|") + std::to_string((int)op) + "|" + key;
+  const std::string k2 = std::string(layout == RedLayout::Contig ? "redC|" : layout == RedLayout::Strided ? "redS|" : "redI|") + std::to_string((int)op) + "|" + key;
   rm_status st = get_kernel(p, k2, "rm_fused_red", [&] { return emit_reduction_cuda(prog, op, layout); }, &kern);
   if (st == RM_OK) {
     dim3 grid, block;
@@ -362,6 +365,14 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       grid = dim3((unsigned)(num_slices * bps));
       block = dim3((unsigned)threads);
       partial_elems = bps > 1 ? (uint64_t)bps * num_slices : 0;
+    } else if (layout == RedLayout::Interleaved) {
+      // one flat vector stream per [inner x len] block; one resident wave (4 CTAs/SM) shared by the blocks
+      const uint64_t blocks = num_slices / inner, nvec = inner * reduce_len / vec;
+      uint64_t gx = std::max<uint64_t>(1, (sms * 4 + blocks - 1) / blocks);
+      gx = std::min<uint64_t>(gx, std::max<uint64_t>(1, nvec / (256 * 2)));
+      grid = dim3((unsigned)gx, (unsigned)blocks);
+      block = dim3(256);
+      partial_elems = gx > 1 ? gx * num_slices : 0;
     } else {
       // sl adjacent slices per CTA (power of two), 256/sl row lanes; split rows over gridDim.y until the SMs are full
       while (sl < 256 && sl < num_slices) sl <<= 1;

@@ -532,6 +532,86 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
   if (pub_n) { __syncthreads(); publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]); }
 }
 )CUDA";
+  } else if (layout == RedLayout::Interleaved) {
+    // Small power-of-two `inner` (e.g. the 8 images of mean(imgs,[2 3]) on a batch-fastest [B,H,W] tensor): block y of the
+    // tensor, [inner x len], is one contiguous stream in which element e belongs to slice e % inner. Every thread sweeps
+    // 256-bit vectors with a grid stride that is a multiple of inner, so vector lane l always lands on slice (b0 + l) % inner
+    // and the VEC per-slice accumulators stay in registers; RED_IU vectors per input are in flight per iteration (the scalar
+    // loads of the Strided kernel kept 16 B per thread in flight and ran at 0.41 of the copy bandwidth, r06). Lanes that
+    // share a slice are folded with xor-shuffles, warps through shared memory in warp order, CTAs by the last CTA (ticket)
+    // in CTA order: deterministic, no floating-point atomics. grid = (CTAs per block, blocks); R = max(inner, VEC).
+    const int iu = ni <= 1 ? 4 : 2;
+    o << "#define RED_IU " << iu << "\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(256, 4) rm_fused_red(" << input_params(ni)
+      << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
+         "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n";
+    o << "  __shared__ double shw[8 * 256];\n  __shared__ bool is_last;\n";
+    o << "  const u32 in_ = (u32)inner, R = in_ > VEC ? in_ : VEC, G = R / VEC;\n";
+    o << "  const u64 blk = inner * len, pbase = (u64)blockIdx.y * blk;\n";
+    o << "  const u64 nvec = blk / VEC, nthr = (u64)gridDim.x * 256;\n";
+    o << "  const u64 v0 = (u64)blockIdx.x * 256 + threadIdx.x;\n";
+    o << "  const u32 b0 = (u32)((v0 * VEC) % R);\n";
+    o << "  double acc[VEC];\n  #pragma unroll\n  for (int l = 0; l < VEC; ++l) acc[l] = IDENT;\n";
+    o << "  u64 v = v0;\n";
+    o << "  for (; v + (u64)(RED_IU - 1) * nthr < nvec; v += (u64)RED_IU * nthr) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "    vec_t a" << k << "[RED_IU];\n";
+    o << "    #pragma unroll\n    for (int u = 0; u < RED_IU; ++u) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "      a" << k << "[u] = ldv(in" << k << " + pbase + (v + (u64)u * nthr) * VEC);\n";
+    o << "    }\n    #pragma unroll\n    for (int u = 0; u < RED_IU; ++u) {\n      #pragma unroll\n      for (int l = 0; l < VEC; ++l) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = a" << k << "[u].x[l];\n";
+    o << "        accumulate(acc[l], " << prog.val_expr << ");\n      }\n    }\n  }\n";
+    o << "  for (; v < nvec; v += nthr) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "    const vec_t a" << k << " = ldv(in" << k << " + pbase + v * VEC);\n";
+    o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = a" << k << ".x[l];\n";
+    o << "      accumulate(acc[l], " << prog.val_expr << ");\n    }\n  }\n";
+    o << R"CUDA(
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // lanes q and q' of a warp hold the same slices iff q % G == q' % G (G is a power of two <= 32)
+  #pragma unroll
+  for (int l = 0; l < VEC; ++l)
+    for (u32 off = 16; off >= G && off > 0; off >>= 1) { const double ov = __shfl_xor_sync(0xffffffffu, acc[l], off); acc[l] = COMBINE(acc[l], ov); }
+  if (lane < G) {
+    #pragma unroll
+    for (int l = 0; l < VEC; ++l) shw[warp * R + b0 + l] = acc[l];
+  }
+  __syncthreads();
+  // slot s of a warp row belongs to slice s % inner (more than one slot per slice only when inner < VEC)
+  double t = IDENT;
+  if (threadIdx.x < in_) {
+    for (u32 w = 0; w < 8; ++w)
+      for (u32 s = threadIdx.x; s < R; s += in_) t = COMBINE(t, shw[w * R + s]);
+  }
+  if (gridDim.x == 1) {
+    if (threadIdx.x < in_) out[(u64)blockIdx.y * in_ + threadIdx.x] = finish(t, use_div, factor);
+    return;
+  }
+  if (threadIdx.x < in_) partial[((u64)blockIdx.y * gridDim.x + blockIdx.x) * in_ + threadIdx.x] = t;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { const u32 tk = atomicAdd(&tickets[blockIdx.y], 1u); is_last = (tk == gridDim.x - 1); }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    // last CTA of the block: thread q walks CTA partials q / inner, q / inner + W, ... of slice q % inner in ascending order,
+    // then the W thread partials of a slice are folded in thread order
+    const u32 W = 256 / in_;
+    const u32 fs = threadIdx.x % in_, fy = threadIdx.x / in_;
+    double acc2 = IDENT;
+    if (fy < W)
+      for (u32 y = fy; y < gridDim.x; y += W) acc2 = COMBINE(acc2, __ldcg(&partial[((u64)blockIdx.y * gridDim.x + y) * in_ + fs]));
+    shw[threadIdx.x] = acc2;   // every read of shw above happened before the two barriers
+    __syncthreads();
+    if (threadIdx.x < in_) {
+      for (u32 w = 1; w < W; ++w) acc2 = COMBINE(acc2, shw[w * in_ + fs]);
+      out[(u64)blockIdx.y * in_ + fs] = finish(acc2, use_div, factor);
+    }
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.y] = 0;
+}
+)CUDA";
   } else {
     // Strided layout: element r of slice s lives at sbase(s) + r*inner. A CTA owns `sl` adjacent slices x (256/sl) row
     // lanes, so a warp always touches contiguous memory even when there are only a handful of slices (e.g. the 8 images

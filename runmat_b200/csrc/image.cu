@@ -201,6 +201,56 @@ __device__ __forceinline__ double rm_powT(double a, double b) { return pow(a, b)
 
 // Fixed-lane variant: (gridDim*blockDim*VEC) %% B == 0, so each thread's lane l always belongs to image (b0+l): the
 // per-image mean / 1/sigma live in registers and the inner loop is load -> 4 FLOPs (+pow) -> store.
+// f32 clamp + gamma specialisation. ncu r06 ([64,2160,3840] f32): the generic body below issues ~50 instructions per pixel
+// (per-element option tests, the a < 0 guard, the denormal pre/post-scaling inside log2f/exp2f) and runs at 4.5 TB/s with the
+// issue slots 79 % busy. With the options fixed at compile time and the clamp guaranteeing a >= 0 the pixel is
+// sub, mul, mul, (add), max, MUFU.LG2, mul, MUFU.EX2 and the sweep is an HBM stream again. `.ftz` on the two MUFU ops: a
+// clamped value below 2^-126 is treated as 0 (what the WGSL pow of the wgpu provider is allowed to do as well); 0^g = 0,
+// inf^g = inf, 1^g = 1 come out of lg2/ex2 directly; gamma == 0 never reaches this kernel.
+__device__ __forceinline__ float pow_nonneg_f32(float a, float g) {
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(a));
+  l *= g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+  return r;
+}
+__global__ void __launch_bounds__(256)
+normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
+                                      const __grid_constant__ NormParams np) {
+  constexpr int VEC = 4, U = 4;
+  const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t b0 = (uint32_t)((v0 * VEC) % B);
+  float mean[VEC], inv[VEC];
+#pragma unroll
+  for (int l = 0; l < VEC; ++l) { mean[l] = (float)stats[2 * (b0 + l)]; inv[l] = (float)stats[2 * (b0 + l) + 1]; }
+  const float gain = np.has_gain ? (float)np.gain : 1.0f, bias = (float)np.bias, gamma = (float)np.gamma;  // v * 1.0f is the identity, bit for bit
+  const bool has_bias = np.has_bias != 0;
+  const float4* xv = reinterpret_cast<const float4*>(x);
+  float4* yv = reinterpret_cast<float4*>(y);
+  auto body = [&](float4 a) {
+    float* e = reinterpret_cast<float*>(&a);
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) {
+      float val = (e[l] - mean[l]) * inv[l];
+      val *= gain;
+      if (has_bias) val += bias;
+      val = val > 0.0f ? val : 0.0f;  // f64::max(v, 0.0): NaN -> 0
+      e[l] = pow_nonneg_f32(val, gamma);
+    }
+    return a;
+  };
+  uint64_t v = v0;
+  for (; v + (U - 1) * nthr < nvec; v += U * nthr) {
+    float4 a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) __stcs(yv + v + (uint64_t)u * nthr, body(a[u]));
+  }
+  for (; v < nvec; v += nthr) __stcs(yv + v, body(__ldcs(xv + v)));
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 normalize_fixed_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
@@ -682,7 +732,9 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
       moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
     }
     moments_finalize_kernel<float><<<(unsigned)B, 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
-    if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+    if (fast_blocks && d->clamp_zero && d->has_gamma && (float)d->gamma != 0.0f && !getenv("RUNMAT_B200_NORMALIZE_GENERIC"))
+      normalize_fixed_clampgamma_f32_kernel<<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+    else if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
     else normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
   }
   cudaError_t e = cudaGetLastError();

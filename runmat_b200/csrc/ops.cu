@@ -474,10 +474,10 @@ RM_EXPORT rm_status rm_debug_precompile_ops(rm_precision precision, uint32_t* co
   const char* vals[] = {"v0", "(v0 * v0)"};
   for (const char* val : vals)
     for (int op = 0; op < 4; ++op)
-      for (int layout = 0; layout < 2; ++layout) {
+      for (int layout = 0; layout < 3; ++layout) {
         if (val != vals[0] && op != 0) continue;
         ReductionProgram prog = red_program(&fake, val, false);
-        RM_TRY(compile_cuda_to_cubin(emit_reduction_cuda(prog, (RedOp)op, layout ? RedLayout::Strided : RedLayout::Contig), "rm_fused_red", &cubin, &log));
+        RM_TRY(compile_cuda_to_cubin(emit_reduction_cuda(prog, (RedOp)op, (RedLayout)layout), "rm_fused_red", &cubin, &log));
         ++n;
       }
   if (compiled) *compiled = n;

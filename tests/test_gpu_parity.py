@@ -1477,6 +1477,59 @@ def test_comm_single_rank_roundtrip():
         p.synchronize()
 
 
+
+def test_interleaved_reduction_layout(prov, prov32, orc, monkeypatch):
+    """Reductions over the middle dimension of [inner, n, post] with a small power-of-two `inner` run as one flat vector stream
+    per post block (RedLayout::Interleaved): inner below / equal / above the vector width, post > 1, sum / mean / prod, NaN
+    include and omit, two-input fused programs, f64 and f32 -- against the oracle and against the Strided kernel."""
+    rng = np.random.default_rng(616)
+    for P, shape in ((prov, (2, 5001, 3)), (prov, (4, 3000, 2)), (prov, (32, 1000, 5)), (prov, (128, 300)), (prov32, (2, 9000, 3)),
+                     (prov32, (4, 8000)), (prov32, (64, 700, 2)), (prov32, (256, 200))):
+        f32 = P is prov32
+        x = rng.uniform(0.5, 1.5, shape)
+        if f32:
+            x = x.astype(np.float32)
+        x64 = x.astype(np.float64)
+        h = P.upload(x)
+        want = orc.sum_dims(x64, [1])
+        bound = np.abs(x64).sum(axis=1, keepdims=True)
+        tol = 1e-6 if f32 else 1e-12
+        got = P.download(P.reduce_sum_dim(h, 1))
+        assert got.shape == want.shape
+        assert np.all(np.abs(got - want) <= tol * bound)
+        assert np.array_equal(got, P.download(P.reduce_sum_dim(h, 1)))  # deterministic
+        gotm = P.download(P.reduce_mean_dim(h, 1))
+        assert np.all(np.abs(gotm - want / shape[1]) <= tol * bound / shape[1])
+        monkeypatch.setenv("RUNMAT_B200_RED_NO_INTERLEAVED", "1")
+        old = P.download(P.reduce_sum_dim(h, 1))
+        monkeypatch.delenv("RUNMAT_B200_RED_NO_INTERLEAVED")
+        assert np.all(np.abs(got - old) <= tol * bound)
+        # NaN poisons exactly one slice
+        xn = x.copy()
+        idx = (1, 17) + ((shape[2] - 1,) if len(shape) == 3 else ())
+        xn[idx] = np.nan
+        hn = P.upload(xn)
+        gn = P.download(P.reduce_sum_dim(hn, 1))
+        nan_at = (1, 0) + ((shape[2] - 1,) if len(shape) == 3 else ())
+        assert np.isnan(gn[nan_at]) and np.count_nonzero(np.isnan(gn)) == 1
+        for hh in (h, hn):
+            P.free(hh)
+    # two-input fused program (x .* y summed along rows, omitnan) on a [128 x 700] matrix: inner = 128 slices
+    x, y = rng.uniform(-1, 1, (128, 700)), rng.uniform(-1, 1, (128, 700))
+    x[5, 9] = np.nan
+    hx, hy = prov.upload(x), prov.upload(y)
+    ops = [ft.FusionOp("primitive", "ElemMul", [0, 1], 10)]
+    for omit in (False, True):
+        sh = ft.reduction_wgsl([0, 1], ops, 10, axis=1, omitnan=omit)
+        got = prov.download(prov.fused_reduction(sh, [hx, hy], (128, 1), 700, 128))
+        close(got, orc.sum_dims(x * y, [1], omit_nan=omit), rtol=1e-12, atol=1e-13)
+    # prod over the middle dimension
+    z = rng.uniform(0.99, 1.01, (8, 4000))
+    got = prov.download(prov.reduce_prod_dim(prov.upload(z), 1)) if hasattr(prov, "reduce_prod_dim") else None
+    if got is not None:
+        assert np.all(np.abs(got.reshape(-1) / np.prod(z, axis=1) - 1) <= 1e-12)
+
+
 def test_few_slices_strided_reduction(prov, prov32, orc):
     """Row-direction reductions with a handful of slices and thousands of rows (many row chunks per slice, folded by the last
     CTA with all threads): sums/means/max/min, NaN include and omit, ragged row counts, f64 and f32."""

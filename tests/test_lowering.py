@@ -101,8 +101,12 @@ def test_reduction_parse_axes_omitnan_and_compile(lib):
             assert ax == axis and om == int(omit)
             assert "(v0*v1)" in src
     for op in range(4):
-        for layout in (0, 1):
-            assert compiles(lib, lower_red(lib, ft.sum_sin_mul_add_wgsl(), op, layout)[0]) > 0
+        for layout in (0, 1, 2):
+            for ty in ("f64", "f32"):
+                src = lower_red(lib, ft.sum_sin_mul_add_wgsl(ty), op, layout)[0]
+                assert compiles(lib, src) > 0
+                if layout == 2:  # interleaved layout: per-lane accumulators, xor-shuffle fold, no floating-point atomics
+                    assert "acc[VEC]" in src and "__shfl_xor_sync" in src and "atomicAdd(&tickets" in src and "atomicAdd(&sh" not in src
 
 
 def test_parse_errors(lib):
