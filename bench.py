@@ -461,41 +461,49 @@ def run_ours(args):
     hostA[:] = A
     hostB[:] = B
 
-    # r06 probe (scripts/pcie_dev): the link gives 50 GB/s H2D with a concurrent D2H. 8 chunks left 0.67 ms of un-overlapped first upload
-    # + last download per step; 32 chunks leave 0.17 ms (each chunk is still 4 MiB per array: full link efficiency).
-    E2E_CHUNKS = 32
-    chunk = ELEMS // E2E_CHUNKS
-    cshape = (chunk, 1)
+    # r06 probe (scripts/pcie_dev): the link gives ~53 GB/s H2D with a concurrent D2H, so a step cannot beat 268 MB / 53 GB/s = 5.06 ms
+    # plus the un-overlapped first upload and last download. Uniform 8 chunks left 0.67 + 0.33 ms of that (5.9 ms/step); 32 uniform
+    # chunks were host-bound (7.0 ms, r07). The schedule below tapers: small chunks at both ends (short pipeline fill and drain),
+    # 1/8-size chunks in the middle (few calls). The per-chunk partial sums go to pinned host memory with async copies: one
+    # synchronize per step.
+    E2E_FRACS = [64, 64, 32, 16, 8, 8, 8, 8, 8, 8, 16, 32, 64, 64]  # chunk = ELEMS / f; sum of 1/f == 1
+    assert abs(sum(1.0 / f for f in E2E_FRACS) - 1.0) < 1e-12
+    chunks, off = [], 0
+    for f in E2E_FRACS:
+        chunks.append((off, ELEMS // f))
+        off += ELEMS // f
+    assert off == ELEMS
+    hostS = pinned_empty(len(chunks))
 
     def e2e_step():
         """Same step from HOST buffers through the C ABI, chunked and software-pipelined: the upload of chunk i+1 (H2D stream)
         is enqueued before the download of chunk i (compute stream), so H2D, kernels and D2H overlap on the full-duplex link."""
         pending = None
-        partials = []
-        for i in range(E2E_CHUNKS + 1):
+        for i in range(len(chunks) + 1):
             nxt = None
-            if i < E2E_CHUNKS:
-                off = i * chunk * 8
-                a = p.upload_ptr(hostA.ctypes.data + off, cshape)
-                b = p.upload_ptr(hostB.ctypes.data + off, cshape)
+            if i < len(chunks):
+                o, n = chunks[i]
+                a = p.upload_ptr(hostA.ctypes.data + o * 8, (n, 1))
+                b = p.upload_ptr(hostB.ctypes.data + o * 8, (n, 1))
                 nxt = (i, a, b)
             if pending is not None:
-                j, pa, pb, pc = pending
-                p.download_async_into_ptr(pc, hostC.ctypes.data + j * chunk * 8, chunk)
-                for h in (pa, pb, pc):
+                j, pa, pb, pc, ps = pending
+                p.download_async_into_ptr(pc, hostC.ctypes.data + chunks[j][0] * 8, chunks[j][1])
+                p.download_async_into_ptr(ps, hostS.ctypes.data + j * 8, 1)
+                for h in (pa, pb, pc, ps):
                     p.free(h)
             if nxt is not None:
                 i_, a, b = nxt
-                c = p.fused_elementwise(ew_shader, [a, b, hOne], cshape, chunk)
-                partials.append(p.fused_reduction(red_shader, [a, b], (1, 1), chunk, 1))
-                pending = (i_, a, b, c)
+                n = chunks[i_][1]
+                c = p.fused_elementwise(ew_shader, [a, b, hOne], (n, 1), n)
+                s_ = p.fused_reduction(red_shader, [a, b], (1, 1), n, 1)
+                pending = (i_, a, b, c, s_)
             else:
                 pending = None
-        p.synchronize()                      # C is now complete in host memory
+        p.synchronize()                      # C and the chunk sums are now complete in host memory
         val = 0.0
-        for h in partials:
-            val += p.read_scalar(h, 0)
-            p.free(h)
+        for j in range(len(chunks)):
+            val += float(hostS[j])
         if world > 1:
             tv = torch.tensor([val], dtype=torch.float64, device=f"cuda:{local_rank}")
             dist.all_reduce(tv)
@@ -524,10 +532,29 @@ def run_ours(args):
         e2e_med, e2e_mean = float(tt[0].item()), float(tt[1].item())
     e2e_ms = e2e_med * e2e_steps
     e2e = {"value": BYTES_STEP * world * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 2 * ELEMS * 8,
-           "d2h_bytes_per_step": ELEMS * 8 + 8, "ms_per_step": e2e_ms / e2e_steps, "ms_per_step_mean": e2e_mean, "ms_per_step_all": [round(x, 3) for x in per_step],
+           "d2h_bytes_per_step": ELEMS * 8 + 8 * len(chunks), "ms_per_step": e2e_ms / e2e_steps, "ms_per_step_mean": e2e_mean, "ms_per_step_all": [round(x, 3) for x in per_step],
            "steps": e2e_steps, "statistic": "median over per-step host wall times (each step ends in a stream synchronize)",
-           "note": "A,B uploaded from pinned host memory, fused elementwise + fused sum, C and the sum downloaded; 32 chunks, software-pipelined (H2D stream / compute+D2H stream)",
+           "note": "A,B uploaded from pinned host memory, fused elementwise + fused sum, C and the sum downloaded; 14 tapered chunks, software-pipelined (H2D stream / compute+D2H stream)",
            "checksum_rel_diff_vs_resident": (abs(e2e_val - checksum_local) / abs(checksum_local)) if world == 1 else None}
+
+    # ---- host cost of one provider call (python ctypes + C dispatch, no synchronisation): says whether a step loop is host-bound
+    def host_us(fn, reps=300):
+        p.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            p.free(fn())
+        dt = time.perf_counter() - t0
+        p.synchronize()
+        return dt / reps * 1e6
+
+    tiny = p.upload(np.array([1.0, 2.0, 3.0, 4.0]), (4, 1))
+    host_call = {"scalar_op_plus_free_us": host_us(lambda: p.scalar_mul(tiny, 2.0)),
+                 "fused_elementwise_plus_free_us": host_us(lambda: p.fused_elementwise(ew_shader, [tiny, tiny, hOne], (4, 1), 4)),
+                 "fused_reduction_plus_free_us": host_us(lambda: p.fused_reduction(red_shader, [tiny, tiny], (1, 1), 4, 1))}
+    if ex.kind == "p2p":
+        host_call["fused_reduction_allreduce_plus_free_us"] = host_us(lambda: p.fused_reduction_allreduce(red_shader, [tiny, tiny], 4))
+        ex.fence()
+    p.free(tiny)
 
     # ---- other configs of BASELINE.json, reported beside the headline (not the metric) --------------------------------
     extra = {}
@@ -562,7 +589,7 @@ def run_ours(args):
             "config": CONFIG,
             "run": {"arm": "B200 provider through the C ABI (ctypes)",
                     "parallelism": f"{world} independent batches, the per-rank sums meet in one scalar exchange per step: {ex.describe()}" if world > 1 else "single GPU",
-                    "exchange": ex.kind, "exchange_verified": exchange_ok, "host_numa_binding": numa,
+                    "exchange": ex.kind, "exchange_verified": exchange_ok, "host_numa_binding": numa, "host_call_cost": host_call,
                     "timed_region": "device-side rendezvous, K steps, closing fence on the last exchange; CUDA events on the provider stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "checksum": checksum, "extra": extra,

@@ -320,6 +320,9 @@ rm_status rm_diag_extract(rm_provider* p, const rm_handle* matrix, int64_t offse
 rm_status rm_set_matmul_engine(rm_provider* p, int engine);
 /* test/debug: waits for the stream; out4 = {non-finite input seen, pipeline error, tiles recomputed in FP64, 0} of the last tcgen05 product */
 rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4);
+/* test/debug: waits for the stream; device-side protocol flags, all zero unless a bounded pipeline wait ran out
+ * ([0] = the TMA-staged imfilter kernel) */
+rm_status rm_debug_device_flags(rm_provider* p, int32_t* out, uint32_t n);
 
 /* ---- a9: mldivide core (lib.rs:2477-2489): square systems by device LU with partial pivoting; non-square,
  *      singular or badly conditioned inputs return RM_UNSUPPORTED (host SVD fallback, as with wgpu today) ---- */

@@ -115,6 +115,7 @@ struct rm_provider {
   void* oz_ws = nullptr;
   // number of times an entry point blocked the host on the device (download, read_scalar, synchronize, find, mldivide's gate ...)
   std::atomic<uint64_t> host_syncs{0};
+  void* dev_flags = nullptr;  // int[64], zero-initialised: [0] imfilter TMA pipeline protocol error (image.cu)
   void* l2_flush = nullptr;
   size_t l2_flush_bytes = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;

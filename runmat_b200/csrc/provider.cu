@@ -243,6 +243,7 @@ RM_EXPORT rm_status rm_provider_destroy(rm_provider* p) {
   p->buffers.clear();
   if (p->reduce_scratch) cudaFreeAsync(p->reduce_scratch, p->stream);
   if (p->l2_flush) cudaFreeAsync(p->l2_flush, p->stream);
+  if (p->dev_flags) cudaFree(p->dev_flags);
   ozaki_workspace_destroy(p);
   cudaStreamSynchronize(p->stream);
   comm_destroy(p);
@@ -297,6 +298,16 @@ RM_EXPORT rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4) {
   int tmp[4];
   RM_TRY(ozaki_last_stats(p, tmp));
   for (int i = 0; i < 4; ++i) out4[i] = tmp[i];
+  return RM_OK;
+}
+RM_EXPORT rm_status rm_debug_device_flags(rm_provider* p, int32_t* out, uint32_t n) {
+  RM_REQUIRE(p && out && n <= 64, RM_INVALID_ARG, "rm_debug_device_flags: bad arguments");
+  for (uint32_t i = 0; i < n; ++i) out[i] = 0;
+  if (!p->dev_flags) return RM_OK;
+  DeviceGuard g(p->ordinal);
+  RM_CUDA(cudaStreamSynchronize(p->stream));
+  p->host_syncs.fetch_add(1, std::memory_order_relaxed);
+  RM_CUDA(cudaMemcpy(out, p->dev_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   return RM_OK;
 }
 RM_EXPORT rm_status rm_get_stream(rm_provider* p, void** s) {

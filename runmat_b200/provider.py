@@ -503,6 +503,12 @@ class B200Provider:
         _check(lib.rm_debug_ozaki_stats(self._p, out))
         return {"nonfinite": int(out[0]), "pipeline_error": int(out[1]), "fp64_tiles": int(out[2])}
 
+    def device_flags(self, n: int = 4) -> list[int]:
+        """Device-side pipeline protocol flags (waits for the stream): all zero unless a bounded wait ran out."""
+        out = (C.c_int32 * n)()
+        _check(lib.rm_debug_device_flags(self._p, out, n))
+        return [int(v) for v in out]
+
     def set_matmul_engine(self, engine: int) -> None:
         _check(lib.rm_set_matmul_engine(self._p, int(engine)))
 

@@ -10,4 +10,5 @@ ncu --set full --clock-control none --import-source on -k regex:rm_fused_ew -s 4
 ncu --set full --clock-control none --import-source on -k regex:rm_fused_red -s 4 -c 2 -f -o gpurun_out/${TAG}_fused_red python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"ozaki_gemm_kernel|slice_kernel|dgemm|evolve_kernel" -c 6 -f -o gpurun_out/${TAG}_gemm_mc python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"moments|normalize|imfilter" -c 8 -f -o gpurun_out/${TAG}_image python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"imfilter" -c 3 -f -o gpurun_out/${TAG}_imfilter python scripts/time_imfilter.py > gpurun_out/${TAG}_imfilter_ncu.log 2>&1
 ls -la gpurun_out

@@ -1333,6 +1333,35 @@ def test_imfilter_4k_rgb_full_size_vs_oracle(prov32, orc):
     assert np.array_equal(got, want)
 
 
+def test_imfilter_tma_staged_path(prov32, orc, monkeypatch):
+    """Large f32 images take the persistent TMA-staged kernel (cp.async.bulk.tensor ring for interior tiles, index-map fill for
+    the border ring): every padding, 3x3 / 5x5 / 7x7, same / full / valid, corr / conv, ragged tile edges, an RGB and a 2-D
+    image -- bit for bit against the f32 oracle and against the per-tile kernel; the pipeline error flag must stay clear."""
+    rng = np.random.default_rng(717)
+    img = rng.uniform(-1, 1, (1028, 1301, 2)).astype(np.float32)  # 17 x 41 x 2 tiles, ragged in both dims
+    hi = prov32.upload(img)
+    for K in (3, 5, 7):
+        k32 = rng.uniform(-1, 1, (K, K)).astype(np.float32)
+        hk = prov32.upload(k32)
+        for padding, shape, mode in (("replicate", "same", "corr"), ("constant", "same", "corr"), ("symmetric", "same", "conv"), ("circular", "same", "corr"),
+                                     ("replicate", "full", "corr"), ("constant", "valid", "conv")):
+            got = prov32.download(prov32.imfilter(hi, hk, padding=padding, constant_value=0.5, shape=shape, mode=mode), np.float32)
+            want = orc.imfilter(img, k32, padding=padding, cval=0.5, shape=shape, mode=mode, f32=True)
+            assert got.shape == want.shape and np.array_equal(got, want), (K, padding, shape, mode)
+        monkeypatch.setenv("RUNMAT_B200_IMFILTER_NO_TMA", "1")
+        ref = prov32.download(prov32.imfilter(hi, hk, padding="replicate"), np.float32)
+        monkeypatch.delenv("RUNMAT_B200_IMFILTER_NO_TMA")
+        assert np.array_equal(ref, prov32.download(prov32.imfilter(hi, hk, padding="replicate"), np.float32))
+    flat = rng.uniform(0, 1, (2048, 2600)).astype(np.float32)  # 2-D image: one plane
+    k5 = rng.uniform(-1, 1, (5, 5)).astype(np.float32)
+    got = prov32.download(prov32.imfilter(prov32.upload(flat), prov32.upload(k5), padding="symmetric"), np.float32)
+    assert np.array_equal(got, orc.imfilter(flat, k5, padding="symmetric", f32=True))
+    odd = rng.uniform(0, 1, (1030, 1301, 2)).astype(np.float32)  # dim 0 not a multiple of 4: TMA strides illegal -> per-tile kernel
+    got = prov32.download(prov32.imfilter(prov32.upload(odd), prov32.upload(k5), padding="replicate"), np.float32)
+    assert np.array_equal(got, orc.imfilter(odd, k5, padding="replicate", f32=True))
+    assert prov32.device_flags()[0] == 0
+
+
 def test_conv2d_matches_host_order(prov, orc):
     rng = np.random.default_rng(23)
     for sshape, kshape in [((7, 9), (3, 3)), ((40, 33), (5, 4)), ((2, 2), (3, 5)), ((130, 70), (1, 7)), ((64, 64), (2, 2))]:
