@@ -15,10 +15,14 @@
 // (acquire loads on its OWN memory, bounded) until all N flags of the bank carry the step, then folds the N values in rank
 // order, so every rank gets the bit-identical sum independent of arrival order. The publish is fused into the tail of the
 // producing kernel (the generated reduction's last block: rm_fused_reduction_allreduce; rm_payoff_partial_sum feeds the
-// stand-alone publish kernel), the combine runs on the communication stream and its result is waited for lazily like an
-// upload. Bank reuse: 8 banks; publish(t) is ordered after this rank's combine(t-4), and a peer's publish(t) therefore proves
-// its combine(t-4) is done, so when rank r overwrites bank (t mod 8) with step t every peer has already folded step t-8
-// (r's publish(t) follows r's combine(t-4), which saw the peer's publish(t-4), which followed the peer's combine(t-8)).
+// stand-alone publish kernel). The combine is LAZY and runs on the compute stream: it is enqueued when the result handle is first
+// used (resolve / free: provider.cu) or, at the latest, right before publish(t + 4). Nothing crosses streams, so the compute
+// stream stays a plain in-order chain of kernels (r07, N = 2: the event edges to and from a communication stream cost ~6 us per
+// 119 us step and broke the programmatic-dependent-launch overlap of consecutive kernels), and a consumer that reads the sum
+// several steps later never waits at all. Bank reuse: 8 banks; publish(t) is ordered after this rank's combine(t-4), and a
+// peer's publish(t) therefore proves its combine(t-4) is done, so when rank r overwrites bank (t mod 8) with step t every peer
+// has already folded step t-8 (r's publish(t) follows r's combine(t-4), which saw the peer's publish(t-4), which followed the
+// peer's combine(t-8)). Every combine runs, even for a handle that is freed unused: it is the protocol's flow-control step.
 #include <dlfcn.h>
 
 #include "common.h"
@@ -95,8 +99,8 @@ struct P2PState {
   int world = 1, rank = 0;
   bool connected = false;
   uint64_t step = 0;
-  cudaEvent_t combine_done[P2P_BANKS] = {};
-  bool recorded[P2P_BANKS] = {};
+  uint64_t ring_id[P2P_BANKS] = {};     // buffer that receives the combine of step (ring_step1 - 1)
+  uint64_t ring_step1[P2P_BANKS] = {};  // step + 1, 0 = empty
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* addr, unsigned long long v) {
@@ -146,48 +150,55 @@ P2PState* p2p_state(rm_provider* p) { return (P2PState*)p->p2p; }
 
 }  // namespace
 
+void p2p_enqueue_combine_locked(rm_provider* p, uint64_t step, void* dst) {
+  P2PState* s = p2p_state(p);
+  if (!s || !s->connected) return;
+  if (p->precision == RM_F64) p2p_combine_kernel<double><<<1, 32, 0, p->stream>>>(s->mine, s->world, step, (double*)dst, s->d_err);
+  else p2p_combine_kernel<float><<<1, 32, 0, p->stream>>>(s->mine, s->world, step, (float*)dst, s->d_err);
+  cudaGetLastError();
+  count_launch(p);
+}
+
+// Enqueues the still-pending combine of `step` (if its handle has not been used or freed yet). Caller holds p->comm_mu.
+static void p2p_force(rm_provider* p, P2PState* s, uint64_t step) {
+  const int b = (int)(step % P2P_BANKS);
+  if (s->ring_step1[b] != step + 1) return;
+  s->ring_step1[b] = 0;
+  std::lock_guard<std::mutex> lk(p->mu);
+  auto it = p->buffers.find(s->ring_id[b]);
+  if (it == p->buffers.end() || it->second.p2p_step1 != step + 1) return;  // already enqueued by resolve() / rm_free()
+  p2p_enqueue_combine_locked(p, step, it->second.ptr);
+  it->second.p2p_step1 = 0;
+}
+
 // Publish context handed to the generated reduction kernel (fused.cu): returns false when no peer exchange is connected.
 // The caller holds p->comm_mu from this call until p2p_finish().
 bool p2p_begin(rm_provider* p, P2PPublish* pub) {
   P2PState* s = p2p_state(p);
   if (!s || !s->connected) return false;
   const uint64_t t = s->step;
-  // bank reuse rule: publish(t) is ordered after this rank's combine(t - LAG)
-  if (t >= (uint64_t)P2P_LAG) {
-    const int b = (int)((t - P2P_LAG) % P2P_BANKS);
-    if (s->recorded[b]) cudaStreamWaitEvent(p->stream, s->combine_done[b], 0);
-  }
+  // bank reuse rule: publish(t) is ordered (same stream) after this rank's combine(t - LAG)
+  if (t >= (uint64_t)P2P_LAG) p2p_force(p, s, t - P2P_LAG);
   pub->peers = (void* const*)s->d_peers;
   pub->n = (uint32_t)s->world;
   pub->rank = (uint32_t)s->rank;
   pub->step = t;
   return true;
 }
-// After the producer (with its fused or stand-alone publish) has been enqueued on the compute stream: enqueue the combine on
-// the communication stream into a fresh 1x1 handle whose ready event the compute stream waits on at first use.
+// After the producer (with its fused or stand-alone publish) has been enqueued on the compute stream: hand out a fresh 1x1 handle
+// whose combine is still pending (enqueued at first use, at free, or before publish(t + LAG), whichever comes first).
 rm_status p2p_finish(rm_provider* p, rm_handle* out) {
   P2PState* s = p2p_state(p);
   const uint64_t t = s->step++;
   uint64_t shp[2] = {1, 1};
   void* dst;
   RM_TRY(alloc_tensor(p, shp, 2, out, &dst));
-  cudaEvent_t produced = take_event(p), done = take_event(p);
-  cudaError_t e = cudaEventRecord(produced, p->stream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->comm_stream, produced, 0);
-  give_event(p, produced);
-  if (e == cudaSuccess) {
-    if (p->precision == RM_F64) p2p_combine_kernel<double><<<1, 32, 0, p->comm_stream>>>(s->mine, s->world, t, (double*)dst, s->d_err);
-    else p2p_combine_kernel<float><<<1, 32, 0, p->comm_stream>>>(s->mine, s->world, t, (float*)dst, s->d_err);
-    e = cudaGetLastError();
-  }
   const int b = (int)(t % P2P_BANKS);
-  if (e == cudaSuccess) e = cudaEventRecord(s->combine_done[b], p->comm_stream);
-  if (e == cudaSuccess) { s->recorded[b] = true; e = cudaEventRecord(done, p->comm_stream); }
-  if (e != cudaSuccess) { give_event(p, done); rm_free(p, out); return fail(RM_ERROR, "p2p exchange: %s", cudaGetErrorString(e)); }
-  count_launch(p);
+  s->ring_id[b] = out->buffer_id;
+  s->ring_step1[b] = t + 1;
   std::lock_guard<std::mutex> lk(p->mu);
   auto it = p->buffers.find(out->buffer_id);
-  if (it != p->buffers.end()) it->second.ready = done; else cudaStreamWaitEvent(p->stream, done, 0);
+  if (it != p->buffers.end()) it->second.p2p_step1 = t + 1;
   return RM_OK;
 }
 
@@ -198,7 +209,6 @@ void p2p_destroy(rm_provider* p) {
   if (!s) return;
   for (int q = 0; q < s->world; ++q)
     if (s->peers[q] && s->peers[q] != s->mine) cudaIpcCloseMemHandle(s->peers[q]);
-  for (int b = 0; b < P2P_BANKS; ++b) if (s->combine_done[b]) cudaEventDestroy(s->combine_done[b]);
   if (s->d_peers) cudaFree(s->d_peers);
   if (s->d_err) cudaFree(s->d_err);
   if (s->mine) cudaFree(s->mine);
@@ -312,7 +322,6 @@ RM_EXPORT rm_status rm_comm_p2p_connect(rm_provider* p, const uint8_t* all_handl
     s->peers[q] = (P2PSlots*)ptr;
   }
   RM_CUDA(cudaMemcpy(s->d_peers, s->peers, sizeof(P2PSlots*) * P2P_MAXR, cudaMemcpyHostToDevice));
-  for (int b = 0; b < P2P_BANKS; ++b) RM_CUDA(cudaEventCreateWithFlags(&s->combine_done[b], cudaEventDisableTiming));
   s->world = (int)world;
   s->rank = (int)rank;
   s->connected = true;
@@ -329,7 +338,11 @@ RM_EXPORT rm_status rm_comm_p2p_error(rm_provider* p, int32_t* err) {
   P2PState* s = p2p_state(p);
   if (!s || !s->connected) return RM_OK;
   DeviceGuard g(p->ordinal);
-  RM_CUDA(cudaStreamSynchronize(p->comm_stream));
+  {
+    std::lock_guard<std::mutex> lk(p->comm_mu);
+    for (uint64_t u = s->step >= (uint64_t)P2P_BANKS ? s->step - P2P_BANKS : 0; u < s->step; ++u) p2p_force(p, s, u);
+  }
+  RM_CUDA(cudaStreamSynchronize(p->stream));
   p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   int h = 0;
   RM_CUDA(cudaMemcpy(&h, s->d_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -384,8 +397,14 @@ RM_EXPORT rm_status rm_comm_allreduce_sum(rm_provider* p, const rm_handle* in, r
 // Orders the compute stream after every collective issued so far (e.g. before closing a timed region).
 RM_EXPORT rm_status rm_comm_fence(rm_provider* p) {
   RM_REQUIRE(p, RM_INVALID_ARG, "comm_fence: null provider");
-  if (!p->comm_stream) return RM_OK;
   DeviceGuard g(p->ordinal);
+  if (P2PState* s = p2p_state(p)) {
+    // peer-memory exchange: enqueue every combine that is still pending (ascending step order) on the compute stream
+    std::lock_guard<std::mutex> lk(p->comm_mu);
+    if (s->connected)
+      for (uint64_t u = s->step >= (uint64_t)P2P_BANKS ? s->step - P2P_BANKS : 0; u < s->step; ++u) p2p_force(p, s, u);
+  }
+  if (!p->comm_stream || !p->nccl_comm) return RM_OK;
   cudaEvent_t ev = take_event(p);
   RM_CUDA(cudaEventRecord(ev, p->comm_stream));
   RM_CUDA(cudaStreamWaitEvent(p->stream, ev, 0));

@@ -60,6 +60,7 @@ struct Buffer {
   void* ptr = nullptr;
   uint64_t elems = 0;  // logical elements (real storage only)
   cudaEvent_t ready = nullptr;  // set by upload: recorded on the H2D stream; the compute stream waits for it at first use
+  uint64_t p2p_step1 = 0;       // comm.cu: step + 1 of the peer-exchange combine that still has to be enqueued into this buffer (0 = none)
 };
 
 struct DispatchCounter {
@@ -166,6 +167,9 @@ struct P2PPublish {
 };
 bool p2p_begin(rm_provider* p, P2PPublish* pub);     // caller holds p->comm_mu until p2p_finish()
 rm_status p2p_finish(rm_provider* p, rm_handle* out);
+// Enqueues the combine of exchange step `step` into `dst` on the compute stream. Caller holds p->mu (the buffer-table lock), so the
+// combine is ordered before any consumer another host thread may enqueue for the same buffer.
+void p2p_enqueue_combine_locked(rm_provider* p, uint64_t step, void* dst);
 // Resolves a handle to its device pointer, validating device_id and element count.
 rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* elems);
 rm_status ensure_scratch(rm_provider* p, size_t bytes);

@@ -27,6 +27,7 @@ struct DriverApi {
   CUresult (*ModuleUnload)(CUmodule) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                            CUstream, void**, void**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;  // optional (programmatic dependent launch)
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   CUresult (*CtxGetCurrent)(CUcontext*) = nullptr;
   CUresult (*CtxSetCurrent)(CUcontext) = nullptr;
@@ -49,6 +50,8 @@ DriverApi& driver() {
     ok &= get("cuGetErrorString", (void**)&api.GetErrorString);
     ok &= get("cuCtxGetCurrent", (void**)&api.CtxGetCurrent);
     ok &= get("cuCtxSetCurrent", (void**)&api.CtxSetCurrent);
+    if (!get("cuLaunchKernelEx", (void**)&api.LaunchKernelEx)) api.LaunchKernelEx = nullptr;
+    if (getenv("RUNMAT_B200_NO_PDL")) api.LaunchKernelEx = nullptr;
     cudaGetLastError();
     api.ok = ok;
   });
@@ -201,7 +204,26 @@ rm_status launch(rm_provider* p, const Kernel& k, dim3 grid, dim3 block, void** 
   CUcontext cur = nullptr;
   d.CtxGetCurrent(&cur);
   if (cur != p->fused->ctx) d.CtxSetCurrent(p->fused->ctx);
-  CUresult r = d.LaunchKernel(k.fn, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)p->stream, args, nullptr);
+  CUresult r;
+  if (d.LaunchKernelEx) {
+    // programmatic stream serialisation: the generated kernels open with griddepcontrol.launch_dependents + griddepcontrol.wait
+    // (fusion_lower.cpp RM_PDL_PROLOGUE), so this kernel's CTAs may become resident while the previous kernel drains
+    CUlaunchAttribute attr;
+    memset(&attr, 0, sizeof attr);
+    attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr.value.programmaticStreamSerializationAllowed = 1;
+    CUlaunchConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDimX = grid.x; cfg.gridDimY = grid.y; cfg.gridDimZ = grid.z;
+    cfg.blockDimX = block.x; cfg.blockDimY = block.y; cfg.blockDimZ = block.z;
+    cfg.sharedMemBytes = 0;
+    cfg.hStream = (CUstream)p->stream;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    r = d.LaunchKernelEx(&cfg, k.fn, args, nullptr);
+  } else {
+    r = d.LaunchKernel(k.fn, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)p->stream, args, nullptr);
+  }
   if (r != CUDA_SUCCESS) return fail(RM_ERROR, "cuLaunchKernel failed: %s", cu_err(r));
   count_launch(p);
   return RM_OK;

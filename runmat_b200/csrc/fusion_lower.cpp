@@ -266,6 +266,11 @@ typedef double T;
 #define VEC 4
 #endif
 struct __align__(32) vec_t { T x[VEC]; };
+// Programmatic dependent launch (fused.cu launches with programmatic stream serialisation): let the NEXT kernel in the stream
+// become resident as soon as every CTA of this one has started, then wait here until the PREVIOUS kernel has completed and its
+// writes are visible. No global memory is touched before the wait, so stream order is preserved exactly; what overlaps is the
+// previous kernel's drain with this kernel's launch latency and ramp. Both instructions are no-ops in a plain launch.
+#define RM_PDL_PROLOGUE() do { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
 #define RM_NAN __longlong_as_double(0x7ff8000000000000LL)
 
 // 256-bit streaming accesses: LDG.E.256 / STG.E.256 on sm_100a, L1 no-allocate (each byte is touched once).
@@ -353,7 +358,7 @@ std::string emit_elementwise_cuda(const ElementwiseProgram& prog, EwVariant vari
     o << "#define UNROLL 2\n";
     o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_ew(" << input_params(ni);
     for (uint32_t k = 0; k < no; ++k) o << "T* __restrict__ out" << k << ", ";
-    o << "u64 n) {\n";
+    o << "u64 n) {\n  RM_PDL_PROLOGUE();\n";
     o << "  const u64 nvec = n / VEC;\n";
     for (uint32_t k = 0; k < ni; ++k)
       if (scalar_mask & (1u << k)) o << "  const T s" << k << " = in" << k << "[0];\n";
@@ -393,7 +398,7 @@ std::string emit_elementwise_cuda(const ElementwiseProgram& prog, EwVariant vari
     o << "struct BParams { u64 len; u32 rank; u32 pad; u64 shape[MAXR]; u64 stride[MAXIN][MAXR]; };\n";
     o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_ew(" << input_params(ni);
     for (uint32_t k = 0; k < no; ++k) o << "T* __restrict__ out" << k << ", ";
-    o << "const __grid_constant__ BParams p) {\n";
+    o << "const __grid_constant__ BParams p) {\n  RM_PDL_PROLOGUE();\n";
     o << "  for (u64 g = (u64)blockIdx.x * 256 + threadIdx.x; g < p.len; g += (u64)gridDim.x * 256) {\n";
     o << "    u64 rem = g;\n";
     for (uint32_t k = 0; k < ni; ++k) o << "    u64 i" << k << " = 0;\n";
@@ -481,7 +486,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
-         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n";
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n  RM_PDL_PROLOGUE();\n";
     o << "  __shared__ double smem[32];\n  __shared__ bool is_last;\n";
     o << "  const u64 slice = blockIdx.x / bps;\n  const u32 bidx = blockIdx.x % bps;\n  const u64 base = slice * len;\n";
     o << "  const u64 nvec = vec_ok ? len / VEC : 0;\n";
@@ -545,7 +550,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << "extern \"C\" __global__ void __launch_bounds__(256, 4) rm_fused_red(" << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
-         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n";
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n  RM_PDL_PROLOGUE();\n";
     o << "  __shared__ double shw[8 * 256];\n  __shared__ bool is_last;\n";
     o << "  const u32 in_ = (u32)inner, R = in_ > VEC ? in_ : VEC, G = R / VEC;\n";
     o << "  const u64 blk = inner * len, pbase = (u64)blockIdx.y * blk;\n";
@@ -620,7 +625,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(" << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
-         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n";
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n  RM_PDL_PROLOGUE();\n";
     o << "  __shared__ bool is_last;\n  __shared__ double sacc[256];\n";
     o << "  const u32 sloc = threadIdx.x % sl, lane = threadIdx.x / sl, rl = blockDim.x / sl;\n";
     o << "  const u64 s = (u64)blockIdx.x * sl + sloc;\n";

@@ -617,20 +617,28 @@ imfilter_packed_f32_kernel(const float* __restrict__ img, const float* __restric
 }
 
 // ---- TMA-staged persistent variant of the packed f32 kernel ------------------------------------------------------------------
-// r06/r07: the packed kernel above needs 200 FMUL2/FFMA2 + 80 LDS per 8 outputs (about 33 us of FP32 pipe for the 2160x3840x3
-// frame) but runs in 111 us: a CTA's life is load tile (dependent LDG -> STS round trips) -> barrier -> math -> store, and the five
-// CTAs an SM holds spend most of it waiting on the load phase. Here a CTA is persistent (grid = 4 per SM, tiles interleaved
-// across CTAs so neighbours in flight share halos in L2) and the tile + halo of the tile three iterations ahead is fetched by ONE
-// cp.async.bulk.tensor.3d (TMA, SASS UTMALDG) into a 3-stage shared-memory ring that completes on an mbarrier: no load
-// instructions, no registers and no warp waits on the data path, the math of tile i overlaps the fetch of tiles i+1..i+3.
-// Border tiles (halo outside the image: replicate / symmetric / circular / constant padding) are filled by the CTA itself through
-// the same index maps as before; they are the outer ring only. Arithmetic and tap order are exactly the packed kernel's, so
-// the result is bit-identical to the reference loop (imfilter.rs:731-745).
+// r06/r07: the packed kernel above needs 200 FMUL2/FFMA2 + 80 LDS per 8 outputs but runs the 2160x3840x3 frame in 111 us: a CTA's
+// life is load tile (dependent LDG -> STS round trips) -> barrier -> math -> store, and the five CTAs an SM holds spend most of it
+// waiting. Here a CTA is persistent (tiles interleaved across CTAs, so the tiles in flight are neighbours and share halos in L2)
+// and warp-specialised:
+//   * warp 8 (one lane) is the producer: for every tile of the CTA it waits until the 8 compute warps have released the ring
+//     stage (mbarrier `empty`, count 8) and fetches tile + halo with ONE cp.async.bulk.tensor.3d (TMA, SASS UTMALDG) that
+//     completes on the stage's `full` mbarrier: no load instructions, registers or warp waits on the data path;
+//   * warps 0-7 each own RBW output rows x 64 columns of the tile: wait `full`, 128-bit-free LDS + packed math exactly as in the
+//     kernel above, release the stage, store. There is no CTA-wide barrier on the interior path, so the warps drift apart and the
+//     math of one overlaps the stores and waits of another (r09, first version with a __syncthreads per tile: barrier stalls 1.6
+//     per issue, 88 us).
+// Border tiles (halo outside the image: replicate / symmetric / circular / constant padding) are filled by the compute warps
+// themselves through the index remap; they are the outer ring only. The TMA wants the box's inner start coordinate on a 16-byte
+// boundary (scripts/imf_dev harness: "illegal instruction" at coordinate 126, fine at 124 / 128), so the fetch starts at the
+// halo's first column rounded DOWN to a multiple of 4 floats (`shift` = 0..3 extra columns on the left). Arithmetic and tap
+// order are exactly the packed kernel's, so the result is bit-identical to the reference loop (imfilter.rs:731-745).
 constexpr int IMF_STAGES = 3;
-template <int K>
+template <int K, int RBW>
 struct ImfTma {
-  static constexpr int SX = FX + K - 1, SY = FY + K - 1;
-  static constexpr int SXP = (SX + 3) & ~3;  // TMA box rows are whole 16-byte units
+  static constexpr int TY = 8 * RBW;  // output rows (dim 1) per tile: 8 compute warps x RBW
+  static constexpr int SX = FX + K - 1, SY = TY + K - 1;
+  static constexpr int SXP = (SX + 3 + 3) & ~3;  // + up to 3 shift columns, rows are whole 16-byte units
   static constexpr uint32_t BOX_BYTES = (uint32_t)SY * SXP * 4;
   static constexpr uint32_t STAGE_BYTES = (BOX_BYTES + 127) / 128 * 128;
   static constexpr uint32_t SMEM = IMF_STAGES * STAGE_BYTES + 128;
@@ -645,24 +653,59 @@ __device__ __forceinline__ bool imf_mbar_wait(uint64_t* bar, uint32_t parity, in
     if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); return false; }  // a protocol bug must surface as an error flag, never as a hung GPU
   }
 }
-template <int K>
-__global__ void __launch_bounds__(256)
+template <int K, int RBW>
+__global__ void __launch_bounds__(288)
 imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ img, const float* __restrict__ ker, float* __restrict__ out,
                         const __grid_constant__ FilterParams fp, uint32_t ntx, uint32_t nty, uint32_t ntiles, int* __restrict__ err) {
-  using C = ImfTma<K>;
+  using C = ImfTma<K, RBW>;
   constexpr int SX = C::SX, SY = C::SY, SXP = C::SXP;
   extern __shared__ __align__(128) unsigned char imf_dsm_raw[];
   // 128-byte alignment of the stages by an OFFSET on the shared array (a pointer round trip through an integer would turn the
   // tile reads into generic LD instead of LDS)
   unsigned char* dsm = imf_dsm_raw + ((128u - (imf_smem_u32(imf_dsm_raw) & 127u)) & 127u);
-  __shared__ __align__(8) uint64_t full[IMF_STAGES];
-  __shared__ int map0[SX], map1[SY];
+  __shared__ __align__(8) uint64_t full[IMF_STAGES], empty[IMF_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < IMF_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(imf_smem_u32(&full[s])));
+    for (int s = 0; s < IMF_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(imf_smem_u32(&full[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(imf_smem_u32(&empty[s])));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  struct TileAt { int64_t t0, t1, h0, h1; uint32_t plane; bool interior; };
+  // columns the fetch starts left of the halo; the same for every tile of a launch (tile origins are multiples of FX = 64)
+  const int shift = (int)((((fp.base[0] - fp.origin[0]) % 4) + 4) % 4);
+  auto tile_at = [&](uint32_t t) {
+    TileAt a;
+    const uint32_t tx = t % ntx, r = t / ntx;
+    a.t0 = (int64_t)tx * FX;
+    a.t1 = (int64_t)(r % nty) * C::TY;
+    a.plane = r / nty;
+    a.h0 = a.t0 + fp.base[0] - fp.origin[0];
+    a.h1 = a.t1 + fp.base[1] - fp.origin[1];
+    a.interior = a.h0 >= 0 && a.h1 >= 0 && a.h0 + SX <= (int64_t)fp.ie[0] && a.h1 + SY <= (int64_t)fp.ie[1];
+    return a;
+  };
+  if (warp == 8) {
+    // ---- producer ------------------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it % IMF_STAGES);
+        const TileAt a = tile_at((uint32_t)t);
+        if (!a.interior) continue;  // border tiles are filled by the compute warps (they wait for `empty` themselves)
+        if (it >= IMF_STAGES && !imf_mbar_wait(&empty[s], ((it / IMF_STAGES) - 1) & 1u, err)) break;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(imf_smem_u32(&full[s])), "r"(C::BOX_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(imf_smem_u32(dsm + (size_t)s * C::STAGE_BYTES)), "l"(&tm), "r"(imf_smem_u32(&full[s])), "r"((int)a.h0 - shift), "r"((int)a.h1), "r"((int)a.plane)
+                     : "memory");
+      }
+    }
+    return;
+  }
+  // ---- compute warps -----------------------------------------------------------------------------------------------------------
   float w[K * K];  // application order (already flipped for convolution)
 #pragma unroll
   for (int i = 0; i < K * K; ++i) {
@@ -674,34 +717,9 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     if (fp.padding == 0) return -1;
     return (int)(fp.padding == 1 ? clamp_index(c, len) : (fp.padding == 3 ? wrap_index(c, len) : reflect_index(c, len)));
   };
-  struct TileAt { int64_t t0, t1, h0, h1; uint32_t plane; bool interior; };
-  auto tile_at = [&](uint32_t t) {
-    TileAt a;
-    const uint32_t tx = t % ntx, r = t / ntx;
-    a.t0 = (int64_t)tx * FX;
-    a.t1 = (int64_t)(r % nty) * FY;
-    a.plane = r / nty;
-    a.h0 = a.t0 + fp.base[0] - fp.origin[0];
-    a.h1 = a.t1 + fp.base[1] - fp.origin[1];
-    a.interior = a.h0 >= 0 && a.h1 >= 0 && a.h0 + SX <= (int64_t)fp.ie[0] && a.h1 + SY <= (int64_t)fp.ie[1];
-    return a;
-  };
-  auto issue = [&](int s, const TileAt& a) {  // one thread: arm the stage's barrier with the box size, then the bulk tensor copy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(imf_smem_u32(&full[s])), "r"(C::BOX_BYTES) : "memory");
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(imf_smem_u32(dsm + (size_t)s * C::STAGE_BYTES)), "l"(&tm), "r"(imf_smem_u32(&full[s])), "r"((int)a.h0), "r"((int)a.h1), "r"((int)a.plane)
-                 : "memory");
-  };
-  if (tid == 0) {
-    for (int s = 0; s < IMF_STAGES; ++s) {
-      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
-      if (t < ntiles) { const TileAt a = tile_at((uint32_t)t); if (a.interior) issue(s, a); }
-    }
-  }
-  const int ly0 = warp * RB2;
+  const int ly0 = warp * RBW;
   const unsigned long long one2 = pack_f32x2(fp.one, fp.one);
-  uint32_t phase = 0;  // bit s: parity of the next completion of stage s
+  uint32_t phase = 0;  // bit s: parity of the next completion of full[s] (it advances on interior tiles only)
   uint32_t it = 0;
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int s = (int)(it % IMF_STAGES);
@@ -711,31 +729,30 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
       imf_mbar_wait(&full[s], (phase >> s) & 1u, err);
       phase ^= 1u << s;
     } else {
-      for (int i = tid; i < SX; i += 256) map0[i] = remap(a.h0 + i, (int64_t)fp.ie[0]);
-      for (int i = tid; i < SY; i += 256) map1[i] = remap(a.h1 + i, (int64_t)fp.ie[1]);
-      __syncthreads();
+      // every compute warp has released the stage's previous use; then fill it cooperatively and meet on a named barrier
+      if (it >= IMF_STAGES) imf_mbar_wait(&empty[s], ((it / IMF_STAGES) - 1) & 1u, err);
       const float* src = img + (uint64_t)a.plane * fp.ie[0] * fp.ie[1];
       for (int sy = warp; sy < SY; sy += 8) {
-        const int c = map1[sy];
+        const int c = remap(a.h1 + sy, (int64_t)fp.ie[1]);
         for (int sx = lane; sx < SX; sx += 32) {
-          const int r = map0[sx];
-          tile[sy * SXP + sx] = (r < 0 || c < 0) ? (float)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+          const int r = remap(a.h0 + sx, (int64_t)fp.ie[0]);
+          tile[sy * SXP + shift + sx] = (r < 0 || c < 0) ? (float)fp.cval : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
         }
       }
-      __syncthreads();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    unsigned long long acc[RB2];
+    unsigned long long acc[RBW];
 #pragma unroll
-    for (int o = 0; o < RB2; ++o) acc[o] = pack_f32x2(0.0f, 0.0f);
+    for (int o = 0; o < RBW; ++o) acc[o] = pack_f32x2(0.0f, 0.0f);
 #pragma unroll
-    for (int j = 0; j < RB2 + K - 1; ++j) {
+    for (int j = 0; j < RBW + K - 1; ++j) {
 #pragma unroll
       for (int k0 = 0; k0 < K; ++k0) {
-        const unsigned long long v = pack_f32x2(tile[(ly0 + j) * SXP + lane + k0], tile[(ly0 + j) * SXP + lane + 32 + k0]);
+        const unsigned long long v = pack_f32x2(tile[(ly0 + j) * SXP + shift + lane + k0], tile[(ly0 + j) * SXP + shift + lane + 32 + k0]);
 #pragma unroll
         for (int k1 = 0; k1 < K; ++k1) {
           const int o = j - k1;
-          if (o >= 0 && o < RB2) {
+          if (o >= 0 && o < RBW) {
             const float wk = w[k0 + k1 * K];
             unsigned long long prod;
             asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod) : "l"(pack_f32x2(wk, wk)), "l"(v));
@@ -744,16 +761,13 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
         }
       }
     }
-    __syncthreads();  // every warp has finished reading stage s (and the index maps)
-    if (tid == 0) {
-      const uint64_t tn = t + (uint64_t)IMF_STAGES * gridDim.x;
-      if (tn < ntiles) { const TileAt an = tile_at((uint32_t)tn); if (an.interior) issue(s, an); }
-    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(imf_smem_u32(&empty[s])) : "memory");  // this warp's reads of the stage are done
     const uint64_t oA = (uint64_t)a.t0 + lane, oB = oA + 32, o1 = (uint64_t)a.t1 + ly0;
     float* dst = out + o1 * fp.oe[0] + (uint64_t)a.plane * fp.oe[0] * fp.oe[1];
-    const int nvalid = o1 + RB2 <= fp.oe[1] ? RB2 : (o1 < fp.oe[1] ? (int)(fp.oe[1] - o1) : 0);
+    const int nvalid = o1 + RBW <= fp.oe[1] ? RBW : (o1 < fp.oe[1] ? (int)(fp.oe[1] - o1) : 0);
 #pragma unroll
-    for (int o = 0; o < RB2; ++o, dst += fp.oe[0]) {
+    for (int o = 0; o < RBW; ++o, dst += fp.oe[0]) {
       if (o < nvalid) {
         float va, vb;
         unpack_f32x2(acc[o], va, vb);
@@ -778,11 +792,10 @@ static ImfEncodeTiledFn imf_encode_tiled() {
   return fn;
 }
 // Returns false when the TMA path does not apply (the caller then launches the per-tile kernel).
-template <int K>
-static bool launch_imfilter_tma(rm_provider* p, dim3 grid_tiles, const float* a, const float* k, float* o, const FilterParams& fp) {
-  using C = ImfTma<K>;
-  if (getenv("RUNMAT_B200_IMFILTER_NO_TMA")) return false;
-  const uint64_t ntiles = (uint64_t)grid_tiles.x * grid_tiles.y * grid_tiles.z;
+template <int K, int RBW>
+static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* k, float* o, const FilterParams& fp) {
+  using C = ImfTma<K, RBW>;
+  const uint64_t ntx = (fp.oe[0] + FX - 1) / FX, nty = (fp.oe[1] + C::TY - 1) / C::TY, ntiles = ntx * nty * fp.oe[2];
   // global strides must be multiples of 16 bytes; coordinates are 32-bit; small problems keep the one-CTA-per-tile kernel
   if (fp.ie[0] % 4 != 0 || fp.ie[0] >= (1ull << 31) || fp.ie[1] >= (1ull << 31) || fp.ie[2] >= (1ull << 31) || ntiles >= (1ull << 32) ||
       ntiles < (uint64_t)p->prop.multiProcessorCount * 8 || ((uintptr_t)a & 15) != 0)
@@ -805,16 +818,29 @@ static bool launch_imfilter_tma(rm_provider* p, dim3 grid_tiles, const float* a,
   if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
-  const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)p->prop.multiProcessorCount * 4);
-  imfilter_tma_f32_kernel<K><<<grid, 256, C::SMEM, p->stream>>>(tm, a, k, o, fp, grid_tiles.x, grid_tiles.y, (uint32_t)ntiles, (int*)p->dev_flags + 0);
+  static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (idempotent; a benign race)
+  if (!attr_set) { cudaFuncSetAttribute(imfilter_tma_f32_kernel<K, RBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr_set = true; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imfilter_tma_f32_kernel<K, RBW>, 288, C::SMEM) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+  if (const char* e = getenv("RUNMAT_B200_IMFILTER_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+  const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)p->prop.multiProcessorCount * per_sm);
+  imfilter_tma_f32_kernel<K, RBW><<<grid, 288, C::SMEM, p->stream>>>(tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty, (uint32_t)ntiles, (int*)p->dev_flags + 0);
   return true;
+}
+template <int K>
+static bool launch_imfilter_tma(rm_provider* p, const float* a, const float* k, float* o, const FilterParams& fp) {
+  if (getenv("RUNMAT_B200_IMFILTER_NO_TMA")) return false;
+  int rbw = 8;  // output rows per compute warp (tile = 64 x 8*rbw)
+  if (const char* e = getenv("RUNMAT_B200_IMFILTER_RBW")) rbw = atoi(e);
+  if (rbw == 4) return launch_imfilter_tma_rb<K, 4>(p, a, k, o, fp);
+  return launch_imfilter_tma_rb<K, 8>(p, a, k, o, fp);
 }
 
 template <typename T, int K>
 static void launch_regblock_k(rm_provider* p, dim3 grid, const T* a, const T* k, T* o, const FilterParams& fp) {
   if constexpr (std::is_same<T, float>::value) {
     if (!getenv("RUNMAT_B200_IMFILTER_SCALAR")) {
-      if (launch_imfilter_tma<K>(p, grid, a, k, o, fp)) return;
+      if (launch_imfilter_tma<K>(p, a, k, o, fp)) return;
       imfilter_packed_f32_kernel<K, K><<<grid, 256, 0, p->stream>>>(a, k, o, fp);
       return;
     }

@@ -73,6 +73,8 @@ rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* ele
     // first use of an uploaded buffer: order the compute stream after its H2D copy (enqueued while the table lock is held, so
     // a concurrent resolve() of the same buffer cannot launch ahead of the wait), then recycle the event
     if (ready) cudaStreamWaitEvent(p->stream, ready, 0);
+    // first use of a peer-exchange result: its (lazy) combine goes onto the compute stream now, ahead of the consumer
+    if (it->second.p2p_step1) { p2p_enqueue_combine_locked(p, it->second.p2p_step1 - 1, it->second.ptr); it->second.p2p_step1 = 0; }
   }
   if (ready) {
     std::lock_guard<std::mutex> lk(p->ev_mu);
@@ -468,6 +470,11 @@ RM_EXPORT rm_status rm_free(rm_provider* p, const rm_handle* h) {
     auto it = p->buffers.find(h->buffer_id);
     if (it == p->buffers.end()) return RM_OK;
     b = it->second;
+    if (b.p2p_step1) {
+      // freed before use: the combine still runs (it is also this rank's flow-control step of the exchange protocol, comm.cu)
+      DeviceGuard g2(p->ordinal);
+      p2p_enqueue_combine_locked(p, b.p2p_step1 - 1, b.ptr);
+    }
     p->buffers.erase(it);
   }
   DeviceGuard g(p->ordinal);

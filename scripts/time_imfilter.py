@@ -8,8 +8,10 @@ img = rng.uniform(0, 1, (2160, 3840, 3)).astype(np.float32)
 hi = p.upload(img)
 for K in (3, 5, 7):
     hk = p.upload(rng.uniform(0, 1, (K, K)).astype(np.float32))
-    for name, env in (("tma-staged", {}), ("per-tile packed", {"RUNMAT_B200_IMFILTER_NO_TMA": "1"}), ("generic tiled", {"RUNMAT_B200_IMFILTER_GENERIC": "1"})):
-        for k in ("RUNMAT_B200_IMFILTER_NO_TMA", "RUNMAT_B200_IMFILTER_GENERIC"):
+    for name, env in (("tma-staged rbw8", {}), ("tma-staged rbw8 2 CTA/SM", {"RUNMAT_B200_IMFILTER_CTAS": "2"}), ("tma-staged rbw4", {"RUNMAT_B200_IMFILTER_RBW": "4"}),
+                      ("tma-staged rbw4 3 CTA/SM", {"RUNMAT_B200_IMFILTER_RBW": "4", "RUNMAT_B200_IMFILTER_CTAS": "3"}),
+                      ("per-tile packed", {"RUNMAT_B200_IMFILTER_NO_TMA": "1"}), ("generic tiled", {"RUNMAT_B200_IMFILTER_GENERIC": "1"})):
+        for k in ("RUNMAT_B200_IMFILTER_NO_TMA", "RUNMAT_B200_IMFILTER_GENERIC", "RUNMAT_B200_IMFILTER_RBW", "RUNMAT_B200_IMFILTER_CTAS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3): p.free(p.imfilter(hi, hk, padding="replicate"))
