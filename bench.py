@@ -428,8 +428,15 @@ def run_ours(args):
         return p.timer_end_ms() / reps
 
     reps = max(args.steps, 10)
+    # `roofline` times each kernel with PLAIN launches (what an ncu capture sees: one launch after the other). The step loop above and
+    # `pipelined` below use the provider's default, programmatic dependent launch: the next kernel's CTAs become resident while
+    # the previous kernel drains, so back-to-back launches overlap and the per-launch average is shorter than any single launch.
+    p.set_launch_overlap(False)
     ew_ms = time_kernel(lambda: p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS), reps)
     red_ms = time_kernel(lambda: p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1), reps)
+    p.set_launch_overlap(True)
+    ew_pdl_ms = time_kernel(lambda: p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS), reps)
+    red_pdl_ms = time_kernel(lambda: p.fused_reduction(red_shader, [hA, hB], (1, 1), ELEMS, 1), reps)
 
     def planner_pair():  # what the reference planner emits for sum(sin(A).*B+1): sin does not fold into a reduction (fusion.rs:1198-1258)
         hC = p.fused_elementwise(ew_shader, [hA, hB, hOne], shape, ELEMS)
@@ -443,6 +450,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": BYTES_EW,
                 "reduction_kernel": {"kernel": "rm_fused_red (sum(sin(A).*B+1), 16 B/elem)", "achieved": BYTES_RED / (red_ms * 1e-3) / 1e9,
                                      "frac": BYTES_RED / (red_ms * 1e-3) / 1e9 / peak, "us_per_launch": red_ms * 1e3},
+                "pipelined": {"what": "the same launches back to back with programmatic dependent launch (provider default; the step loop runs this way): "
+                                      "average time per launch, launches overlap head to tail",
+                              "ew_us": ew_pdl_ms * 1e3, "ew_gbs": BYTES_EW / (ew_pdl_ms * 1e-3) / 1e9, "red_us": red_pdl_ms * 1e3,
+                              "red_gbs": BYTES_RED / (red_pdl_ms * 1e-3) / 1e9},
                 "planner_shaped_pair": {"what": "fused_elementwise (writes C) + reduce_sum(C): the two calls the reference planner emits for sum(sin(A).*B+1) "
                                                 "(sin does not fold into a reduction, fusion.rs:1198-1258); 32 B/elem",
                                         "us": pair_ms * 1e3, "achieved": 32 * ELEMS / (pair_ms * 1e-3) / 1e9, "frac": 32 * ELEMS / (pair_ms * 1e-3) / 1e9 / peak,

@@ -320,6 +320,10 @@ rm_status rm_diag_extract(rm_provider* p, const rm_handle* matrix, int64_t offse
 rm_status rm_set_matmul_engine(rm_provider* p, int engine);
 /* test/debug: waits for the stream; out4 = {non-finite input seen, pipeline error, tiles recomputed in FP64, 0} of the last tcgen05 product */
 rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4);
+/* measurement / tuning: the generated fused kernels are launched with programmatic stream serialisation (each opens with
+ * griddepcontrol.launch_dependents + griddepcontrol.wait, so a kernel becomes resident while its predecessor drains; stream order
+ * of all memory effects is unchanged). 0 switches to plain launches, e.g. to time one kernel in isolation. Default: enabled. */
+rm_status rm_set_launch_overlap(rm_provider* p, int enabled);
 /* test/debug: waits for the stream; device-side protocol flags, all zero unless a bounded pipeline wait ran out
  * ([0] = the TMA-staged imfilter kernel) */
 rm_status rm_debug_device_flags(rm_provider* p, int32_t* out, uint32_t n);

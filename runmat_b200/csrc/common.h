@@ -125,6 +125,7 @@ struct rm_provider {
   std::mutex ev_mu;
   std::vector<cudaEvent_t> event_pool;  // recycled per-buffer "ready" events
   int matmul_engine = 0;
+  bool launch_overlap = true;  // fused.cu: programmatic dependent launch of the generated kernels (rm_set_launch_overlap)
   // multi-GPU exchange (comm.cu): one NCCL communicator per provider, collectives on their own stream
   void* nccl_comm = nullptr;
   cudaStream_t comm_stream = nullptr;

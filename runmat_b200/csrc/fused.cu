@@ -205,7 +205,7 @@ rm_status launch(rm_provider* p, const Kernel& k, dim3 grid, dim3 block, void** 
   d.CtxGetCurrent(&cur);
   if (cur != p->fused->ctx) d.CtxSetCurrent(p->fused->ctx);
   CUresult r;
-  if (d.LaunchKernelEx) {
+  if (d.LaunchKernelEx && p->launch_overlap) {
     // programmatic stream serialisation: the generated kernels open with griddepcontrol.launch_dependents + griddepcontrol.wait
     // (fusion_lower.cpp RM_PDL_PROLOGUE), so this kernel's CTAs may become resident while the previous kernel drains
     CUlaunchAttribute attr;

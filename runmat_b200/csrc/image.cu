@@ -653,8 +653,11 @@ __device__ __forceinline__ bool imf_mbar_wait(uint64_t* bar, uint32_t parity, in
     if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); return false; }  // a protocol bug must surface as an error flag, never as a hung GPU
   }
 }
-template <int K, int RBW>
-__global__ void __launch_bounds__(288)
+// MODE 0: scalar FMUL + FADD; 1: packed FMUL2 + FFMA2(x1); 2: mixed -- the first half of a warp's rows packed, the second half scalar
+// Resident CTAs the register allocation is held to: the K*K weights live in registers, so 7x7 gets two CTAs per SM; up to 5x5
+// four fit (RBW = 4: 3 x 10 KB stages each) or three (RBW = 8).
+template <int K, int RBW, int MODE>
+__global__ void __launch_bounds__(288, (K <= 5 ? (RBW == 4 ? 4 : 3) : 2))
 imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ img, const float* __restrict__ ker, float* __restrict__ out,
                         const __grid_constant__ FilterParams fp, uint32_t ntx, uint32_t nty, uint32_t ntiles, int* __restrict__ err) {
   using C = ImfTma<K, RBW>;
@@ -673,7 +676,7 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  struct TileAt { int64_t t0, t1, h0, h1; uint32_t plane; bool interior; };
+  struct TileAt { int64_t t0, t1, h0, h1; uint32_t plane; bool interior, tma; };
   // columns the fetch starts left of the halo; the same for every tile of a launch (tile origins are multiples of FX = 64)
   const int shift = (int)((((fp.base[0] - fp.origin[0]) % 4) + 4) % 4);
   auto tile_at = [&](uint32_t t) {
@@ -685,6 +688,9 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     a.h0 = a.t0 + fp.base[0] - fp.origin[0];
     a.h1 = a.t1 + fp.base[1] - fp.origin[1];
     a.interior = a.h0 >= 0 && a.h1 >= 0 && a.h0 + SX <= (int64_t)fp.ie[0] && a.h1 + SY <= (int64_t)fp.ie[1];
+    // Border tiles are fetched by the TMA as well (out-of-image elements arrive as zeros) and patched in shared memory from the
+    // in-image part of the same box; only circular padding reads from the far side of the image and keeps the manual fill.
+    a.tma = a.interior || fp.padding != 3;
     return a;
   };
   if (warp == 8) {
@@ -694,7 +700,7 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
       for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = (int)(it % IMF_STAGES);
         const TileAt a = tile_at((uint32_t)t);
-        if (!a.interior) continue;  // border tiles are filled by the compute warps (they wait for `empty` themselves)
+        if (!a.tma) continue;  // circular-padding border tiles are filled by the compute warps (they wait for `empty` themselves)
         if (it >= IMF_STAGES && !imf_mbar_wait(&empty[s], ((it / IMF_STAGES) - 1) & 1u, err)) break;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(imf_smem_u32(&full[s])), "r"(C::BOX_BYTES) : "memory");
@@ -719,15 +725,34 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
   };
   const int ly0 = warp * RBW;
   const unsigned long long one2 = pack_f32x2(fp.one, fp.one);
-  uint32_t phase = 0;  // bit s: parity of the next completion of full[s] (it advances on interior tiles only)
+  uint32_t phase = 0;  // bit s: parity of the next completion of full[s] (it advances on TMA-fetched tiles only)
   uint32_t it = 0;
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int s = (int)(it % IMF_STAGES);
     float* tile = (float*)(dsm + (size_t)s * C::STAGE_BYTES);
     const TileAt a = tile_at((uint32_t)t);
-    if (a.interior) {
+    if (a.tma) {
       imf_mbar_wait(&full[s], (phase >> s) & 1u, err);
       phase ^= 1u << s;
+      if (!a.interior) {
+        // patch the out-of-image elements of the box (zeros from the TMA): constant -> cval; replicate / symmetric -> the value
+        // at the remapped coordinate, which lies in the in-image part of this same box (read from global memory if it does not)
+        const float* src = img + (uint64_t)a.plane * fp.ie[0] * fp.ie[1];
+        for (int idx = tid; idx < SY * SX; idx += 256) {
+          const int sy = idx / SX, sx = idx - sy * SX;
+          const int64_t gx = a.h0 + sx, gy = a.h1 + sy;
+          if (gx >= 0 && gx < (int64_t)fp.ie[0] && gy >= 0 && gy < (int64_t)fp.ie[1]) continue;
+          const int r = remap(gx, (int64_t)fp.ie[0]), c = remap(gy, (int64_t)fp.ie[1]);
+          float v;
+          if (r < 0 || c < 0) v = (float)fp.cval;
+          else {
+            const int64_t bx = (int64_t)r - a.h0, by = (int64_t)c - a.h1;
+            v = (bx >= 0 && bx < SX && by >= 0 && by < SY) ? tile[by * SXP + shift + bx] : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
+          }
+          tile[sy * SXP + shift + sx] = v;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
     } else {
       // every compute warp has released the stage's previous use; then fill it cooperatively and meet on a named barrier
       if (it >= IMF_STAGES) imf_mbar_wait(&empty[s], ((it / IMF_STAGES) - 1) & 1u, err);
@@ -742,21 +767,29 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     unsigned long long acc[RBW];
+    float accA[RBW], accB[RBW];
 #pragma unroll
-    for (int o = 0; o < RBW; ++o) acc[o] = pack_f32x2(0.0f, 0.0f);
+    for (int o = 0; o < RBW; ++o) { acc[o] = pack_f32x2(0.0f, 0.0f); accA[o] = 0.0f; accB[o] = 0.0f; }
 #pragma unroll
     for (int j = 0; j < RBW + K - 1; ++j) {
 #pragma unroll
       for (int k0 = 0; k0 < K; ++k0) {
-        const unsigned long long v = pack_f32x2(tile[(ly0 + j) * SXP + shift + lane + k0], tile[(ly0 + j) * SXP + shift + lane + 32 + k0]);
+        const float tA = tile[(ly0 + j) * SXP + shift + lane + k0], tB = tile[(ly0 + j) * SXP + shift + lane + 32 + k0];
+        const unsigned long long v = pack_f32x2(tA, tB);
 #pragma unroll
         for (int k1 = 0; k1 < K; ++k1) {
           const int o = j - k1;
           if (o >= 0 && o < RBW) {
             const float wk = w[k0 + k1 * K];
-            unsigned long long prod;
-            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod) : "l"(pack_f32x2(wk, wk)), "l"(v));
-            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[o]) : "l"(acc[o]), "l"(one2), "l"(prod));
+            if (MODE == 1 || (MODE == 2 && o < RBW / 2)) {  // o is a compile-time constant after unrolling
+              unsigned long long prod;
+              asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod) : "l"(pack_f32x2(wk, wk)), "l"(v));
+              asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[o]) : "l"(acc[o]), "l"(one2), "l"(prod));
+            } else {
+              // scalar FMUL + FADD (the library is compiled -fmad=false): one rounding after the multiply, one after the add
+              accA[o] = __fadd_rn(accA[o], __fmul_rn(wk, tA));
+              accB[o] = __fadd_rn(accB[o], __fmul_rn(wk, tB));
+            }
           }
         }
       }
@@ -770,7 +803,8 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     for (int o = 0; o < RBW; ++o, dst += fp.oe[0]) {
       if (o < nvalid) {
         float va, vb;
-        unpack_f32x2(acc[o], va, vb);
+        if (MODE == 1 || (MODE == 2 && o < RBW / 2)) unpack_f32x2(acc[o], va, vb);
+        else { va = accA[o]; vb = accB[o]; }
         if (oA < fp.oe[0]) __stcs(dst + oA, va);
         if (oB < fp.oe[0]) __stcs(dst + oB, vb);
       }
@@ -792,7 +826,7 @@ static ImfEncodeTiledFn imf_encode_tiled() {
   return fn;
 }
 // Returns false when the TMA path does not apply (the caller then launches the per-tile kernel).
-template <int K, int RBW>
+template <int K, int RBW, int MODE>
 static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* k, float* o, const FilterParams& fp) {
   using C = ImfTma<K, RBW>;
   const uint64_t ntx = (fp.oe[0] + FX - 1) / FX, nty = (fp.oe[1] + C::TY - 1) / C::TY, ntiles = ntx * nty * fp.oe[2];
@@ -819,12 +853,12 @@ static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* 
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (idempotent; a benign race)
-  if (!attr_set) { cudaFuncSetAttribute(imfilter_tma_f32_kernel<K, RBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(imfilter_tma_f32_kernel<K, RBW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr_set = true; }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imfilter_tma_f32_kernel<K, RBW>, 288, C::SMEM) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imfilter_tma_f32_kernel<K, RBW, MODE>, 288, C::SMEM) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
   const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)p->prop.multiProcessorCount * per_sm);
-  imfilter_tma_f32_kernel<K, RBW><<<grid, 288, C::SMEM, p->stream>>>(tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty, (uint32_t)ntiles, (int*)p->dev_flags + 0);
+  imfilter_tma_f32_kernel<K, RBW, MODE><<<grid, 288, C::SMEM, p->stream>>>(tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty, (uint32_t)ntiles, (int*)p->dev_flags + 0);
   return true;
 }
 template <int K>
@@ -832,8 +866,10 @@ static bool launch_imfilter_tma(rm_provider* p, const float* a, const float* k, 
   if (getenv("RUNMAT_B200_IMFILTER_NO_TMA")) return false;
   int rbw = 8;  // output rows per compute warp (tile = 64 x 8*rbw)
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_RBW")) rbw = atoi(e);
-  if (rbw == 4) return launch_imfilter_tma_rb<K, 4>(p, a, k, o, fp);
-  return launch_imfilter_tma_rb<K, 8>(p, a, k, o, fp);
+  int mode = 1;
+  if (const char* e = getenv("RUNMAT_B200_IMFILTER_MODE")) mode = atoi(e);
+  if (rbw == 4) return mode == 0 ? launch_imfilter_tma_rb<K, 4, 0>(p, a, k, o, fp) : mode == 2 ? launch_imfilter_tma_rb<K, 4, 2>(p, a, k, o, fp) : launch_imfilter_tma_rb<K, 4, 1>(p, a, k, o, fp);
+  return mode == 0 ? launch_imfilter_tma_rb<K, 8, 0>(p, a, k, o, fp) : mode == 2 ? launch_imfilter_tma_rb<K, 8, 2>(p, a, k, o, fp) : launch_imfilter_tma_rb<K, 8, 1>(p, a, k, o, fp);
 }
 
 template <typename T, int K>

@@ -302,6 +302,11 @@ RM_EXPORT rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4) {
   for (int i = 0; i < 4; ++i) out4[i] = tmp[i];
   return RM_OK;
 }
+RM_EXPORT rm_status rm_set_launch_overlap(rm_provider* p, int enabled) {
+  RM_REQUIRE(p, RM_INVALID_ARG, "rm_set_launch_overlap: null provider");
+  p->launch_overlap = enabled != 0;
+  return RM_OK;
+}
 RM_EXPORT rm_status rm_debug_device_flags(rm_provider* p, int32_t* out, uint32_t n) {
   RM_REQUIRE(p && out && n <= 64, RM_INVALID_ARG, "rm_debug_device_flags: bad arguments");
   for (uint32_t i = 0; i < n; ++i) out[i] = 0;

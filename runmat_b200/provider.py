@@ -503,6 +503,10 @@ class B200Provider:
         _check(lib.rm_debug_ozaki_stats(self._p, out))
         return {"nonfinite": int(out[0]), "pipeline_error": int(out[1]), "fp64_tiles": int(out[2])}
 
+    def set_launch_overlap(self, enabled: bool) -> None:
+        """Programmatic dependent launch of the generated fused kernels (default on); off = plain launches (isolated timing)."""
+        _check(lib.rm_set_launch_overlap(self._p, 1 if enabled else 0))
+
     def device_flags(self, n: int = 4) -> list[int]:
         """Device-side pipeline protocol flags (waits for the stream): all zero unless a bounded wait ran out."""
         out = (C.c_int32 * n)()

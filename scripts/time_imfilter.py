@@ -8,10 +8,10 @@ img = rng.uniform(0, 1, (2160, 3840, 3)).astype(np.float32)
 hi = p.upload(img)
 for K in (3, 5, 7):
     hk = p.upload(rng.uniform(0, 1, (K, K)).astype(np.float32))
-    for name, env in (("tma-staged rbw8", {}), ("tma-staged rbw8 2 CTA/SM", {"RUNMAT_B200_IMFILTER_CTAS": "2"}), ("tma-staged rbw4", {"RUNMAT_B200_IMFILTER_RBW": "4"}),
-                      ("tma-staged rbw4 3 CTA/SM", {"RUNMAT_B200_IMFILTER_RBW": "4", "RUNMAT_B200_IMFILTER_CTAS": "3"}),
+    for name, env in (("tma-staged packed rbw8", {}), ("tma-staged packed rbw4", {"RUNMAT_B200_IMFILTER_RBW": "4"}), ("tma-staged mixed rbw4", {"RUNMAT_B200_IMFILTER_RBW": "4", "RUNMAT_B200_IMFILTER_MODE": "2"}),
+                      ("tma-staged scalar rbw4", {"RUNMAT_B200_IMFILTER_RBW": "4", "RUNMAT_B200_IMFILTER_MODE": "0"}),
                       ("per-tile packed", {"RUNMAT_B200_IMFILTER_NO_TMA": "1"}), ("generic tiled", {"RUNMAT_B200_IMFILTER_GENERIC": "1"})):
-        for k in ("RUNMAT_B200_IMFILTER_NO_TMA", "RUNMAT_B200_IMFILTER_GENERIC", "RUNMAT_B200_IMFILTER_RBW", "RUNMAT_B200_IMFILTER_CTAS"):
+        for k in ("RUNMAT_B200_IMFILTER_NO_TMA", "RUNMAT_B200_IMFILTER_GENERIC", "RUNMAT_B200_IMFILTER_RBW", "RUNMAT_B200_IMFILTER_CTAS", "RUNMAT_B200_IMFILTER_MODE"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3): p.free(p.imfilter(hi, hk, padding="replicate"))

@@ -28,7 +28,7 @@ EXTENSIONS = {
     "rm_comm_p2p_connect", "rm_comm_p2p_connected", "rm_comm_p2p_error", "rm_fused_reduction_allreduce", "rm_stochastic_evolution_sharded",
     "rm_payoff_partial_sum",
     # measurement / tuning / debug
-    "rm_timer_begin", "rm_timer_end_ms", "rm_flush_l2", "rm_set_matmul_engine", "rm_debug_ozaki_stats", "rm_debug_device_flags", "rm_get_rng_state",
+    "rm_timer_begin", "rm_timer_end_ms", "rm_flush_l2", "rm_set_matmul_engine", "rm_debug_ozaki_stats", "rm_debug_device_flags", "rm_set_launch_overlap", "rm_get_rng_state",
     # the named per-op images are reached through the generic dispatchers (rm_elem_binary / rm_unary / rm_scalar_op_apply)
     "rm_elem_add", "rm_elem_mul", "rm_elem_max", "rm_elem_min", "rm_elem_sub", "rm_elem_div", "rm_elem_pow", "rm_elem_hypot", "rm_elem_atan2",
     "rm_unary_sin", "rm_unary_cos", "rm_unary_tan", "rm_unary_tanh", "rm_unary_exp", "rm_unary_log", "rm_unary_sqrt", "rm_unary_abs",
