@@ -112,9 +112,36 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 // stand-alone publish (for partials produced by a kernel that does not carry the fused tail)
+// Fold of one exchange step by ONE WARP (lanes < n wait for one rank's flag each, bounded; the N values are then folded in rank
+// order through shuffles, so every rank gets the bit-identical sum). Used by the stand-alone combine kernel and, fused in front of
+// a publish, by the publish kernel below; the generated reduction kernel carries the same code (fusion_lower.cpp combine_prev).
 template <typename T>
-__global__ void p2p_publish_kernel(P2PSlots* const* __restrict__ peers, int n, int rank, unsigned long long step, const T* __restrict__ value) {
+__device__ __forceinline__ void p2p_fold_warp(const P2PSlots* __restrict__ mine, int n, unsigned long long step, T* __restrict__ out, int* __restrict__ err) {
+  const int q = threadIdx.x & 31;
+  const int b = (int)(step % P2P_BANKS);
+  int bad = 0;
+  double v = 0.0;
+  if (q < n) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flags[b][q]) < step + 1) {
+      if (clock64() - t0 > 20000000000LL) { bad = 1; break; }  // ~10 s: a dead peer raises the error flag, never hangs the GPU
+      __nanosleep(100);
+    }
+    v = *(volatile const double*)&mine->vals[b][q];
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  double s = 0.0;
+  for (int r = 0; r < n; ++r) s += __shfl_sync(0xffffffffu, v, r);  // rank order
+  if (q == 0) {
+    if (bad) atomicExch(err, 1);
+    *out = (T)(bad ? __longlong_as_double(0x7ff8000000000000LL) : s);  // exchanged and folded in f64 whatever the storage type
+  }
+}
+template <typename T>
+__global__ void p2p_publish_kernel(P2PSlots* const* __restrict__ peers, int n, int rank, unsigned long long step, const T* __restrict__ value,
+                                   T* __restrict__ prev_dst, unsigned long long prev_step1, int* __restrict__ err) {
   const int q = threadIdx.x;
+  if (prev_step1) { p2p_fold_warp<T>(peers[rank], n, prev_step1 - 1, prev_dst, err); __syncwarp(); }
   if (q >= n) return;
   const int b = (int)(step % P2P_BANKS);
   P2PSlots* dst = peers[q];
@@ -123,27 +150,7 @@ __global__ void p2p_publish_kernel(P2PSlots* const* __restrict__ peers, int n, i
 }
 template <typename T>
 __global__ void p2p_combine_kernel(const P2PSlots* __restrict__ mine, int n, unsigned long long step, T* __restrict__ out, int* __restrict__ err) {
-  __shared__ double v[P2P_MAXR];
-  __shared__ int bad;
-  const int q = threadIdx.x;
-  const int b = (int)(step % P2P_BANKS);
-  if (q == 0) bad = 0;
-  __syncthreads();
-  if (q < n) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(&mine->flags[b][q]) < step + 1) {
-      if (clock64() - t0 > 20000000000LL) { bad = 1; break; }  // ~10 s: a dead peer raises the error flag, never hangs the GPU
-      __nanosleep(200);
-    }
-    v[q] = *(volatile const double*)&mine->vals[b][q];
-  }
-  __syncthreads();
-  if (q == 0) {
-    if (bad) atomicExch(err, 1);
-    double s = 0.0;
-    for (int r = 0; r < n; ++r) s += v[r];  // rank order: bit-identical on every rank
-    *out = (T)(bad ? __longlong_as_double(0x7ff8000000000000LL) : s);  // exchanged and folded in f64 whatever the storage type
-  }
+  p2p_fold_warp<T>(mine, n, step, out, err);
 }
 
 P2PState* p2p_state(rm_provider* p) { return (P2PState*)p->p2p; }
@@ -159,15 +166,17 @@ void p2p_enqueue_combine_locked(rm_provider* p, uint64_t step, void* dst) {
   count_launch(p);
 }
 
-// Enqueues the still-pending combine of `step` (if its handle has not been used or freed yet). Caller holds p->comm_mu.
-static void p2p_force(rm_provider* p, P2PState* s, uint64_t step) {
+// The still-pending combine of `step` (if its handle has not been used or freed yet): enqueued as a kernel of its own, or -- with
+// `take` -- handed to the caller, who fuses it in front of the publish it is about to enqueue. Caller holds p->comm_mu.
+static void p2p_force(rm_provider* p, P2PState* s, uint64_t step, void** take = nullptr) {
   const int b = (int)(step % P2P_BANKS);
   if (s->ring_step1[b] != step + 1) return;
   s->ring_step1[b] = 0;
   std::lock_guard<std::mutex> lk(p->mu);
   auto it = p->buffers.find(s->ring_id[b]);
   if (it == p->buffers.end() || it->second.p2p_step1 != step + 1) return;  // already enqueued by resolve() / rm_free()
-  p2p_enqueue_combine_locked(p, step, it->second.ptr);
+  if (take) *take = it->second.ptr;
+  else p2p_enqueue_combine_locked(p, step, it->second.ptr);
   it->second.p2p_step1 = 0;
 }
 
@@ -177,8 +186,17 @@ bool p2p_begin(rm_provider* p, P2PPublish* pub) {
   P2PState* s = p2p_state(p);
   if (!s || !s->connected) return false;
   const uint64_t t = s->step;
-  // bank reuse rule: publish(t) is ordered (same stream) after this rank's combine(t - LAG)
-  if (t >= (uint64_t)P2P_LAG) p2p_force(p, s, t - P2P_LAG);
+  // bank reuse rule: publish(t) is ordered after this rank's combine(t - LAG) -- fused into the publishing kernel itself (the last
+  // block folds step t - LAG into its handle, then publishes step t): in steady state the exchange costs no kernel of its own
+  // (r15, N = 2: a separate 1-CTA combine kernel per step sat between two programmatically-overlapped kernels and cost ~8 us)
+  pub->prev_dst = nullptr;
+  pub->prev_step1 = 0;
+  if (t >= (uint64_t)P2P_LAG) {
+    void* dst = nullptr;
+    p2p_force(p, s, t - P2P_LAG, &dst);
+    if (dst) { pub->prev_dst = dst; pub->prev_step1 = t - P2P_LAG + 1; }
+  }
+  pub->err = s->d_err;
   pub->peers = (void* const*)s->d_peers;
   pub->n = (uint32_t)s->world;
   pub->rank = (uint32_t)s->rank;
@@ -363,8 +381,10 @@ RM_EXPORT rm_status rm_comm_allreduce_sum(rm_provider* p, const rm_handle* in, r
     std::lock_guard<std::mutex> lk(p->comm_mu);
     P2PPublish pub;
     if (p2p_begin(p, &pub)) {
-      if (p->precision == RM_F64) p2p_publish_kernel<double><<<1, 32, 0, p->stream>>>((P2PSlots* const*)pub.peers, (int)pub.n, (int)pub.rank, pub.step, (const double*)src);
-      else p2p_publish_kernel<float><<<1, 32, 0, p->stream>>>((P2PSlots* const*)pub.peers, (int)pub.n, (int)pub.rank, pub.step, (const float*)src);
+      if (p->precision == RM_F64)
+        p2p_publish_kernel<double><<<1, 32, 0, p->stream>>>((P2PSlots* const*)pub.peers, (int)pub.n, (int)pub.rank, pub.step, (const double*)src, (double*)pub.prev_dst, pub.prev_step1, pub.err);
+      else
+        p2p_publish_kernel<float><<<1, 32, 0, p->stream>>>((P2PSlots* const*)pub.peers, (int)pub.n, (int)pub.rank, pub.step, (const float*)src, (float*)pub.prev_dst, pub.prev_step1, pub.err);
       RM_LAUNCH_CHECK();
       count_launch(p);
       return p2p_finish(p, out);

@@ -165,6 +165,11 @@ struct P2PPublish {
   void* const* peers = nullptr;  // device array of per-rank slot buffers
   uint32_t n = 0, rank = 0;
   uint64_t step = 0;
+  // combine of an earlier step fused in front of this publish (bank-reuse rule of the protocol): destination of the folded sum
+  // (provider precision), its step + 1 (0 = nothing pending) and the device error flag of the bounded wait
+  void* prev_dst = nullptr;
+  uint64_t prev_step1 = 0;
+  int* err = nullptr;
 };
 bool p2p_begin(rm_provider* p, P2PPublish* pub);     // caller holds p->comm_mu until p2p_finish()
 rm_status p2p_finish(rm_provider* p, rm_handle* out);

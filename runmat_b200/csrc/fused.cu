@@ -438,6 +438,12 @@ rm_status run_reduction_program(rm_provider* p, const ReductionProgram& prog, co
       args.push_back(&pub_n);
       args.push_back(&pub_rank);
       args.push_back(&pub_step);
+      void* pub_prev_dst = publish ? publish->prev_dst : nullptr;
+      unsigned long long pub_prev_step1 = publish ? publish->prev_step1 : 0;
+      int* pub_err = publish ? publish->err : nullptr;
+      args.push_back(&pub_prev_dst);
+      args.push_back(&pub_prev_step1);
+      args.push_back(&pub_err);
       args.push_back(&param0);  // free scalar of the value expression (`p0`), e.g. the strike of the payoff reduction
       st = launch(p, kern, grid, block, args.data());
     }

@@ -467,6 +467,36 @@ __device__ __forceinline__ T finish(double acc, int use_div, double factor) {
 // over NVLink; nothing waits here, the fold happens in the consumer's combine.
 #define P2P_BANKS 8
 #define P2P_MAXR 16
+// Combine of an earlier exchange step fused in front of the publish (comm.cu p2p_fold_warp, same protocol): executed by warp 0 of
+// the block that holds the final scalar. Lanes < n wait (bounded) for one rank's flag each in this rank's own slot buffer, the N
+// values are folded in rank order, lane 0 writes the sum into the earlier step's result handle.
+__device__ __forceinline__ void combine_prev(void* const* peers, u32 n, u32 rank, u64 prev_step1, T* prev_dst, int* err) {
+  const u64 step = prev_step1 - 1;
+  const char* base = (const char*)peers[rank];
+  const u64 slot0 = (step % P2P_BANKS) * P2P_MAXR;
+  const u32 q = threadIdx.x & 31;
+  int bad = 0;
+  double v = 0.0;
+  if (q < n) {
+    const unsigned long long* flag = (const unsigned long long*)(base + (u64)P2P_BANKS * P2P_MAXR * 8 + (slot0 + q) * 8);
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long f;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flag) : "memory");
+      if (f >= step + 1) break;
+      if (clock64() - t0 > 20000000000LL) { bad = 1; break; }
+      __nanosleep(100);
+    }
+    v = *(volatile const double*)(base + (slot0 + q) * 8);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  double s = 0.0;
+  for (u32 r = 0; r < n; ++r) s += __shfl_sync(0xffffffffu, v, r);
+  if (q == 0) {
+    if (bad) atomicExch(err, 1);
+    *prev_dst = (T)(bad ? CANON_NAN : s);
+  }
+}
 __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 rank, u64 step, double value) {
   if (threadIdx.x < n) {
     char* base = (char*)peers[threadIdx.x];
@@ -486,7 +516,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
-         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n  RM_PDL_PROLOGUE();\n";
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, T* __restrict__ pub_prev_dst, u64 pub_prev_step1,\n    int* __restrict__ pub_err, double p0) {\n  RM_PDL_PROLOGUE();\n";
     o << "  __shared__ double smem[32];\n  __shared__ bool is_last;\n";
     o << "  const u64 slice = blockIdx.x / bps;\n  const u32 bidx = blockIdx.x % bps;\n  const u64 base = slice * len;\n";
     o << "  const u64 nvec = vec_ok ? len / VEC : 0;\n";
@@ -517,7 +547,11 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
   double total = block_reduce(COMBINE(acc0, acc1), smem);
   if (bps == 1) {
     if (threadIdx.x == 0) { const T r = finish(total, use_div, factor); out[slice] = r; smem[0] = (double)r; }
-    if (pub_n) { __syncthreads(); publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]); }
+    if (pub_n) {
+    __syncthreads();
+    if (pub_prev_step1 && threadIdx.x < 32) combine_prev(pub_peers, pub_n, pub_rank, pub_prev_step1, pub_prev_dst, pub_err);
+    publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]);
+  }
     return;
   }
   // two-stage, atomic-free on the data path: partials are combined by the LAST block in a fixed order
@@ -534,7 +568,11 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
   for (u32 b = threadIdx.x; b < bps; b += blockDim.x) acc2 = COMBINE(acc2, __ldcg(&partial[slice * bps + b]));
   double total2 = block_reduce(acc2, smem);
   if (threadIdx.x == 0) { const T r = finish(total2, use_div, factor); out[slice] = r; tickets[slice] = 0; smem[0] = (double)r; }
-  if (pub_n) { __syncthreads(); publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]); }
+  if (pub_n) {
+    __syncthreads();
+    if (pub_prev_step1 && threadIdx.x < 32) combine_prev(pub_peers, pub_n, pub_rank, pub_prev_step1, pub_prev_dst, pub_err);
+    publish_scalar(pub_peers, pub_n, pub_rank, pub_step, smem[0]);
+  }
 }
 )CUDA";
   } else if (layout == RedLayout::Interleaved) {
@@ -550,7 +588,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << "extern \"C\" __global__ void __launch_bounds__(256, 4) rm_fused_red(" << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
-         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n  RM_PDL_PROLOGUE();\n";
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, T* __restrict__ pub_prev_dst, u64 pub_prev_step1,\n    int* __restrict__ pub_err, double p0) {\n  RM_PDL_PROLOGUE();\n";
     o << "  __shared__ double shw[8 * 256];\n  __shared__ bool is_last;\n";
     o << "  const u32 in_ = (u32)inner, R = in_ > VEC ? in_ : VEC, G = R / VEC;\n";
     o << "  const u64 blk = inner * len, pbase = (u64)blockIdx.y * blk;\n";
@@ -625,7 +663,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(" << input_params(ni)
       << "T* __restrict__ out, double* __restrict__ partial, u32* __restrict__ pflags, u32* __restrict__ tickets,\n"
          "    u64 len, u64 num_slices, int vec_ok, int use_div, double factor, u32 bps, u64 inner, u32 sl,\n"
-         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, double p0) {\n  RM_PDL_PROLOGUE();\n";
+         "    void* const* __restrict__ pub_peers, u32 pub_n, u32 pub_rank, u64 pub_step, T* __restrict__ pub_prev_dst, u64 pub_prev_step1,\n    int* __restrict__ pub_err, double p0) {\n  RM_PDL_PROLOGUE();\n";
     o << "  __shared__ bool is_last;\n  __shared__ double sacc[256];\n";
     o << "  const u32 sloc = threadIdx.x % sl, lane = threadIdx.x / sl, rl = blockDim.x / sl;\n";
     o << "  const u64 s = (u64)blockIdx.x * sl + sloc;\n";

@@ -354,45 +354,86 @@ __global__ void __launch_bounds__(2 * NB) perm_apply_kernel(double* __restrict__
 // substitution with the stored diagonal; MODE 2 (TRSM_LOWER): forward substitution with the stored diagonal (linsolve's
 // general lower-triangular systems). One CTA handles 32 columns; T and the column tile live in shared memory.
 constexpr int TRSM_UPPER = 0, TRSM_LOWER_UNIT = 1, TRSM_LOWER = 2;
+// r06 launch list: the first version (columns in shared memory, 8 row-parts per column, two __syncthreads per substitution step)
+// took 22 us per 64x64 block whatever the number of right-hand sides, ~240 launches per 4096 solve. Here a warp owns 4 columns
+// and keeps them in REGISTERS (lane l holds rows l and l+32): a substitution step is one shuffle broadcast of x_i per column, two
+// conflict-free shared loads of T's column i and two DFMAs per column -- no block-wide barrier inside the 64-step chain.
 template <int MODE>
 __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restrict__ T, uint64_t ldt, int jb, double* __restrict__ Bm, uint64_t ldb, uint64_t ncols) {
   extern __shared__ double trsm_smem[];
-  double (*sT)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem);                    // [NB][NB+1]
-  double (*sB)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem + NB * (NB + 1));    // [32][NB+1]  ([col][row])
-  const uint64_t c0 = (uint64_t)blockIdx.x * 32;
-  for (int i = threadIdx.x; i < jb * jb; i += 256) { const int r = i % jb, c = i / jb; sT[r][c] = T[r + (uint64_t)c * ldt]; }
-  for (int i = threadIdx.x; i < jb * 32; i += 256) {
-    const int r = i % jb, c = i / jb;
-    sB[c][r] = (c0 + c < ncols) ? Bm[r + (c0 + c) * ldb] : 0.0;
+  double (*sT)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem);  // [row][col], padded: lanes walking rows hit distinct banks
+  for (int i = threadIdx.x; i < NB * NB; i += 256) {
+    const int r = i % NB, c = i / NB;
+    sT[r][c] = (r < jb && c < jb) ? T[r + (uint64_t)c * ldt] : (r == c ? 1.0 : 0.0);  // identity padding: rows >= jb never change anything
   }
   __syncthreads();
-  const int col = threadIdx.x & 31, part = threadIdx.x >> 5;  // 8 row-parts per column
-  if (MODE == TRSM_LOWER_UNIT) {
-    for (int i = 0; i < jb; ++i) {
-      const double xi = sB[col][i];
-      for (int k = i + 1 + part; k < jb; k += 8) sB[col][k] -= sT[k][i] * xi;
-      __syncthreads();
+  constexpr int CW = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t c0 = (uint64_t)blockIdx.x * 32 + (uint64_t)warp * CW;
+  double b0[CW], b1[CW];
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    const bool ok = c0 + c < ncols;
+    b0[c] = (ok && lane < jb) ? Bm[lane + (c0 + c) * ldb] : 0.0;
+    b1[c] = (ok && lane + 32 < jb) ? Bm[lane + 32 + (c0 + c) * ldb] : 0.0;
+  }
+  if (MODE == TRSM_LOWER_UNIT || MODE == TRSM_LOWER) {
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const double l0 = sT[lane][i], l1 = sT[lane + 32][i];
+      const double d = MODE == TRSM_LOWER ? sT[i][i] : 1.0;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        double xi = __shfl_sync(0xffffffffu, b0[c], i);
+        if (MODE == TRSM_LOWER) { xi = xi / d; if (lane == i) b0[c] = xi; }
+        if (lane > i) b0[c] -= l0 * xi;
+        b1[c] -= l1 * xi;
+      }
     }
-  } else if (MODE == TRSM_LOWER) {
-    for (int i = 0; i < jb; ++i) {
-      if (part == 0) sB[col][i] = sB[col][i] / sT[i][i];
-      __syncthreads();
-      const double xi = sB[col][i];
-      for (int k = i + 1 + part; k < jb; k += 8) sB[col][k] -= sT[k][i] * xi;
-      __syncthreads();
+#pragma unroll 4
+    for (int i = 32; i < NB; ++i) {
+      const double l1 = sT[lane + 32][i];
+      const double d = MODE == TRSM_LOWER ? sT[i][i] : 1.0;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        double xi = __shfl_sync(0xffffffffu, b1[c], i - 32);
+        if (MODE == TRSM_LOWER) { xi = xi / d; if (lane == i - 32) b1[c] = xi; }
+        if (lane + 32 > i) b1[c] -= l1 * xi;
+      }
     }
   } else {
-    for (int i = jb - 1; i >= 0; --i) {
-      if (part == 0) sB[col][i] = sB[col][i] / sT[i][i];
-      __syncthreads();
-      const double xi = sB[col][i];
-      for (int k = part; k < i; k += 8) sB[col][k] -= sT[k][i] * xi;
-      __syncthreads();
+#pragma unroll 4
+    for (int i = NB - 1; i >= 32; --i) {
+      const double u0 = sT[lane][i], u1 = sT[lane + 32][i];
+      const double d = sT[i][i];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        double xi = __shfl_sync(0xffffffffu, b1[c], i - 32);
+        xi = xi / d;
+        if (lane == i - 32) b1[c] = xi;
+        if (lane + 32 < i) b1[c] -= u1 * xi;
+        b0[c] -= u0 * xi;
+      }
+    }
+#pragma unroll 4
+    for (int i = 31; i >= 0; --i) {
+      const double u0 = sT[lane][i];
+      const double d = sT[i][i];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        double xi = __shfl_sync(0xffffffffu, b0[c], i);
+        xi = xi / d;
+        if (lane == i) b0[c] = xi;
+        if (lane < i) b0[c] -= u0 * xi;
+      }
     }
   }
-  for (int i = threadIdx.x; i < jb * 32; i += 256) {
-    const int r = i % jb, c = i / jb;
-    if (c0 + c < ncols) Bm[r + (c0 + c) * ldb] = sB[c][r];
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    if (c0 + c < ncols) {
+      if (lane < jb) Bm[lane + (c0 + c) * ldb] = b0[c];
+      if (lane + 32 < jb) Bm[lane + 32 + (c0 + c) * ldb] = b1[c];
+    }
   }
 }
 
@@ -620,7 +661,11 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   SV_CUDA(cudaMallocAsync((void**)&rowbuf, 2 * NB * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&cand, (size_t)2 * std::max(slab_max_grid, 1u) * sizeof(Candidate), st));
   SV_CUDA(cudaMallocAsync((void**)&moves, sizeof(RowMoves), st));
-  SV_CUDA(cudaMallocAsync((void**)&LU, n * n * 8, st));
+  // Augmented system [A | B] in one column-major buffer (ld = n): the row interchanges, the U12 solves and the trailing updates
+  // of the factorisation then carry the right-hand sides along, i.e. the forward substitution L y = P b costs no launches of its
+  // own (r06: 64 triangular solves + 63 skinny GEMMs = 3.3 ms of the 32 ms at n = 4096).
+  const uint64_t ntot = n + nrhs;
+  SV_CUDA(cudaMallocAsync((void**)&LU, n * ntot * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&ipiv, n * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&scratch, (size_t)max_grid * sizeof(PivotEntry), st));
   SV_CUDA(cudaMallocAsync((void**)&info, 8, st));
@@ -633,7 +678,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   SV_CUDA(cudaMemcpyAsync(LU, pa, n * n * 8, cudaMemcpyDeviceToDevice, st));
   SV_TRY(alloc_tensor(p, oshape, 2, out, &px));
   have_out = true;
-  double* X = (double*)px;
+  double* X = LU + n * n;  // the right-hand sides ride in the augmented columns; copied to the result tensor at the end
   SV_CUDA(cudaMemcpyAsync(X, pb, n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
   absmax_kernel<<<(unsigned)std::min<uint64_t>((n * n + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 8), 256, 0, st>>>(LU, n * n, amax, info + 1);
   count_launch(p);
@@ -672,18 +717,18 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     }
     // row interchanges outside the panel (LU columns left and right of it) and on the right-hand sides
     const uint64_t rest = n - j0 - jb;
-    if (n - jb > 0) perm_apply_kernel<<<(unsigned)std::min<uint64_t>(n - jb, 4096), 2 * NB, 0, st>>>(LU, n, n - jb, j0, (uint64_t)jb, moves);
-    perm_apply_kernel<<<(unsigned)std::min<uint64_t>(nrhs, 4096), 2 * NB, 0, st>>>(X, n, nrhs, nrhs, 0, moves);
-    count_launch(p, 3);
+    perm_apply_kernel<<<(unsigned)std::min<uint64_t>(ntot - jb, 4096), 2 * NB, 0, st>>>(LU, n, ntot - jb, j0, (uint64_t)jb, moves);
+    count_launch(p, 2);
     const uint64_t rest_in = Jend - (j0 + jb);  // columns of the outer block still to factor
     if (rest_in > 0) {
       // inside the outer block: A12 <- L11^-1 A12 ; A22 -= A21 * A12
       trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((rest_in + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest_in);
       count_launch(p);
       SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, LU + j0 + (j0 + jb) * n, n, LU + (j0 + jb) + (j0 + jb) * n, n, rest, rest_in, (uint64_t)jb));
-    } else if (Jend < n) {
-      // outer block [J0, Jend) is factored: U12 <- L11^-1 A12 by 64-row steps, then one rank-(Jend-J0) trailing update
-      const uint64_t right = n - Jend;
+    } else {
+      // outer block [J0, Jend) is factored: U12 <- L11^-1 A12 by 64-row steps (A12 includes the right-hand-side columns), then one
+      // rank-(Jend-J0) update of the rows below
+      const uint64_t right = ntot - Jend;
       for (uint64_t i0 = J0; i0 < Jend; i0 += NB) {
         const int ib = (int)std::min<uint64_t>(NB, Jend - i0);
         trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, st>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
@@ -691,7 +736,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
         const uint64_t below = Jend - (i0 + ib);
         if (below > 0) SV_TRY(dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, LU + i0 + Jend * n, n, LU + (i0 + ib) + Jend * n, n, below, right, (uint64_t)ib));
       }
-      SV_TRY(dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + Jend * n, n, LU + Jend + Jend * n, n, right, right, Jend - J0));
+      if (n > Jend) SV_TRY(dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + Jend * n, n, LU + Jend + Jend * n, n, n - Jend, right, Jend - J0));
     }
   }
   SV_CUDA(cudaGetLastError());
@@ -713,14 +758,6 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     return fail(RM_UNSUPPORTED, "mldivide: matrix is singular or badly conditioned for LU (min pivot %.3e, max |A| %.3e); not supported by provider", h_info[0] ? 0.0 : h_mm[0], amaxv);
   }
 
-  // forward substitution: L y = P b
-  for (uint64_t j0 = 0; j0 < n; j0 += NB) {
-    const int jb = (int)std::min<uint64_t>(NB, n - j0);
-    trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((nrhs + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, X + j0, n, nrhs);
-    count_launch(p);
-    const uint64_t rest = n - j0 - jb;
-    if (rest > 0) SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, X + j0, n, X + j0 + jb, n, rest, nrhs, (uint64_t)jb));
-  }
   // backward substitution: U x = y
   for (uint64_t jend = n; jend > 0;) {
     const uint64_t j0 = ((jend - 1) / NB) * NB;
@@ -730,6 +767,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     if (j0 > 0) SV_TRY(dgemm_sub_strided(p, LU + j0 * n, n, X + j0, n, X, n, j0, nrhs, (uint64_t)jb));
     jend = j0;
   }
+  SV_CUDA(cudaMemcpyAsync(px, X, n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
   SV_CUDA(cudaGetLastError());
   cleanup(false);
 #undef SV_CUDA
