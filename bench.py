@@ -797,11 +797,12 @@ def single_gpu_kernels(p, rank, local_rank, peak_hbm):
     st = p.ozaki_stats()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     bf16 = float(peaks.get("bf16_tflops", 2250.0 * 0.76))
-    int8_ops = 29 * 2.0 * n ** 3  # 28 digit products + the accuracy guard's magnitude product, all exact int8 GEMMs
-    out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "fp64_fallback_tiles": st["fp64_tiles"],
-                              "engine": "auto -> tcgen05 (Ozaki int8 split, 7 slices = 28 exact int8 GEMMs + 1 guard GEMM, TMEM int32 accumulate, f64 recombine; "
-                                        "device-side accuracy guard, no host sync)",
-                              "roofline": {"bound": "tensor", "work_model": "29 int8 GEMMs of 2*8192^3 op; peak = 2 x the measured bf16 burst (int8 rate = 2 x bf16 on tcgen05)",
+    ng = st.get("int8_gemms") or 29  # digit products + the accuracy guard's magnitude product, all exact int8 GEMMs (reported by the library)
+    int8_ops = ng * 2.0 * n ** 3
+    out["matmul_8192_f64"] = {"ms": ms, "gflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "fp64_fallback_tiles": st["fp64_tiles"], "int8_gemms": ng,
+                              "engine": f"auto -> tcgen05 (Ozaki int8 split: {ng - 1} exact int8 digit GEMMs + 1 guard GEMM, TMEM int32 accumulate, f64 recombine; "
+                                        "8-bit digits x 6 slices for K <= 21760, 7-bit x 7 beyond; device-side accuracy guard, no host sync)",
+                              "roofline": {"bound": "tensor", "work_model": f"{ng} int8 GEMMs of 2*8192^3 op; peak = 2 x the measured bf16 burst (int8 rate = 2 x bf16 on tcgen05)",
                                            "achieved": int8_ops / (ms * 1e-3) / 1e12, "peak": 2 * bf16, "unit": "TOP/s", "frac": int8_ops / (ms * 1e-3) / 1e12 / (2 * bf16),
                                            "f64_equivalent_tflops": 2.0 * n ** 3 / (ms * 1e-3) / 1e12}}
     p.set_matmul_engine(1)

@@ -318,7 +318,8 @@ rm_status rm_diag_extract(rm_provider* p, const rm_handle* matrix, int64_t offse
  * The tcgen05 engine is element-wise safe on every input: entries whose terms hide under the row/column maximum, and
  * non-finite inputs, are detected on the device and recomputed by the FP64 kernel in the same stream (gemm_ozaki.cu). */
 rm_status rm_set_matmul_engine(rm_provider* p, int engine);
-/* test/debug: waits for the stream; out4 = {non-finite input seen, pipeline error, tiles recomputed in FP64, 0} of the last tcgen05 product */
+/* test/debug: waits for the stream; out4 = {non-finite input seen, pipeline error, tiles recomputed in FP64, int8 GEMMs per tile
+ * (digit products + guard)} of the last tcgen05 product */
 rm_status rm_debug_ozaki_stats(rm_provider* p, int32_t* out4);
 /* measurement / tuning: the generated fused kernels are launched with programmatic stream serialisation (each opens with
  * griddepcontrol.launch_dependents + griddepcontrol.wait, so a kernel becomes resident while its predecessor drains; stream order

@@ -118,6 +118,7 @@ struct rm_provider {
   std::atomic<uint64_t> host_syncs{0};
   void* dev_flags = nullptr;  // int[64], zero-initialised: [0] imfilter TMA pipeline protocol error (image.cu)
   void* l2_flush = nullptr;
+  cudaStream_t aux_stream = nullptr;  // solve.cu: update stream of the look-ahead LU (created at first use)
   size_t l2_flush_bytes = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   // uploads run on their own stream so H2D copies overlap compute and D2H traffic queued on `stream`
@@ -254,6 +255,6 @@ int ozaki_default_slices();
 void ozaki_workspace_destroy(rm_provider* p);
 rm_status ozaki_last_stats(rm_provider* p, int out[4]);
 rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const double* B, uint64_t ldb, double* C, uint64_t ldc,
-                            uint64_t m, uint64_t n, uint64_t k);
+                            uint64_t m, uint64_t n, uint64_t k, cudaStream_t stream = nullptr);
 
 }  // namespace rm

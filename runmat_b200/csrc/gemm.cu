@@ -325,7 +325,8 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
 
 // C (ldc) -= A (lda) * B (ldb) on sub-matrices of column-major storage: the GEMM core of mldivide's blocked LU / solves.
 rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const double* B, uint64_t ldb, double* C, uint64_t ldc,
-                            uint64_t m, uint64_t n, uint64_t k) {
+                            uint64_t m, uint64_t n, uint64_t k, cudaStream_t stream) {
+  if (!stream) stream = p->stream;
   if (m == 0 || n == 0 || k == 0) return RM_OK;
   Epilogue ep{};
   ep.alpha = 1.0;
@@ -334,10 +335,10 @@ rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const
   const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A) % 16 == 0) && (((uintptr_t)B) % 16 == 0);
   if (aligned) {
     cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
+    dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
   } else {
     cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, p->stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
+    dgemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
   }
   RM_LAUNCH_CHECK();
   count_launch(p);

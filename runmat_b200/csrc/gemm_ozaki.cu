@@ -13,6 +13,8 @@
 //      last one. The C tile (256 KB) is owned by one CTA, so the read-modify-write stays in L2.
 // Truncation error: 2^(-7S) of the row/column maximum per element; S = 7 (49 bits) is below the rounding noise of a
 // native f64 dot product of length 8192 (~sqrt(k)*2^-53 relative to sum|a||b|), S = 8 gives 56 bits.
+// Round 2: for K <= 21760 the digits are 8 bits wide (base 256, q in [-128, 127] after a carry fix-up, |x| < 0.49): S = 6 slices
+// carry 48 bits with 21 + 1 int8 GEMMs instead of 28 + 1 (formulas below with 7 -> 8, 128 -> 256, 2^-16 -> 2^-18).
 //
 // Element-wise accuracy guard (a posteriori, on the device, no host round trip). The split is accurate relative to
 // rowmax(A)_i * colmax(B)_j, not relative to sum_k |a_ik||b_kj| (a row [1e20, 1] against a column [1e-20; 1] loses the
@@ -133,9 +135,13 @@ __device__ __forceinline__ double oz_apply_epilogue(double v, const OzEpilogue& 
 }
 
 // exponent e with |x| * 2^-e < 1/2 for every |x| <= max (bits = IEEE pattern of max >= 0)
-__device__ __forceinline__ int scale_exponent(unsigned long long maxbits) {
+// 8-bit digits additionally need |x| < 0.49, so that the leading digit rint(256 x) stays <= 125 and can absorb a carry (slice_kernel)
+__device__ __forceinline__ int scale_exponent(unsigned long long maxbits, int bits) {
   if (maxbits == 0ull) return 0;
-  return ilogb(__longlong_as_double((long long)maxbits)) + 2;
+  const double mx = __longlong_as_double((long long)maxbits);
+  int e = ilogb(mx) + 2;
+  if (bits == 8 && scalbn(mx, -e) >= 0.49) ++e;
+  return e;
 }
 
 // ---- 1. per-row / per-column maxima (as IEEE bit patterns: non-negative doubles order like integers) --------------------
@@ -170,7 +176,7 @@ __global__ void colmax_kernel(const double* __restrict__ B, uint64_t k, uint64_t
 // Tile: 32 rows x 128 k. Each thread converts 16 elements; the write-out is 16-byte vectors, 128 B per (slice,row).
 template <bool IS_A>
 __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ X, uint64_t rows, uint64_t K, const unsigned long long* __restrict__ maxbits,
-                                                    int8_t* __restrict__ out, uint64_t rows_p, uint64_t Kp, int S, const int* __restrict__ flags) {
+                                                    int8_t* __restrict__ out, uint64_t rows_p, uint64_t Kp, int S, int bits, const int* __restrict__ flags) {
   extern __shared__ __align__(16) int8_t sh[];  // [S + 1][32][144]; slice S = |q_0| (the accuracy guard's magnitude operand)
   constexpr int PITCH = 144;
   if (flags[0]) return;  // non-finite input: every tile goes to the FP64 kernel, no slices needed
@@ -185,14 +191,37 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ X
     double x = 0.0;
     if (r < rows && kk < K) {
       const double v = IS_A ? X[r + kk * rows] : X[kk + r * K];
-      x = scalbn(v, -scale_exponent(maxbits[r]));  // exact; |x| < 1/2
+      x = scalbn(v, -scale_exponent(maxbits[r], bits));  // exact; |x| < 1/2 (< 0.49 with 8-bit digits)
     }
-    for (int s = 0; s < S; ++s) {
-      x *= 128.0;                 // exact
-      const double q = rint(x);   // |q| <= 64
-      x -= q;                     // exact remainder, |x| <= 1/2
-      sh[(s * 32 + rl) * PITCH + kl] = (int8_t)(int)q;
-      if (s == 0) sh[(S * 32 + rl) * PITCH + kl] = (int8_t)(int)fabs(q);
+    if (bits == 7) {
+      for (int s = 0; s < S; ++s) {
+        x *= 128.0;                 // exact
+        const double q = rint(x);   // |q| <= 64
+        x -= q;                     // exact remainder, |x| <= 1/2
+        sh[(s * 32 + rl) * PITCH + kl] = (int8_t)(int)q;
+        if (s == 0) sh[(S * 32 + rl) * PITCH + kl] = (int8_t)(int)fabs(q);
+      }
+    } else {
+      // base 256: rint gives digits in [-128, 128]; +128 does not fit an int8, so it becomes -128 with a carry into the next
+      // more significant digit (128 * 256^-(s+1) = 256^-s - 128 * 256^-(s+1)). The leading digit is <= 125 and absorbs a carry.
+      int qd[MAX_SLICES];
+#pragma unroll
+      for (int s = 0; s < MAX_SLICES; ++s) {
+        qd[s] = 0;
+        if (s < S) {
+          x *= 256.0;                // exact
+          const double q = rint(x);  // |q| <= 128
+          x -= q;                    // exact remainder, |x| <= 1/2
+          qd[s] = (int)q;
+        }
+      }
+#pragma unroll
+      for (int s = MAX_SLICES - 1; s >= 1; --s)
+        if (qd[s] >= 128) { qd[s] -= 256; qd[s - 1] += 1; }
+#pragma unroll
+      for (int s = 0; s < MAX_SLICES; ++s)
+        if (s < S) sh[(s * 32 + rl) * PITCH + kl] = (int8_t)qd[s];
+      sh[(S * 32 + rl) * PITCH + kl] = (int8_t)(qd[0] < 0 ? -qd[0] : qd[0]);
     }
   }
   __syncthreads();
@@ -215,7 +244,7 @@ __device__ __forceinline__ void pass_pair(int pi, int S, int idx, int* s, int* t
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C, uint64_t M, uint64_t N,
-                  int Mp, int Np, int Kp, int S, const unsigned long long* __restrict__ amax, const unsigned long long* __restrict__ bmax,
+                  int Mp, int Np, int Kp, int S, int bits, const unsigned long long* __restrict__ amax, const unsigned long long* __restrict__ bmax,
                   const __grid_constant__ OzEpilogue ep, int* __restrict__ flags, int* __restrict__ tileflags, long long guard_min) {
   extern __shared__ uint8_t smem_raw[];
   if (flags[0]) return;  // non-finite input (uniform for the grid): the conditional FP64 kernel computes every tile
@@ -306,14 +335,14 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tile_coords(tile, tiles_m, tiles_n, &m0, &n0);
       const uint64_t row = (uint64_t)m0 + q * 32 + lane;
       const bool row_ok = row < M;
-      const int ea = row_ok ? scale_exponent(amax[row]) : 0;
+      const int ea = row_ok ? scale_exponent(amax[row], bits) : 0;
       for (int pi = 0; pi < npass && ok; ++pi, ++g) {
         const uint32_t buf = g & 1;
         if (!mbar_wait(&tmem_full[buf], (g >> 1) & 1, err)) { ok = false; break; }
         tc_fence_after();
         if (pi < S) {
           const int d = S - 1 - pi;
-          const double scale = scalbn(1.0, -7 * (d + 2));
+          const double scale = scalbn(1.0, -bits * (d + 2));
           const bool first = pi == 0, last = d == 0;
           for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
@@ -331,7 +360,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (col < N) {
                   double r = acc[j] + (double)(int)v[j] * scale;
                   if (last) {
-                    r = scalbn(r, ea + scale_exponent(bmax[col]));
+                    r = scalbn(r, ea + scale_exponent(bmax[col], bits));
                     if (ep.active) r = oz_apply_epilogue(r, ep, row, col);
                   }
                   C[row + col * M] = r;
@@ -417,6 +446,7 @@ struct OzWorkspace {
   CUtensorMap tmA, tmB;
   void *mapA_ptr = nullptr, *mapB_ptr = nullptr;
   uint64_t mapA_rows = 0, mapB_rows = 0, mapA_k = 0, mapB_k = 0;
+  int last_gemms = 0;  // int8 GEMMs per output tile of the last product: S(S+1)/2 digit products + the guard's magnitude product
 };
 
 void ozaki_workspace_destroy(rm_provider* p) {
@@ -448,9 +478,16 @@ cudaError_t grow(rm_provider* p, T** ptr, size_t* have, size_t want) {
 rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double* C, uint64_t m, uint64_t n, uint64_t k,
                        const rm_matmul_epilogue* epd, const void* prow, const void* pcol, void* pdiag, bool ep_active, bool* used, OzGuard* guard) {
   *used = false;
-  const int S = ozaki_default_slices();
-  if (k > 65536 || m == 0 || n == 0 || k == 0) return RM_OK;  // int32 headroom: S*K*64^2 < 2^31
+  if (k > 65536 || m == 0 || n == 0 || k == 0) return RM_OK;  // int32 headroom of the 7-bit split: S*K*64^2 < 2^31
   const uint64_t Mp = (m + BM - 1) / BM * BM, Np = (n + BN - 1) / BN * BN, Kp = (k + BK - 1) / BK * BK;
+  // Digit width. 8-bit digits (|q| <= 128) cover 48 bits with S = 6 slices = 21 int8 GEMMs instead of the 28 of the 7-bit split
+  // (S = 7, 49 bits); an anti-diagonal of up to 6 pairs then needs 6 * K * 128^2 < 2^31, i.e. K <= 21760. Longer products keep
+  // the 7-bit digits. RUNMAT_B200_OZAKI_BITS / RUNMAT_B200_OZAKI_SLICES override.
+  int bits = Kp * 6ull * 16384ull < (1ull << 31) ? 8 : 7;
+  if (const char* e = getenv("RUNMAT_B200_OZAKI_BITS")) { const int b = atoi(e); if (b == 7 || (b == 8 && bits == 8)) bits = b; }
+  int S = bits == 8 ? 6 : 7;
+  if (getenv("RUNMAT_B200_OZAKI_SLICES")) S = ozaki_default_slices();
+  if (bits == 8 && (uint64_t)S * Kp * 16384ull >= (1ull << 31)) { bits = 7; }
   if (Mp * (S + 1) >= (1ull << 31) || Np * (S + 1) >= (1ull << 31)) return RM_OK;
   cudaStream_t st = p->stream;
   if (!p->oz_ws) p->oz_ws = new OzWorkspace();
@@ -479,8 +516,8 @@ rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double*
     w.attrs_set = true;
     w.attr_slices = S;
   }
-  slice_kernel<true><<<dim3((unsigned)(Mp / 32), (unsigned)(Kp / 128)), 256, slice_smem, st>>>(A, m, k, w.amax, w.As, Mp, Kp, S, w.flags);
-  slice_kernel<false><<<dim3((unsigned)(Np / 32), (unsigned)(Kp / 128)), 256, slice_smem, st>>>(B, n, k, w.bmax, w.Bs, Np, Kp, S, w.flags);
+  slice_kernel<true><<<dim3((unsigned)(Mp / 32), (unsigned)(Kp / 128)), 256, slice_smem, st>>>(A, m, k, w.amax, w.As, Mp, Kp, S, bits, w.flags);
+  slice_kernel<false><<<dim3((unsigned)(Np / 32), (unsigned)(Kp / 128)), 256, slice_smem, st>>>(B, n, k, w.bmax, w.Bs, Np, Kp, S, bits, w.flags);
   if (w.mapA_ptr != w.As || w.mapA_rows != (uint64_t)(S + 1) * Mp || w.mapA_k != Kp) {
     RM_TRY(make_map(w.As, (uint64_t)(S + 1) * Mp, Kp, BM, &w.tmA));
     w.mapA_ptr = w.As; w.mapA_rows = (uint64_t)(S + 1) * Mp; w.mapA_k = Kp;
@@ -494,14 +531,16 @@ rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double*
   if (epd)
     ep = OzEpilogue{epd->alpha, epd->beta, (const double*)prow, (const double*)pcol, epd->row_op == RM_SCALE_DIVIDE, epd->col_op == RM_SCALE_DIVIDE,
                     epd->has_clamp_min, epd->has_clamp_max, epd->has_pow, epd->clamp_min, epd->clamp_max, epd->pow_exponent, (double*)pdiag, ep_active ? 1 : 0};
-  // accuracy guard threshold (see the header comment): L_ij >= K * e_S * 2^51, e_S = 2^-7S * (1/2 + S/4)
-  const double gmin = std::ceil((double)k * std::ldexp(0.5 + 0.25 * S, 51 - 7 * S));
+  // accuracy guard threshold (see the header comment), digit base B = 2^bits: flag when K * e_S > 2^-35 * L_ij * (2B)^-2 with
+  // e_S = B^-S * (1/2 + S/4), i.e. L_ij must reach K * (1/2 + S/4) * 2^(37 + 2 bits - bits S)   (bits = 7: 2^(51 - 7S))
+  const double gmin = std::ceil((double)k * std::ldexp(0.5 + 0.25 * S, 37 + 2 * bits - bits * S));
   const long long guard_min = gmin >= 4.0e18 ? (long long)4e18 : std::max<long long>(1, (long long)gmin);
   const int grid = (int)std::min<size_t>(ntiles, (size_t)p->prop.multiProcessorCount);
-  ozaki_gemm_kernel<<<grid, NTHREADS, OZ_SMEM, st>>>(w.tmA, w.tmB, C, m, n, (int)Mp, (int)Np, (int)Kp, S, w.amax, w.bmax, ep, w.flags, w.tileflags, guard_min);
+  ozaki_gemm_kernel<<<grid, NTHREADS, OZ_SMEM, st>>>(w.tmA, w.tmB, C, m, n, (int)Mp, (int)Np, (int)Kp, S, bits, w.amax, w.bmax, ep, w.flags, w.tileflags, guard_min);
   OZ_CUDA(cudaGetLastError());
   count_launch(p, 5);
 #undef OZ_CUDA
+  w.last_gemms = S * (S + 1) / 2 + 1;
   guard->flags = w.flags;
   guard->tileflags = w.tileflags;
   guard->tiles_m = (int)(Mp / BM);
@@ -519,6 +558,7 @@ rm_status ozaki_last_stats(rm_provider* p, int out[4]) {
   RM_CUDA(cudaMemcpyAsync(out, w->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   RM_CUDA(cudaStreamSynchronize(p->stream));
   p->host_syncs.fetch_add(1, std::memory_order_relaxed);
+  out[3] = w->last_gemms;
   return RM_OK;
 }
 

@@ -246,6 +246,7 @@ RM_EXPORT rm_status rm_provider_destroy(rm_provider* p) {
   if (p->reduce_scratch) cudaFreeAsync(p->reduce_scratch, p->stream);
   if (p->l2_flush) cudaFreeAsync(p->l2_flush, p->stream);
   if (p->dev_flags) cudaFree(p->dev_flags);
+  if (p->aux_stream) { cudaStreamSynchronize(p->aux_stream); cudaStreamDestroy(p->aux_stream); p->aux_stream = nullptr; }
   ozaki_workspace_destroy(p);
   cudaStreamSynchronize(p->stream);
   comm_destroy(p);

@@ -162,6 +162,7 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
   // net row permutation of this panel, maintained by warp 0 of CTA 0 (rows touched <= 2*NB)
   __shared__ unsigned long long p_rows[2 * NB], p_cur[2 * NB];
   __shared__ unsigned p_n;
+  __shared__ unsigned long long s_pivots[NB];
   // CLUSTER variant: the per-column exchange (candidates, row c) stays in distributed shared memory and the per-column
   // barrier is a cluster barrier (~0.3 us) instead of a grid-wide cooperative sync (~2.5 us). One cluster = the whole grid.
   __shared__ Candidate s_cand[2];
@@ -255,28 +256,7 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
       const Candidate* win = cand + (size_t)buf * nblk + s_pblock;
       for (int cc = tid; cc < jb; cc += SLAB_ROWS) { s_row[cc] = __ldcg(&win->row[cc]); s_rowc[cc] = __ldcg(&rowc[buf * NB + cc]); }
     }
-    // CTA 0 / warp 0: fold swap (j0+c <-> j0+prow) into the net permutation (32-lane parallel lookup of the two rows)
-    if (blockIdx.x == 0 && warp == 0 && prow != (uint64_t)c) {
-      const unsigned long long want[2] = {j0 + (uint64_t)c, j0 + prow};
-      unsigned slot[2];
-      for (int q = 0; q < 2; ++q) {
-        unsigned found = 0xffffffffu;
-        const unsigned cnt = p_n;
-        for (unsigned base = 0; base < cnt; base += 32) {
-          const unsigned k = base + lane;
-          const unsigned hit = __ballot_sync(0xffffffffu, k < cnt && p_rows[k] == want[q]);
-          if (hit) { found = base + __ffs(hit) - 1; break; }
-        }
-        if (found == 0xffffffffu) {
-          found = cnt;
-          if (lane == 0) { p_rows[cnt] = want[q]; p_cur[cnt] = want[q]; p_n = cnt + 1; }
-        }
-        __syncwarp();
-        slot[q] = found;
-      }
-      if (lane == 0) { const unsigned long long t = p_cur[slot[0]]; p_cur[slot[0]] = p_cur[slot[1]]; p_cur[slot[1]] = t; }
-      __syncwarp();
-    }
+    if (blockIdx.x == 0 && tid == 0) s_pivots[c] = prow;  // the net row permutation is composed after the column loop (off the per-column critical path)
     __syncthreads();
     if (prow != (uint64_t)c) {
       // row c (always in CTA 0) receives the pivot row; the pivot's home CTA receives the old row c
@@ -291,13 +271,41 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
       const double l = slab[tid][c] / pivot;
       slab[tid][c] = l;
 #pragma unroll 8
-      for (int cc = c + 1; cc < jb; ++cc) slab[tid][cc] -= l * s_row[cc];
+      for (int cc = c + 1; cc < jb; ++cc) slab[tid][cc] = fma(-l, s_row[cc], slab[tid][cc]);  // explicit DFMA (the library is built -fmad=false)
     }
     __syncthreads();
   }
   if (valid) for (int cc = 0; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = slab[tid][cc];
   if constexpr (CLUSTER) cg::this_cluster().sync();  // nobody exits while a peer may still read its shared memory
   if (blockIdx.x == 0) {
+    __syncthreads();
+    // CTA 0 / warp 0: fold the jb swaps (j0+c <-> j0+pivot[c]) into the net permutation (32-lane parallel lookup of the two rows).
+    // r17 ncu: doing this inside the column loop made CTA 0 the last to arrive at every cluster barrier.
+    if (warp == 0) {
+      for (int c = 0; c < jb; ++c) {
+        const uint64_t prow = s_pivots[c];
+        if (prow == (uint64_t)c) continue;
+        const unsigned long long want[2] = {j0 + (uint64_t)c, j0 + prow};
+        unsigned slot[2];
+        for (int q = 0; q < 2; ++q) {
+          unsigned found = 0xffffffffu;
+          const unsigned cnt = p_n;
+          for (unsigned base = 0; base < cnt; base += 32) {
+            const unsigned k = base + lane;
+            const unsigned hit = __ballot_sync(0xffffffffu, k < cnt && p_rows[k] == want[q]);
+            if (hit) { found = base + __ffs(hit) - 1; break; }
+          }
+          if (found == 0xffffffffu) {
+            found = cnt;
+            if (lane == 0) { p_rows[cnt] = want[q]; p_cur[cnt] = want[q]; p_n = cnt + 1; }
+          }
+          __syncwarp();
+          slot[q] = found;
+        }
+        if (lane == 0) { const unsigned long long t = p_cur[slot[0]]; p_cur[slot[0]] = p_cur[slot[1]]; p_cur[slot[1]] = t; }
+        __syncwarp();
+      }
+    }
     __syncthreads();
     if (tid == 0) {
       uint32_t k2 = 0;
@@ -367,6 +375,11 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
     sT[r][c] = (r < jb && c < jb) ? T[r + (uint64_t)c * ldt] : (r == c ? 1.0 : 0.0);  // identity padding: rows >= jb never change anything
   }
   __syncthreads();
+  // reciprocals of the diagonal, computed once and in parallel: a division inside the 64-step dependent chain cost more than the
+  // rest of a step (r17: the upper solves ran 25 us, the unit-diagonal ones 10 us)
+  __shared__ double s_rdiag[NB];
+  if (MODE != TRSM_LOWER_UNIT && threadIdx.x < NB) s_rdiag[threadIdx.x] = 1.0 / sT[threadIdx.x][threadIdx.x];
+  __syncthreads();
   constexpr int CW = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t c0 = (uint64_t)blockIdx.x * 32 + (uint64_t)warp * CW;
@@ -381,11 +394,11 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
       const double l0 = sT[lane][i], l1 = sT[lane + 32][i];
-      const double d = MODE == TRSM_LOWER ? sT[i][i] : 1.0;
+      const double d = MODE == TRSM_LOWER ? s_rdiag[i] : 1.0;
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
         double xi = __shfl_sync(0xffffffffu, b0[c], i);
-        if (MODE == TRSM_LOWER) { xi = xi / d; if (lane == i) b0[c] = xi; }
+        if (MODE == TRSM_LOWER) { xi = xi * d; if (lane == i) b0[c] = xi; }
         if (lane > i) b0[c] -= l0 * xi;
         b1[c] -= l1 * xi;
       }
@@ -393,11 +406,11 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
 #pragma unroll 4
     for (int i = 32; i < NB; ++i) {
       const double l1 = sT[lane + 32][i];
-      const double d = MODE == TRSM_LOWER ? sT[i][i] : 1.0;
+      const double d = MODE == TRSM_LOWER ? s_rdiag[i] : 1.0;
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
         double xi = __shfl_sync(0xffffffffu, b1[c], i - 32);
-        if (MODE == TRSM_LOWER) { xi = xi / d; if (lane == i - 32) b1[c] = xi; }
+        if (MODE == TRSM_LOWER) { xi = xi * d; if (lane == i - 32) b1[c] = xi; }
         if (lane + 32 > i) b1[c] -= l1 * xi;
       }
     }
@@ -405,11 +418,11 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
 #pragma unroll 4
     for (int i = NB - 1; i >= 32; --i) {
       const double u0 = sT[lane][i], u1 = sT[lane + 32][i];
-      const double d = sT[i][i];
+      const double d = s_rdiag[i];
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
         double xi = __shfl_sync(0xffffffffu, b1[c], i - 32);
-        xi = xi / d;
+        xi = xi * d;
         if (lane == i - 32) b1[c] = xi;
         if (lane + 32 < i) b1[c] -= u1 * xi;
         b0[c] -= u0 * xi;
@@ -418,11 +431,11 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
 #pragma unroll 4
     for (int i = 31; i >= 0; --i) {
       const double u0 = sT[lane][i];
-      const double d = sT[i][i];
+      const double d = s_rdiag[i];
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
         double xi = __shfl_sync(0xffffffffu, b0[c], i);
-        xi = xi / d;
+        xi = xi * d;
         if (lane == i) b0[c] = xi;
         if (lane < i) b0[c] -= u0 * xi;
       }
@@ -660,7 +673,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   const unsigned slab_max_grid = (unsigned)std::max(0, slab_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
   SV_CUDA(cudaMallocAsync((void**)&rowbuf, 2 * NB * 8, st));
   SV_CUDA(cudaMallocAsync((void**)&cand, (size_t)2 * std::max(slab_max_grid, 1u) * sizeof(Candidate), st));
-  SV_CUDA(cudaMallocAsync((void**)&moves, sizeof(RowMoves), st));
+  SV_CUDA(cudaMallocAsync((void**)&moves, sizeof(RowMoves) * ((n + NB - 1) / NB), st));  // one net permutation per panel (applied by both streams)
   // Augmented system [A | B] in one column-major buffer (ld = n): the row interchanges, the U12 solves and the trailing updates
   // of the factorisation then carry the right-hand sides along, i.e. the forward substitution L y = P b costs no launches of its
   // own (r06: 64 triangular solves + 63 skinny GEMMs = 3.3 ms of the 32 ms at n = 4096).
@@ -683,62 +696,113 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   absmax_kernel<<<(unsigned)std::min<uint64_t>((n * n + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 8), 256, 0, st>>>(LU, n * n, amax, info + 1);
   count_launch(p);
 
-  // Two-level blocking: 64-wide panels are factored and applied only inside the current NBO-wide outer block; the rest of
-  // the matrix sees ONE rank-NBO update per outer block (a k=64 DMMA update of the whole trailing matrix per panel ran at
-  // ~7 TFLOP/s and re-read/wrote the trailing matrix 4x as often).
+  // Two-level blocking with look-ahead on two streams.
+  //  * 64-wide panels are factored and applied only inside the current NBO-wide outer block (stream A = the provider stream: the
+  //    latency-bound critical path: cluster panel kernel, in-block row interchanges, in-block triangular solve + k=64 update);
+  //  * everything to the right of the block -- row interchanges, U12 <- L11^-1 A12 (the right-hand sides ride along as extra
+  //    columns), the rank-NBO trailing update -- runs on stream B. B updates the NEXT block's columns first and signals A, so the
+  //    panels of block K+1 overlap the bulk of block K's trailing update (r06: panels 16 ms, everything else 16 ms, serialised).
+  //  * Row interchanges are never applied to the columns LEFT of the current block: those hold finished L factors that nothing
+  //    reads again (the forward substitution is folded into the factorisation, the back substitution only needs U), and leaving
+  //    them alone is what makes A(K+1) and B(K) touch disjoint memory.
   uint64_t NBO = 256;
   if (const char* e = getenv("RUNMAT_B200_LU_OUTER")) { const long v = atol(e); if (v >= NB && v % NB == 0) NBO = (uint64_t)v; }
-  for (uint64_t j0 = 0; j0 < n; j0 += NB) {
-    int jb = (int)std::min<uint64_t>(NB, n - j0);
-    const uint64_t m = n - j0;
-    const uint64_t J0 = (j0 / NBO) * NBO, Jend = std::min<uint64_t>(J0 + NBO, n);
-    unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, max_grid);
-    grid = std::max(grid, 1u);
-    uint64_t lda = n, nn = n, jj = j0;
-    const unsigned slab_grid = (unsigned)((m + SLAB_ROWS - 1) / SLAB_ROWS);
-    unsigned cl = 1;
-    while (cl < slab_grid) cl <<= 1;
-    if (cl <= cluster_max && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
-      // whole panel inside one thread-block cluster (grid rounded up to a power of two; surplus CTAs own no rows)
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(cl); cfg.blockDim = dim3(SLAB_ROWS); cfg.dynamicSmemBytes = SLAB_SMEM; cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      SV_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_smem_kernel<true>, LU, lda, nn, jj, jb, ipiv, cand, rowbuf, info, pivmm, moves));
-    } else if (slab_grid <= slab_max_grid && slab_grid <= max_grid && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
-      void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &cand, &rowbuf, &info, &pivmm, &moves};
-      SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_smem_kernel<false>, dim3(slab_grid), dim3(SLAB_ROWS), args, SLAB_SMEM, st));
-    } else {
-      void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
-      SV_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st));
-      perm_build_kernel<<<1, 32, 0, st>>>(ipiv, j0, jb, moves);
+  const bool lookahead = !getenv("RUNMAT_B200_LU_NO_LOOKAHEAD");
+  if (lookahead && !p->aux_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    SV_CUDA(cudaStreamCreateWithPriority(&p->aux_stream, cudaStreamNonBlocking, lo));  // lowest priority: panel CTAs go first
+  }
+  cudaStream_t sb = lookahead ? p->aux_stream : st;
+  const uint64_t nblocks = (n + NBO - 1) / NBO;
+  std::vector<cudaEvent_t> evE(nblocks, nullptr), evF(nblocks + 1, nullptr);
+  auto destroy_events = [&] { for (auto e : evE) if (e) cudaEventDestroy(e); for (auto e : evF) if (e) cudaEventDestroy(e); };
+  if (lookahead) {
+    for (auto& e : evE) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : evF) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(evF[0], st);  // B starts after the set-up copies on A
+    cudaStreamWaitEvent(sb, evF[0], 0);
+  }
+  rm_status loop_status = RM_OK;
+  cudaError_t loop_err = cudaSuccess;
+  for (uint64_t K = 0; K < nblocks && loop_status == RM_OK && loop_err == cudaSuccess; ++K) {
+    const uint64_t J0 = K * NBO, Jend = std::min<uint64_t>(J0 + NBO, n);
+    if (lookahead && K > 0) cudaStreamWaitEvent(st, evF[K], 0);  // block K's columns carry every earlier update
+    for (uint64_t j0 = J0; j0 < Jend && loop_status == RM_OK && loop_err == cudaSuccess; j0 += NB) {
+      int jb = (int)std::min<uint64_t>(NB, n - j0);
+      const uint64_t m = n - j0;
+      RowMoves* mv = moves + j0 / NB;
+      unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, max_grid);
+      grid = std::max(grid, 1u);
+      uint64_t lda = n, nn = n, jj = j0;
+      const unsigned slab_grid = (unsigned)((m + SLAB_ROWS - 1) / SLAB_ROWS);
+      unsigned cl = 1;
+      while (cl < slab_grid) cl <<= 1;
+      if (cl <= cluster_max && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+        // whole panel inside one thread-block cluster (grid rounded up to a power of two; surplus CTAs own no rows)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cl); cfg.blockDim = dim3(SLAB_ROWS); cfg.dynamicSmemBytes = SLAB_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        loop_err = cudaLaunchKernelEx(&cfg, lu_panel_smem_kernel<true>, LU, lda, nn, jj, jb, ipiv, cand, rowbuf, info, pivmm, mv);
+      } else if (slab_grid <= slab_max_grid && slab_grid <= max_grid && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+        void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &cand, &rowbuf, &info, &pivmm, &mv};
+        loop_err = cudaLaunchCooperativeKernel((void*)lu_panel_smem_kernel<false>, dim3(slab_grid), dim3(SLAB_ROWS), args, SLAB_SMEM, st);
+      } else {
+        void* args[] = {&LU, &lda, &nn, &jj, &jb, &ipiv, &scratch, &info, &pivmm};
+        loop_err = cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(grid), dim3(256), args, 0, st);
+        perm_build_kernel<<<1, 32, 0, st>>>(ipiv, j0, jb, mv);
+      }
+      if (loop_err != cudaSuccess) break;
+      // row interchanges on the other columns of this outer block
+      const uint64_t inblk = Jend - J0 - jb;
+      if (inblk > 0) perm_apply_kernel<<<(unsigned)std::min<uint64_t>(inblk, 4096), 2 * NB, 0, st>>>(LU + J0 * n, n, inblk, j0 - J0, (uint64_t)jb, mv);
+      count_launch(p, 2);
+      const uint64_t rest = n - j0 - jb;
+      const uint64_t rest_in = Jend - (j0 + jb);  // columns of the outer block still to factor
+      if (rest_in > 0) {
+        // inside the outer block: A12 <- L11^-1 A12 ; A22 -= A21 * A12
+        trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((rest_in + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest_in);
+        count_launch(p);
+        loop_status = dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, LU + j0 + (j0 + jb) * n, n, LU + (j0 + jb) + (j0 + jb) * n, n, rest, rest_in, (uint64_t)jb, st);
+      }
     }
-    // row interchanges outside the panel (LU columns left and right of it) and on the right-hand sides
-    const uint64_t rest = n - j0 - jb;
-    perm_apply_kernel<<<(unsigned)std::min<uint64_t>(ntot - jb, 4096), 2 * NB, 0, st>>>(LU, n, ntot - jb, j0, (uint64_t)jb, moves);
-    count_launch(p, 2);
-    const uint64_t rest_in = Jend - (j0 + jb);  // columns of the outer block still to factor
-    if (rest_in > 0) {
-      // inside the outer block: A12 <- L11^-1 A12 ; A22 -= A21 * A12
-      trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((rest_in + 31) / 32), 256, TRSM_SMEM, st>>>(LU + j0 + j0 * n, n, jb, LU + j0 + (j0 + jb) * n, n, rest_in);
-      count_launch(p);
-      SV_TRY(dgemm_sub_strided(p, LU + (j0 + jb) + j0 * n, n, LU + j0 + (j0 + jb) * n, n, LU + (j0 + jb) + (j0 + jb) * n, n, rest, rest_in, (uint64_t)jb));
-    } else {
-      // outer block [J0, Jend) is factored: U12 <- L11^-1 A12 by 64-row steps (A12 includes the right-hand-side columns), then one
-      // rank-(Jend-J0) update of the rows below
-      const uint64_t right = ntot - Jend;
-      for (uint64_t i0 = J0; i0 < Jend; i0 += NB) {
+    if (loop_status != RM_OK || loop_err != cudaSuccess) break;
+    // ---- right of the block (stream B): interchanges, U12, trailing update ----
+    if (lookahead) { cudaEventRecord(evE[K], st); cudaStreamWaitEvent(sb, evE[K], 0); }
+    const uint64_t right = ntot - Jend;
+    if (right > 0) {
+      for (uint64_t j0 = J0; j0 < Jend; j0 += NB)
+        perm_apply_kernel<<<(unsigned)std::min<uint64_t>(right, 4096), 2 * NB, 0, sb>>>(LU + Jend * n, n, right, right, 0, moves + j0 / NB);
+      count_launch(p, (Jend - J0 + NB - 1) / NB);
+      for (uint64_t i0 = J0; i0 < Jend && loop_status == RM_OK; i0 += NB) {
         const int ib = (int)std::min<uint64_t>(NB, Jend - i0);
-        trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, st>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
+        trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, sb>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
         count_launch(p);
         const uint64_t below = Jend - (i0 + ib);
-        if (below > 0) SV_TRY(dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, LU + i0 + Jend * n, n, LU + (i0 + ib) + Jend * n, n, below, right, (uint64_t)ib));
+        if (below > 0) loop_status = dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, LU + i0 + Jend * n, n, LU + (i0 + ib) + Jend * n, n, below, right, (uint64_t)ib, sb);
       }
-      if (n > Jend) SV_TRY(dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + Jend * n, n, LU + Jend + Jend * n, n, n - Jend, right, Jend - J0));
+      if (n > Jend && loop_status == RM_OK) {
+        // the next block's columns first (then A may start its panels), the rest afterwards
+        const uint64_t next_cols = std::min<uint64_t>(NBO, n - Jend);
+        loop_status = dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + Jend * n, n, LU + Jend + Jend * n, n, n - Jend, next_cols, Jend - J0, sb);
+        if (lookahead) cudaEventRecord(evF[K + 1], sb);
+        if (right > next_cols && loop_status == RM_OK)
+          loop_status = dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + (Jend + next_cols) * n, n, LU + Jend + (Jend + next_cols) * n, n, n - Jend, right - next_cols,
+                                          Jend - J0, sb);
+      }
     }
   }
+  if (lookahead) {
+    // A continues (conditioning gate, back substitution) once B has drained
+    cudaEventRecord(evF[nblocks], sb);
+    cudaStreamWaitEvent(st, evF[nblocks], 0);
+    destroy_events();  // destruction is deferred by the runtime until the recorded work has completed
+  }
+  if (loop_err != cudaSuccess) { cudaGetLastError(); cleanup(true); return fail(RM_ERROR, "mldivide: panel launch failed: %s", cudaGetErrorString(loop_err)); }
+  SV_TRY(loop_status);
   SV_CUDA(cudaGetLastError());
 
   // conditioning / singularity gate (one small D2H): fall back to the host SVD path when LU is not trustworthy

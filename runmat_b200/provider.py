@@ -501,7 +501,7 @@ class B200Provider:
         """Device flags of the last tcgen05 product (waits for the stream): test/debug hook."""
         out = (C.c_int32 * 4)()
         _check(lib.rm_debug_ozaki_stats(self._p, out))
-        return {"nonfinite": int(out[0]), "pipeline_error": int(out[1]), "fp64_tiles": int(out[2])}
+        return {"nonfinite": int(out[0]), "pipeline_error": int(out[1]), "fp64_tiles": int(out[2]), "int8_gemms": int(out[3])}
 
     def set_launch_overlap(self, enabled: bool) -> None:
         """Programmatic dependent launch of the generated fused kernels (default on); off = plain launches (isolated timing)."""

@@ -737,6 +737,37 @@ def test_matmul_tcgen05_engine_details(prov, orc):
         prov.set_matmul_engine(0)
 
 
+def test_matmul_tcgen05_digit_widths(prov, orc, monkeypatch):
+    """The tcgen05 engine splits into 8-bit digits (6 slices, 21 + 1 int8 GEMMs) up to K = 21760 and into 7-bit digits (7 slices,
+    28 + 1) beyond or on request: both must meet the element-wise bar, agree on exact integer data, and the 8-bit carry fix-up
+    (digit +128 -> -128 with a carry) must hold on values that sit exactly on digit boundaries."""
+    rng = np.random.default_rng(88)
+    prov.set_matmul_engine(2)
+    try:
+        a, b = rng.uniform(-1, 1, (260, 640)), rng.uniform(-1, 1, (640, 300))
+        # entries exactly half-way between 8-bit digits at several depths (scaled by the row maximum 0.4990234375 < 0.49 * ... no carry out)
+        a[0, :] = 0.25
+        a[0, :8] = [0.25 + 2.0 ** -9, 0.25 + 2.0 ** -17, 0.25 - 2.0 ** -9, 0.498046875, 127.5 / 65536, -127.5 / 65536, 0.499, -0.499]
+        want = orc.matmul(a, b)
+        for bits, gemms in (("8", 22), ("7", 29)):
+            monkeypatch.setenv("RUNMAT_B200_OZAKI_BITS", bits)
+            got = prov.download(prov.matmul(prov.upload(a), prov.upload(b)))
+            matmul_close(got, a, b, want)
+            st = prov.ozaki_stats()
+            assert st["int8_gemms"] == gemms and st["pipeline_error"] == 0 and st["fp64_tiles"] == 0, (bits, st)
+            ai = rng.integers(-2000, 2000, (300, 200)).astype(np.float64)
+            bi = rng.integers(-2000, 2000, (200, 260)).astype(np.float64)
+            assert np.array_equal(prov.download(prov.matmul(prov.upload(ai), prov.upload(bi))), ai @ bi), bits
+        monkeypatch.delenv("RUNMAT_B200_OZAKI_BITS")
+        # a long inner dimension keeps the 7-bit split (int32 headroom of an anti-diagonal)
+        a, b = rng.uniform(-1, 1, (130, 22000)), rng.uniform(-1, 1, (22000, 260))
+        got = prov.download(prov.matmul(prov.upload(a), prov.upload(b)))
+        matmul_close(got, a, b, orc.matmul(a, b))
+        assert prov.ozaki_stats()["int8_gemms"] == 29
+    finally:
+        prov.set_matmul_engine(0)
+
+
 def _adversarial_pairs(rng, m, k, n):
     """Inputs whose entries hide terms far below the row / column maximum: the norm-wise Ozaki split
     alone would drop them; the device-side accuracy guard must hand those tiles to the FP64 kernel."""
@@ -779,7 +810,8 @@ def test_matmul_tcgen05_accuracy_guard(prov, orc):
             a, b = gen((300, 520)), gen((520, 640))
             got = prov.download(prov.matmul(prov.upload(a), prov.upload(b)))
             matmul_close(got, a, b, orc.matmul(a, b))
-            assert prov.ozaki_stats() == {"nonfinite": 0, "pipeline_error": 0, "fp64_tiles": 0}
+            st = prov.ozaki_stats()
+            assert (st["nonfinite"], st["pipeline_error"], st["fp64_tiles"]) == (0, 0, 0), st
         # one weak row only: the rest of the product stays on the tensor cores
         a, b = rng.uniform(-1, 1, (700, 520)), rng.uniform(-1, 1, (520, 900))
         a[5, :] *= 10.0 ** rng.uniform(-25, 0, 520)
