@@ -328,7 +328,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    from runmat_b200 import B200Provider, fusion_text as ft
+    from runmat_b200 import B200Provider
+    import fusion_text as ft
     from runmat_b200.provider import pinned_empty
 
     dist = None
@@ -688,7 +689,8 @@ MC_FP64_INSTR_PER_PATH_STEP = 48.5
 
 
 def image_batch_leg(p, rank, world, local_rank, dist, torch, peak_hbm):
-    from runmat_b200 import B200Provider, ImageNormalizeDescriptor, fusion_text as ft
+    from runmat_b200 import B200Provider, ImageNormalizeDescriptor
+    import fusion_text as ft
     from runmat_b200.sharding import batch_slices_for_rank, lcg_image_shard
 
     Bt, H, W = 64, 2160, 3840

@@ -391,6 +391,27 @@ rm_status rm_conv2d(rm_provider* p, const rm_handle* signal, const rm_handle* ke
 
 /* ---- a15: telemetry / tuning hints (lib.rs:3010-3060) -------------------------------------------- */
 rm_status rm_telemetry_snapshot(rm_provider* p, rm_telemetry* out);
+/* ProviderTelemetry::kernel_launches (lib.rs:1353, KernelLaunchTelemetry lib.rs:1369-1375): bounded log of the most recent
+ * launches, newest last, at most RM_MAX_KERNEL_LAUNCH_EVENTS = 64 like the reference (accelerate/src/telemetry.rs:12, 219-239).
+ * Kernel names and shape keys follow the wgpu provider ("fused_elementwise": len/inputs/rank, "fused_reduction":
+ * reduce_len/slices/rank, "matmul": m/n/k, "linsolve_triangular", ...); `tuning` holds this backend's choices. */
+#define RM_MAX_KERNEL_LAUNCH_EVENTS 64
+#define RM_LAUNCH_ATTRS 4
+typedef struct rm_kernel_attr { char key[16]; uint64_t value; } rm_kernel_attr;
+typedef struct rm_kernel_launch_event {
+  char kernel[32];
+  rm_precision precision;
+  uint32_t n_shape, n_tuning;
+  rm_kernel_attr shape[RM_LAUNCH_ATTRS];
+  rm_kernel_attr tuning[RM_LAUNCH_ATTRS];
+} rm_kernel_launch_event;
+/* copies up to `cap` events (oldest first) into `out`; *count = number written */
+rm_status rm_kernel_launch_log(rm_provider* p, rm_kernel_launch_event* out, uint32_t cap, uint32_t* count);
+/* spawn_handle_concurrency (lib.rs:1400-1402, SpawnHandleConcurrency lib.rs:825-834): handles are ids into a mutex-guarded
+ * table and all work is stream-ordered, so tasks may share and mutate handles like the in-process provider
+ * (simple_provider.rs:2605): returns RM_SPAWN_SYNCHRONIZED_MUTATION. */
+typedef enum rm_spawn_handle_concurrency { RM_SPAWN_IMMUTABLE_SHARE = 0, RM_SPAWN_COPY_ON_WRITE = 1, RM_SPAWN_SYNCHRONIZED_MUTATION = 2, RM_SPAWN_REJECT = 3 } rm_spawn_handle_concurrency;
+rm_spawn_handle_concurrency rm_spawn_handle_concurrency_policy(rm_provider* p);
 rm_status rm_reset_telemetry(rm_provider* p);
 
 /* ---- measurement helpers (extension; used by bench.py so timing is taken with CUDA events on the

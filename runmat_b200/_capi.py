@@ -114,6 +114,17 @@ lib.rm_host_sync_count.restype = C.c_uint64
 lib.rm_two_pass_threshold.restype = C.c_uint64
 lib.rm_default_reduction_workgroup_size.restype = C.c_uint32
 
+class KernelAttr(C.Structure):
+    _fields_ = [("key", C.c_char * 16), ("value", C.c_uint64)]
+
+
+class KernelLaunchEvent(C.Structure):
+    """rm_kernel_launch_event (KernelLaunchTelemetry, accelerate-api/src/lib.rs:1369-1375)."""
+
+    _fields_ = [("kernel", C.c_char * 32), ("precision", C.c_int), ("n_shape", C.c_uint32), ("n_tuning", C.c_uint32),
+                ("shape", KernelAttr * 4), ("tuning", KernelAttr * 4)]
+
+
 # Every symbol include/rm_accel.h declares (tests/test_abi.py checks the library exports all of them).
 DECLARED_SYMBOLS = None
 

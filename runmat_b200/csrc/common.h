@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -134,6 +135,11 @@ struct rm_provider {
   std::mutex comm_mu;   // one exchange (publish + combine enqueue) at a time
   void* p2p = nullptr;  // comm.cu: peer-memory slot exchange state
 
+  // bounded launch log (ProviderTelemetry::kernel_launches): ring of the last RM_MAX_KERNEL_LAUNCH_EVENTS events
+  std::mutex log_mu;
+  rm_kernel_launch_event launch_log[RM_MAX_KERNEL_LAUNCH_EVENTS];
+  uint64_t launch_log_n = 0;  // events recorded so far (ring index = n % cap)
+
   rm::FusedCache* fused = nullptr;
 
   size_t elem_size() const { return precision == RM_F64 ? 8 : 4; }
@@ -181,6 +187,18 @@ void p2p_enqueue_combine_locked(rm_provider* p, uint64_t step, void* dst);
 rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* elems);
 rm_status ensure_scratch(rm_provider* p, size_t bytes);
 inline void count_launch(rm_provider* p, uint64_t n = 1) { p->kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+struct LaunchAttr { const char* key; uint64_t value; };
+// record_kernel_launch (accelerate/src/telemetry.rs:219-239): newest last, oldest dropped beyond the cap
+inline void record_launch(rm_provider* p, const char* kernel, std::initializer_list<LaunchAttr> shape, std::initializer_list<LaunchAttr> tuning) {
+  std::lock_guard<std::mutex> lk(p->log_mu);
+  rm_kernel_launch_event& e = p->launch_log[p->launch_log_n % RM_MAX_KERNEL_LAUNCH_EVENTS];
+  memset(&e, 0, sizeof e);
+  snprintf(e.kernel, sizeof e.kernel, "%s", kernel);
+  e.precision = p->precision;
+  for (const LaunchAttr& a : shape) if (e.n_shape < RM_LAUNCH_ATTRS) { snprintf(e.shape[e.n_shape].key, 16, "%s", a.key); e.shape[e.n_shape++].value = a.value; }
+  for (const LaunchAttr& a : tuning) if (e.n_tuning < RM_LAUNCH_ATTRS) { snprintf(e.tuning[e.n_tuning].key, 16, "%s", a.key); e.tuning[e.n_tuning++].value = a.value; }
+  ++p->launch_log_n;
+}
 
 // normalize_scalar_shape-style helper: MATLAB values are rank >= 2.
 inline void make_shape2(uint64_t r, uint64_t c, uint64_t* shape) { shape[0] = r; shape[1] = c; }

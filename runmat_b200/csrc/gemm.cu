@@ -258,7 +258,7 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
   RM_TRY(resolve(p, a, &pa, nullptr));
   RM_TRY(resolve(p, b, &pb, nullptr));
   void *prow = nullptr, *pcol = nullptr, *pdiag = nullptr;
-  bool active = false;
+  bool active = false, used_tcgen05 = false;
   if (epd) {
     active = !(epd->alpha == 1.0 && epd->beta == 0.0 && !epd->row_scale && !epd->col_scale && !epd->has_clamp_min &&
                !epd->has_clamp_max && !epd->has_pow && !epd->diag_output);  // MatmulEpilogue::is_noop (lib.rs:3540-3549)
@@ -290,6 +290,7 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
       st = ozaki_matmul(p, (const double*)pa, (const double*)pb, (double*)pc, m, n, k, epd, prow, pcol, pdiag, active, &used, &guard);
       if (st != RM_OK) { std::string msg = last_error(); oz_lock.unlock(); rm_free(p, out); set_error("%s", msg.c_str()); return st; }
       if (!used) { guard = OzGuard{}; oz_lock.unlock(); }
+      used_tcgen05 = used;
     }
     Epilogue ep{};
     ep.alpha = 1.0;
@@ -319,7 +320,11 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { st = fail(RM_ERROR, "matmul launch failed: %s", cudaGetErrorString(e)); rm_free(p, out); }
-  else count_launch(p);
+  else {
+    count_launch(p);
+    // shape keys as record_matmul_kernel_launch logs them (backend/wgpu/provider/helpers.rs:36-50); tuning: this backend's engine
+    record_launch(p, "matmul", {{"m", m}, {"n", n}, {"k", k}}, {{"tcgen05", used_tcgen05 ? 1ull : 0ull}, {"epilogue", epd ? 1ull : 0ull}});
+  }
   return st;
 }
 

@@ -271,7 +271,13 @@ RM_EXPORT rm_status rm_fused_elementwise_multi(rm_provider* p, const char* shade
   std::string key;
   RM_TRY(parsed(g_ew_cache, shader, parse_elementwise_wgsl, &prog, &key));
   RM_REQUIRE(prog->n_outputs == num_outputs, RM_INVALID_ARG, "fused_elementwise: shader writes %u outputs, caller expects %u", prog->n_outputs, num_outputs);
-  return run_elementwise_program(p, *prog, "wgsl:" + key, inputs, n_inputs, output_shape, rank, len, outs);
+  rm_status st = run_elementwise_program(p, *prog, "wgsl:" + key, inputs, n_inputs, output_shape, rank, len, outs);
+  if (st == RM_OK) {
+    // names / shape keys as the wgpu provider logs them (backend/wgpu/provider/ops/telemetry.rs:26-61)
+    if (num_outputs == 1) record_launch(p, "fused_elementwise", {{"len", len}, {"inputs", n_inputs}, {"rank", rank}}, {{"block", 256}, {"vec_bytes", 32}});
+    else record_launch(p, "fused_elementwise_multi", {{"len", len}, {"inputs", n_inputs}, {"rank", rank}, {"num_outputs", num_outputs}}, {{"block", 256}, {"vec_bytes", 32}});
+  }
+  return st;
 }
 
 RM_EXPORT rm_status rm_fused_elementwise(rm_provider* p, const char* shader, const rm_handle* inputs, uint32_t n_inputs,
@@ -300,8 +306,11 @@ RM_EXPORT rm_status rm_fused_reduction(rm_provider* p, const char* shader, const
   if (flavor == RM_FLAVOR_MEAN) { use_div = reduce_len ? 1 : 0; factor = reduce_len ? (double)reduce_len : 1.0; }
   else if (flavor == RM_FLAVOR_CUSTOM) factor = custom_scale;
   const RedLayout layout = prog.axis == 0 ? RedLayout::Contig : RedLayout::Strided;
-  return run_reduction_program(p, prog, "wgsl:" + key, RedOp::Sum, layout, inputs, n_inputs, output_shape, rank,
-                               reduce_len, num_slices, /*inner=*/num_slices, use_div, factor, out);
+  rm_status st = run_reduction_program(p, prog, "wgsl:" + key, RedOp::Sum, layout, inputs, n_inputs, output_shape, rank,
+                                       reduce_len, num_slices, /*inner=*/num_slices, use_div, factor, out);
+  if (st == RM_OK)  // backend/wgpu/provider/ops/telemetry.rs:126-146
+    record_launch(p, "fused_reduction", {{"reduce_len", reduce_len}, {"slices", num_slices}, {"rank", rank}}, {{"block", 256}, {"flavor", (uint64_t)flavor}, {"axis", (uint64_t)prog.axis}});
+  return st;
 }
 
 // Sharded form: every rank reduces its own inputs to ONE scalar and the scalars are summed over the ranks of the

@@ -791,11 +791,22 @@ RM_EXPORT rm_status rm_telemetry_snapshot(rm_provider* p, rm_telemetry* out) {
   out->kernel_launches = p->kernel_launches.load();
   return RM_OK;
 }
+RM_EXPORT rm_status rm_kernel_launch_log(rm_provider* p, rm_kernel_launch_event* out, uint32_t cap, uint32_t* count) {
+  RM_REQUIRE(p && count && (out || cap == 0), RM_INVALID_ARG, "kernel_launch_log: bad arguments");
+  std::lock_guard<std::mutex> lk(p->log_mu);
+  const uint64_t have = std::min<uint64_t>(p->launch_log_n, RM_MAX_KERNEL_LAUNCH_EVENTS);
+  const uint64_t n = std::min<uint64_t>(have, cap);
+  for (uint64_t i = 0; i < n; ++i) out[i] = p->launch_log[(p->launch_log_n - n + i) % RM_MAX_KERNEL_LAUNCH_EVENTS];  // the newest n, oldest first
+  *count = (uint32_t)n;
+  return RM_OK;
+}
+RM_EXPORT rm_spawn_handle_concurrency rm_spawn_handle_concurrency_policy(rm_provider*) { return RM_SPAWN_SYNCHRONIZED_MUTATION; }
 RM_EXPORT rm_status rm_reset_telemetry(rm_provider* p) {
   RM_REQUIRE(p, RM_INVALID_ARG, "null provider");
   p->t_fused_elementwise.reset(); p->t_fused_reduction.reset(); p->t_matmul.reset();
   p->t_linsolve.reset(); p->t_mldivide.reset(); p->t_mrdivide.reset();
   p->upload_bytes = 0; p->download_bytes = 0; p->cache_hits = 0; p->cache_misses = 0; p->kernel_launches = 0;
+  { std::lock_guard<std::mutex> lk(p->log_mu); p->launch_log_n = 0; }
   return RM_OK;
 }
 RM_EXPORT void rm_fused_cache_counters(rm_provider* p, uint64_t* hits, uint64_t* misses) {

@@ -836,6 +836,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   cleanup(false);
 #undef SV_CUDA
 #undef SV_TRY
+  record_launch(p, "mldivide_lu", {{"n", n}, {"nrhs", nrhs}}, {{"panel", NB}, {"outer", NBO}, {"lookahead", lookahead ? 1ull : 0ull}});
   return RM_OK;
 }
 

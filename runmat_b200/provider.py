@@ -503,6 +503,22 @@ class B200Provider:
         _check(lib.rm_debug_ozaki_stats(self._p, out))
         return {"nonfinite": int(out[0]), "pipeline_error": int(out[1]), "fp64_tiles": int(out[2]), "int8_gemms": int(out[3])}
 
+    def kernel_launch_log(self) -> list[dict]:
+        """ProviderTelemetry.kernel_launches: the bounded log of recent launches (64 events, newest last)."""
+        ev = (_capi.KernelLaunchEvent * 64)()
+        n = C.c_uint32()
+        _check(lib.rm_kernel_launch_log(self._p, ev, 64, C.byref(n)))
+        out = []
+        for e in ev[:n.value]:
+            out.append({"kernel": e.kernel.decode(), "precision": "f64" if e.precision == 1 else "f32",
+                        "shape": {a.key.decode(): int(a.value) for a in e.shape[:e.n_shape]},
+                        "tuning": {a.key.decode(): int(a.value) for a in e.tuning[:e.n_tuning]}})
+        return out
+
+    def spawn_handle_concurrency(self) -> str:
+        """AccelProvider::spawn_handle_concurrency (lib.rs:1400-1402)."""
+        return ["ImmutableShare", "CopyOnWrite", "SynchronizedMutation", "Reject"][int(lib.rm_spawn_handle_concurrency_policy(self._p))]
+
     def set_launch_overlap(self, enabled: bool) -> None:
         """Programmatic dependent launch of the generated fused kernels (default on); off = plain launches (isolated timing)."""
         _check(lib.rm_set_launch_overlap(self._p, 1 if enabled else 0))

@@ -19,6 +19,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
 LIB = ROOT / "runmat_b200" / "librm_accel_b200.so"
 OUT = ROOT / "profiles"
 
@@ -85,7 +86,8 @@ def main():
             if kernel in mangled and not kernel.startswith("rm_fused"):
                 write_extract(kernel, mangled, lines, "runmat_b200/librm_accel_b200.so (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false)")
     # the generated (NVRTC) headline kernels: lower them through the library's debug entry points and disassemble the cubin
-    from runmat_b200 import _capi, fusion_text as ft
+    from runmat_b200 import _capi
+    import fusion_text as ft
 
     lib = _capi.lib
     for name, shader, fn, args in (("rm_fused_ew", ft.sin_mul_add_wgsl(), lib.rm_debug_lower_elementwise, (0, 4)),

@@ -1,7 +1,8 @@
 """Asymptotic read bandwidth of the fused reduction kernel: plain sum over 1 GiB (separates fixed launch/finish cost from streaming rate)."""
 import sys, numpy as np
-sys.path.insert(0, '.')
-from runmat_b200 import B200Provider, fusion_text as ft
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+from runmat_b200 import B200Provider
+import fusion_text as ft
 p = B200Provider(0)
 plain = ft.reduction_wgsl([0], [], 0, axis=0)
 for logn in (24, 27, 29):

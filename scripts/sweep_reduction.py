@@ -9,8 +9,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import sys, math, numpy as np
-sys.path.insert(0, %r)
-from runmat_b200 import B200Provider, fusion_text as ft
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from runmat_b200 import B200Provider
+import fusion_text as ft
 p = B200Provider(0)
 n = 4096
 rng = np.random.default_rng(0)
@@ -24,7 +25,7 @@ for name, shader, ins, nbytes in (("sum(sin(A).*B+1)", sh, [hA, hB], 16*n*n), ("
     ms = p.timer_end_ms() / 50
     print(f"{name}: {ms*1e3:.1f} us {nbytes/ms/1e6:.0f} GB/s", end="  |  ")
 print()
-''' % ROOT
+''' % (ROOT, ROOT)
 for unroll, minb, bpsm in itertools.product((2, 4), (0, 5, 6, 8), (4, 8, 16)):
     env = dict(os.environ, RUNMAT_B200_RED_UNROLL=str(unroll), RUNMAT_B200_RED_MINB=str(minb), RUNMAT_B200_RED_BPSM=str(bpsm))
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)

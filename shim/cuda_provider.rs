@@ -14,7 +14,7 @@ use runmat_accelerate_api::{
     CovNormalization, CovRows, CovarianceOptions, FindDirection, HostTensorOwned, HostTensorView, ImageNormalizeDescriptor,
     ImfilterMode, ImfilterOptions, ImfilterPadding, ImfilterShape, MatmulEpilogue, PowerStepEpilogue, ProviderConvMode,
     ProviderDispatchStats, ProviderFindResult, ProviderLinsolveOptions, ProviderLinsolveResult, ProviderMoments2, ProviderPrecision,
-    ProviderTelemetry, ReduceDimResult, ReductionFlavor, ScaleOp, SpawnHandleConcurrency,
+    KernelAttrTelemetry, KernelLaunchTelemetry, ProviderTelemetry, ReduceDimResult, ReductionFlavor, ScaleOp, SpawnHandleConcurrency,
 };
 use std::ffi::{c_char, c_int, c_void, CStr, CString};
 
@@ -106,6 +106,22 @@ pub struct RmTelemetry {
     pub kernel_launches: u64,
 }
 
+/// rm_kernel_launch_event (include/rm_accel.h): one entry of the bounded launch log
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct RmKernelAttr { pub key: [u8; 16], pub value: u64 }
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct RmKernelLaunchEvent {
+    pub kernel: [u8; 32],
+    pub precision: c_int,
+    pub n_shape: u32,
+    pub n_tuning: u32,
+    pub shape: [RmKernelAttr; 4],
+    pub tuning: [RmKernelAttr; 4],
+}
+fn c_chars(b: &[u8]) -> String { String::from_utf8_lossy(&b[..b.iter().position(|&c| c == 0).unwrap_or(b.len())]).into_owned() }
+
 #[link(name = "rm_accel_b200")]
 extern "C" {
     fn rm_provider_create(cuda_ordinal: c_int, device_id: u32, precision: c_int, out: *mut *mut c_void) -> c_int;
@@ -139,6 +155,8 @@ extern "C" {
     fn rm_set_rng_state(p: *mut c_void, state: u64) -> c_int;
     fn rm_telemetry_snapshot(p: *mut c_void, out: *mut RmTelemetry) -> c_int;
     fn rm_reset_telemetry(p: *mut c_void) -> c_int;
+    fn rm_kernel_launch_log(p: *mut c_void, out: *mut RmKernelLaunchEvent, cap: u32, count: *mut u32) -> c_int;
+    fn rm_spawn_handle_concurrency_policy(p: *mut c_void) -> c_int;
     fn rm_fused_cache_counters(p: *mut c_void, hits: *mut u64, misses: *mut u64);
     // "next" rows: solves, indexing/layout class, fusion-pattern hooks, filters
     fn rm_mldivide(p: *mut c_void, lhs: *const RmHandle, rhs: *const RmHandle, out: *mut RmHandle) -> c_int;
@@ -220,6 +238,22 @@ fn empty_raw() -> RmHandle {
 }
 
 impl CudaProvider {
+    /// ProviderTelemetry::kernel_launches: the library's bounded log (64 events, newest last)
+    fn launch_log(&self) -> Vec<KernelLaunchTelemetry> {
+        let mut ev: Vec<RmKernelLaunchEvent> = Vec::with_capacity(64);
+        let mut n: u32 = 0;
+        unsafe {
+            if rm_kernel_launch_log(self.raw, ev.as_mut_ptr(), 64, &mut n) != 0 { return Vec::new(); }
+            ev.set_len(n as usize);
+        }
+        let attrs = |a: &[RmKernelAttr], k: u32| a[..k as usize].iter().map(|x| KernelAttrTelemetry { key: c_chars(&x.key), value: x.value }).collect::<Vec<_>>();
+        ev.iter().map(|e| KernelLaunchTelemetry {
+            kernel: c_chars(&e.kernel),
+            precision: Some(if e.precision == 1 { "f64".to_string() } else { "f32".to_string() }),
+            shape: attrs(&e.shape, e.n_shape),
+            tuning: attrs(&e.tuning, e.n_tuning),
+        }).collect()
+    }
     /// `cuda_ordinal`: CUDA device; `device_id`: the id from `runmat_accelerate_api::next_device_id()` (lib.rs:3279).
     pub fn new(cuda_ordinal: i32, device_id: u32) -> Result<Self> {
         let mut raw = std::ptr::null_mut();
@@ -322,10 +356,6 @@ impl AccelProvider for CudaProvider {
         let mut out = empty_raw();
         check(unsafe { rm_reshape(self.raw, &to_raw(handle)?, s.as_ptr(), s.len() as u32, &mut out) })?;
         Ok(GpuTensorHandle { shape: new_shape.to_vec(), device_id: handle.device_id, buffer_id: handle.buffer_id })
-    }
-    fn spawn_handle_concurrency(&self) -> SpawnHandleConcurrency {
-        // handles are immutable ids into a mutex-guarded table; every result is a new buffer except scatter_linear / diag_output
-        SpawnHandleConcurrency::ImmutableShare
     }
     fn linspace(&self, start: f64, stop: f64, count: usize) -> Result<GpuTensorHandle> {
         let mut out = empty_raw();
@@ -662,6 +692,15 @@ impl AccelProvider for CudaProvider {
     }
     fn warmup(&self) { unsafe { rm_warmup(self.raw) }; }
 
+    fn spawn_handle_concurrency(&self) -> SpawnHandleConcurrency {
+        match unsafe { rm_spawn_handle_concurrency_policy(self.raw) } {
+            0 => SpawnHandleConcurrency::ImmutableShare,
+            1 => SpawnHandleConcurrency::CopyOnWrite,
+            2 => SpawnHandleConcurrency::SynchronizedMutation,
+            _ => SpawnHandleConcurrency::Reject,
+        }
+    }
+
     fn telemetry_snapshot(&self) -> ProviderTelemetry {
         let mut t = RmTelemetry::default();
         unsafe { rm_telemetry_snapshot(self.raw, &mut t) };
@@ -671,7 +710,7 @@ impl AccelProvider for CudaProvider {
             linsolve: cv(t.linsolve), mldivide: cv(t.mldivide), mrdivide: cv(t.mrdivide),
             upload_bytes: t.upload_bytes, download_bytes: t.download_bytes, solve_fallbacks: Vec::new(),
             fusion_cache_hits: t.fusion_cache_hits, fusion_cache_misses: t.fusion_cache_misses,
-            bind_group_cache_hits: 0, bind_group_cache_misses: 0, bind_group_cache_by_layout: None, kernel_launches: Vec::new(),
+            bind_group_cache_hits: 0, bind_group_cache_misses: 0, bind_group_cache_by_layout: None, kernel_launches: self.launch_log(),
         }
     }
     fn reset_telemetry(&self) { unsafe { rm_reset_telemetry(self.raw) }; }

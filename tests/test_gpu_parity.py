@@ -15,7 +15,8 @@ import numpy as np
 import pytest
 
 from kat_util import KATS, arr, assert_same, num
-from runmat_b200 import ImageNormalizeDescriptor, MatmulEpilogue, ProviderError, fusion_text as ft
+from runmat_b200 import ImageNormalizeDescriptor, MatmulEpilogue, ProviderError
+import fusion_text as ft
 
 pytestmark = pytest.mark.gpu
 
@@ -1365,6 +1366,31 @@ def test_imfilter_4k_rgb_full_size_vs_oracle(prov32, orc):
     assert np.array_equal(got, want)
 
 
+def test_kernel_launch_log_and_spawn_policy(prov):
+    """ProviderTelemetry::kernel_launches is a bounded log (64 events, newest last) with the wgpu provider's kernel names and shape
+    keys (backend/wgpu/provider/ops/telemetry.rs:26-146, helpers.rs:36-50); spawn policy = the in-process provider's."""
+    prov.reset_telemetry()
+    assert prov.kernel_launch_log() == []
+    x = np.random.default_rng(1).uniform(-1, 1, (96, 80))
+    h = prov.upload(x)
+    one = prov.upload(np.array([[1.0]]))
+    c = prov.fused_elementwise(ft.sin_mul_add_wgsl(), [h, h, one], (96, 80), 96 * 80)
+    s_ = prov.fused_reduction(ft.sum_sin_mul_add_wgsl(), [h, h], (1, 1), 96 * 80, 1)
+    m = prov.matmul(h, prov.upload(x.T.copy()))
+    log = prov.kernel_launch_log()
+    assert [e["kernel"] for e in log] == ["fused_elementwise", "fused_reduction", "matmul"]
+    assert log[0]["shape"] == {"len": 96 * 80, "inputs": 3, "rank": 2} and log[0]["precision"] == "f64"
+    assert log[1]["shape"] == {"reduce_len": 96 * 80, "slices": 1, "rank": 2}
+    assert log[2]["shape"] == {"m": 96, "n": 96, "k": 80}
+    for _ in range(70):
+        prov.free(prov.fused_reduction(ft.sum_sin_mul_add_wgsl(), [h, h], (1, 1), 96 * 80, 1))
+    log = prov.kernel_launch_log()
+    assert len(log) == 64 and all(e["kernel"] == "fused_reduction" for e in log)  # oldest dropped
+    assert prov.spawn_handle_concurrency() == "SynchronizedMutation"
+    for hh in (h, one, c, s_, m):
+        prov.free(hh)
+
+
 def test_imfilter_tma_staged_path(prov32, orc, monkeypatch):
     """Large f32 images take the persistent TMA-staged kernel (cp.async.bulk.tensor ring for interior tiles, index-map fill for
     the border ring): every padding, 3x3 / 5x5 / 7x7, same / full / valid, corr / conv, ragged tile edges, an RGB and a 2-D
@@ -1473,7 +1499,8 @@ def test_telemetry_counts(prov):
 def test_comm_p2p_self_exchange(orc):
     """The peer-memory exchange with world == 1 (a rank connected to itself) runs the whole protocol on one GPU: fused publish
     from the reduction kernel's last block, stand-alone publish, lazy combine on the communication stream, 8-bank reuse."""
-    from runmat_b200 import B200Provider, fusion_text as ft
+    from runmat_b200 import B200Provider
+    import fusion_text as ft
 
     with B200Provider(0, device_id=78) as p:
         assert not p.comm_p2p_connected()

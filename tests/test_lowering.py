@@ -3,7 +3,7 @@ import ctypes as C
 
 import pytest
 
-from runmat_b200 import fusion_text as ft
+import fusion_text as ft
 
 
 @pytest.fixture(scope="module")
