@@ -167,6 +167,15 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
   // barrier is a cluster barrier (~0.3 us) instead of a grid-wide cooperative sync (~2.5 us). One cluster = the whole grid.
   __shared__ Candidate s_cand[2];
   __shared__ double s_pub_rowc[2][NB];
+  // CLUSTER variant, per-column exchange without the hardware cluster barrier (r17 ncu: barrier.cluster wait = 29 % of the kernel's
+  // stall samples, the remote candidate reads that followed it another 13 %): every CTA PUSHES its candidate (|value|, row) into
+  // slot [buf][rank] of every peer's mailbox with plain DSMEM stores followed by a release store of the column stamp; a CTA then
+  // only spins (acquire) on its OWN shared memory until all stamps of the column have arrived and resolves the pivot locally.
+  // Double buffering is safe: a CTA reaches column c+2 only after it has seen every peer's stamp for c+1, which a peer sends after
+  // it has finished reading column c.
+  __shared__ double mb_val[2][16];
+  __shared__ unsigned long long mb_idx[2][16];
+  __shared__ unsigned mb_flag[2][16];
   const unsigned nblk = gridDim.x;
   const uint64_t m = n - j0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,8 +184,13 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
   double* P = A + j0 + j0 * lda;
   for (int cc = 0; cc < jb; ++cc) slab[tid][cc] = valid ? P[r + (uint64_t)cc * lda] : 0.0;
   if (blockIdx.x == 0 && tid == 0) p_n = 0;
+  if constexpr (CLUSTER) {
+    if (tid < 32) { mb_flag[0][tid & 15] = 0; mb_flag[1][tid & 15] = 0; }
+    cg::this_cluster().sync();  // every mailbox is initialised before the first push
+  }
   __syncthreads();
 
+  double loc_pmin = 1.7976931348623157e308, loc_pmax = 0.0;  // CTA 0 / lane 0: extreme |pivot| of this panel (a global read-modify-write per column sat on the critical path)
   for (int c = 0; c < jb; ++c) {
     const int buf = c & 1;  // double-buffered exchange area: column c+1 may be published while a slow CTA still reads column c
     Candidate* mine = CLUSTER ? &s_cand[buf] : cand + (size_t)buf * nblk + blockIdx.x;
@@ -210,7 +224,31 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
       if (tid < jb && lp < (uint64_t)SLAB_ROWS) mine->row[tid] = slab[lp][tid];
       if (blockIdx.x == 0 && tid >= NB && tid < NB + jb) (CLUSTER ? s_pub_rowc[buf] : rowc + buf * NB)[tid - NB] = slab[c][tid - NB];
     }
-    if constexpr (CLUSTER) cg::this_cluster().sync(); else grid.sync();
+    if constexpr (CLUSTER) {
+      __syncthreads();  // this CTA's candidate row (and row c) are complete in its shared memory before the stamp goes out
+      if (warp == 0 && (unsigned)lane < nblk) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const unsigned me = blockIdx.x;
+        const double myv = s_cand[buf].val;
+        const unsigned long long myi = s_cand[buf].idx;
+        *cluster.map_shared_rank(&mb_val[buf][me], lane) = myv;
+        *cluster.map_shared_rank(&mb_idx[buf][me], lane) = myi;
+        unsigned* fl = cluster.map_shared_rank(&mb_flag[buf][me], lane);
+        asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(fl), "r"((unsigned)(c + 1)) : "memory");
+        // wait for peer `lane`'s stamp in OUR mailbox (bounded: a protocol bug raises info instead of hanging the GPU)
+        const unsigned* mine_fl = &mb_flag[buf][lane];
+        const long long t0 = clock64();
+        for (;;) {
+          unsigned f;
+          asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(f) : "l"(mine_fl) : "memory");
+          if (f == (unsigned)(c + 1)) break;
+          if (clock64() - t0 > 4000000000LL) { atomicExch(info, 1); break; }
+        }
+      }
+      __syncwarp();
+    } else {
+      grid.sync();
+    }
     // ---- every CTA resolves the global pivot redundantly: warp 0, one candidate per lane ----
     if (warp == 0) {
       double gv = -1.0;
@@ -220,8 +258,7 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
         double v;
         unsigned long long i;
         if constexpr (CLUSTER) {
-          const Candidate* cb = cg::this_cluster().map_shared_rank(&s_cand[buf], b);
-          v = cb->val; i = cb->idx;
+          v = *(volatile double*)&mb_val[buf][b]; i = *(volatile unsigned long long*)&mb_idx[buf][b];
         } else {
           const Candidate* cb = cand + (size_t)buf * nblk + b;
           v = __ldcg(&cb->val); i = __ldcg(&cb->idx);
@@ -240,10 +277,7 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
       if (blockIdx.x == 0 && lane == 0) {
         ipiv[j0 + c] = j0 + gi;
         if (!(gv > 0.0)) atomicExch(info, 1);
-        if (gv > 0.0) {
-          if (gv < piv_minmax[0]) piv_minmax[0] = gv;
-          if (gv > piv_minmax[1]) piv_minmax[1] = gv;
-        }
+        if (gv > 0.0) { loc_pmin = fmin(loc_pmin, gv); loc_pmax = fmax(loc_pmax, gv); }  // folded into piv_minmax once, after the loop
       }
     }
     __syncthreads();
@@ -276,6 +310,10 @@ lu_panel_smem_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
     __syncthreads();
   }
   if (valid) for (int cc = 0; cc < jb; ++cc) P[r + (uint64_t)cc * lda] = slab[tid][cc];
+  if (blockIdx.x == 0 && tid == 0) {
+    if (loc_pmin < piv_minmax[0]) piv_minmax[0] = loc_pmin;
+    if (loc_pmax > piv_minmax[1]) piv_minmax[1] = loc_pmax;
+  }
   if constexpr (CLUSTER) cg::this_cluster().sync();  // nobody exits while a peer may still read its shared memory
   if (blockIdx.x == 0) {
     __syncthreads();
