@@ -11,6 +11,7 @@
 // host stream and the result is independent of how paths are sharded over GPUs. The whole T-step loop runs
 // in registers: S is read once and written once (16 B/path); the kernel is FP64-ALU/SFU bound.
 #include "common.h"
+#include "mc_math.h"
 
 namespace rm {
 
@@ -40,17 +41,28 @@ __device__ __forceinline__ double lcg_next_uniform(uint64_t& s) {
   s = s * LCG_MULT + LCG_INC;
   return (double)(s >> 11) * (1.0 / 9007199254740992.0);
 }
+// LEAN: log / sincos from mc_math.h (coefficients in __constant__ memory: one DFMA per Horner step; the CUDA library versions
+// rebuild their coefficients as immediates every iteration, r06 SASS). false = the CUDA math library (RUNMAT_B200_MC_LIBM=1).
+template <bool LEAN>
 __device__ __forceinline__ void box_muller(uint64_t& s, double& z0, double& z1) {
   double u1 = lcg_next_uniform(s);
   if (u1 <= 0.0) u1 = 2.2250738585072014e-308;  // f64::MIN_POSITIVE
   const double u2 = lcg_next_uniform(s);
-  const double radius = sqrt(-2.0 * log(u1));
-  const double angle = 2.0 * 3.14159265358979323846 * u2;
-  double sn, cs;
-  sincos(angle, &sn, &cs);
+  double sn, cs, radius;
+  if (LEAN) {
+    radius = sqrt(-2.0 * rm_mc::log_unit(u1));
+    rm_mc::sincos_turn(u2, &sn, &cs);
+  } else {
+    radius = sqrt(-2.0 * log(u1));
+    const double angle = 2.0 * 3.14159265358979323846 * u2;
+    sincos(angle, &sn, &cs);
+  }
   z0 = radius * cs;
   z1 = radius * sn;
 }
+template <bool LEAN>
+__device__ __forceinline__ double mc_exp(double x) { return LEAN ? rm_mc::exp_fast(x) : exp(x); }
+inline bool mc_lean() { return getenv("RUNMAT_B200_MC_LIBM") == nullptr; }
 
 template <typename T>
 __global__ void uniform_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, uint64_t hop_mult, uint64_t hop_plus) {
@@ -65,7 +77,7 @@ __global__ void uniform_kernel(T* __restrict__ out, uint64_t n, uint64_t state0,
   }
 }
 
-template <typename T>
+template <typename T, bool LEAN>
 __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, uint64_t hop_mult, uint64_t hop_plus) {
   const uint64_t pairs = (n + 1) / 2;
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,7 +87,7 @@ __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, 
   for (uint64_t j = tid; j < pairs; j += nthr) {
     uint64_t s2 = s;
     double z0, z1;
-    box_muller(s2, z0, z1);
+    box_muller<LEAN>(s2, z0, z1);
     out[2 * j] = (T)z0;
     if (2 * j + 1 < n) out[2 * j + 1] = (T)z1;
     s = hop_mult * s + hop_plus;  // 2*nthr draws ahead
@@ -84,7 +96,7 @@ __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, 
 
 // One thread per Box-Muller pair of the GLOBAL path vector. `first_pair` is the global index of this
 // launch's first pair; local element e_local = e_global - path_offset.
-template <typename T>
+template <typename T, bool LEAN>
 __global__ void __launch_bounds__(256)
 evolve_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t len, uint64_t path_offset, uint64_t first_pair,
               uint64_t n_pairs, uint64_t state0, uint64_t step_mult, uint64_t step_plus, double drift, double scale, uint32_t steps) {
@@ -100,10 +112,10 @@ evolve_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t len, uint6
   for (uint32_t t = 0; t < steps; ++t) {
     uint64_t s2 = s;
     double z0, z1;
-    box_muller(s2, z0, z1);
+    box_muller<LEAN>(s2, z0, z1);
     // stochastic_evolution.rs:25-27: term = drift + scale*noise; value *= exp(term)   (no FMA: -fmad=false)
-    s0v *= exp(drift + scale * z0);
-    s1v *= exp(drift + scale * z1);
+    s0v *= mc_exp<LEAN>(drift + scale * z0);
+    s1v *= mc_exp<LEAN>(drift + scale * z1);
     s = step_mult * s + step_plus;  // one whole pass (2*ceil(global_len/2) draws) ahead
   }
   if (has0) out[e0 - path_offset] = (T)s0v;
@@ -137,9 +149,9 @@ rm_status evolve(rm_provider* p, const rm_handle* state, double drift, double sc
   const uint64_t n_pairs = last_pair - first_pair + 1;
   const unsigned blocks = (unsigned)((n_pairs + 255) / 256);
   if (p->precision == RM_F64)
-    evolve_kernel<double><<<blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps);
+    (mc_lean() ? evolve_kernel<double, true> : evolve_kernel<double, false>)<<<blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps);
   else
-    evolve_kernel<float><<<blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps);
+    (mc_lean() ? evolve_kernel<float, true> : evolve_kernel<float, false>)<<<blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "stochastic_evolution launch failed: %s", cudaGetErrorString(e)); }
   count_launch(p);
@@ -169,8 +181,8 @@ rm_status random_fill(rm_provider* p, const uint64_t* shape, uint32_t rank, rm_h
   uint64_t hm, hp;
   lcg_affine_pow(NORMAL ? 2 * nthr : nthr, &hm, &hp);
   if (NORMAL) {
-    if (p->precision == RM_F64) normal_kernel<double><<<(unsigned)blocks, 256, 0, p->stream>>>((double*)dst, n, state0, hm, hp);
-    else normal_kernel<float><<<(unsigned)blocks, 256, 0, p->stream>>>((float*)dst, n, state0, hm, hp);
+    if (p->precision == RM_F64) (mc_lean() ? normal_kernel<double, true> : normal_kernel<double, false>)<<<(unsigned)blocks, 256, 0, p->stream>>>((double*)dst, n, state0, hm, hp);
+    else (mc_lean() ? normal_kernel<float, true> : normal_kernel<float, false>)<<<(unsigned)blocks, 256, 0, p->stream>>>((float*)dst, n, state0, hm, hp);
   } else {
     if (p->precision == RM_F64) uniform_kernel<double><<<(unsigned)blocks, 256, 0, p->stream>>>((double*)dst, n, state0, hm, hp);
     else uniform_kernel<float><<<(unsigned)blocks, 256, 0, p->stream>>>((float*)dst, n, state0, hm, hp);
