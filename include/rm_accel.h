@@ -122,7 +122,9 @@ rm_status rm_comm_fence(rm_provider* p);
  * rm_comm_p2p_export (allocates its slot buffer, returns the 64-byte CUDA IPC handle), the host gathers the handles of all
  * ranks in rank order, every rank calls rm_comm_p2p_connect. Afterwards rm_comm_allreduce_sum of a 1-element f64 tensor and
  * rm_fused_reduction_allreduce use peer stores instead of a NCCL launch; results are bit-identical on every rank (fixed rank
- * order). world == 1 connects a rank to itself. */
+ * order). The fold ("combine") of an exchange is lazy: it is fused in front of the publish issued four exchanges later, or
+ * enqueued on the provider stream when the result handle is first used or freed -- no communication stream, no kernel of its
+ * own in a steady loop. Every rank must issue the same sequence of exchanges. world == 1 connects a rank to itself. */
 #define RM_COMM_P2P_HANDLE_BYTES 64
 rm_status rm_comm_p2p_export(rm_provider* p, uint8_t* handle_out, uint32_t len);
 rm_status rm_comm_p2p_connect(rm_provider* p, const uint8_t* all_handles, uint32_t len, uint32_t rank, uint32_t world);

@@ -41,11 +41,15 @@ RM_MC_HD double exp_fast(double x) {
   const double k = rint(x * 1.4426950408889634074);
   double r = fma(k, -6.93147180369123816490e-01, x);   // ln2 hi (trailing zeros: k * hi is exact)
   r = fma(k, -1.90821492927058770002e-10, r);          // ln2 lo
-  double p = kExp[12];
+  // two independent Horner chains (even / odd powers) in r^2: half the dependent-DFMA depth of a plain degree-12 Horner (r24 ncu:
+  // FP64 pipe 67 % and issue 70 % busy -- the kernel waits on dependent chains, not on a pipe)
+  const double r2 = r * r;
+  double pe = kExp[12], po = kExp[11];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 11; i >= 0; --i) p = fma(p, r, kExp[i]);
+  for (int i = 10; i >= 0; i -= 2) { pe = fma(pe, r2, kExp[i]); if (i >= 1) po = fma(po, r2, kExp[i - 1]); }
+  const double p = fma(po, r, pe);
   return p * bits_to_double((uint64_t)((int64_t)k + 1023) << 52);  // exact scaling by 2^k, -1010 <= k <= 1010
 }
 
@@ -57,11 +61,13 @@ RM_MC_HD double log_unit(double u) {
   if (m > 1.4142135623730951) { m *= 0.5; e += 1; }                                 // [0.7071, 1.4142]
   const double s = (m - 1.0) / (m + 1.0);
   const double s2 = s * s;
-  double p = kAtanh[9];
+  const double s4 = s2 * s2;
+  double pa = kAtanh[8], pb = kAtanh[9];  // even / odd coefficients of the series in s2: two chains in s4
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 8; i >= 0; --i) p = fma(p, s2, kAtanh[i]);
+  for (int i = 6; i >= 0; i -= 2) { pa = fma(pa, s4, kAtanh[i]); pb = fma(pb, s4, kAtanh[i + 1]); }
+  const double p = fma(pb, s2, pa);
   const double lm = 2.0 * s * p;  // log(m)
   const double ed = (double)e;
   return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lm));
