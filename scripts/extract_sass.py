@@ -29,6 +29,10 @@ INTEREST = {
     "dgemm_dmma_kernel": ["DMMA", "LDGSTS"],
     "evolve_kernel": ["DFMA", "DMUL", "DADD", "MUFU"],
     "imfilter_regblock_kernel": ["FMUL", "FADD", "FFMA"],
+    "imfilter_tma_f32_kernelILi5ELi8ELi1": ["FMUL2", "FFMA2", "UTMALDG", "SYNCS", "LDS"],
+    "imfilter_packed_f32_kernelILi5": ["FMUL2", "FFMA2", "LDS"],
+    "normalize_fixed_clampgamma_f32_kernel": ["MUFU", "FMUL", "FADD", "FMNMX"],
+    "trsm_block_kernelILi0": ["SHFL", "DFMA", "LDS", "BAR"],
     "moments_partial_fold_kernel": ["SHFL", "DADD", "DFMA", "ATOM"],
     "normalize_fixed_kernel": ["MUFU", "FMUL", "FADD"],
     "lu_panel_smem_kernel": ["DFMA", "DMUL", "BAR", "UCGABAR"],
