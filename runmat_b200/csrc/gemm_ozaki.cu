@@ -45,6 +45,11 @@ constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
 constexpr int OZ_SMEM = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int TMEM_COLS = 512;  // two 256-column int32 accumulators
+// pair kernel: per CTA 128 rows of A + 128 of the pair tile's 256 columns of B per stage
+constexpr int P_STAGES = 6;
+constexpr int P_B_STAGE = (BN / 2) * BK;
+constexpr int P_STAGE_BYTES = A_STAGE + P_B_STAGE;  // 32 KB
+constexpr int OZ_SMEM_PAIR = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 constexpr int NTHREADS = 192;
 constexpr int MAX_SLICES = 8;
 
@@ -86,6 +91,31 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- cta_group::2 forms (a CTA pair = cluster 2x1x1 owns a 256 x 256 tile; PTX forms as in cute/arch/mma_sm100_umma.hpp,
+//      copy_sm100_tma.hpp, cutlass/arch/barrier.h; brought up in scripts/ozaki_dev/i8gemm2_test.cu) --------------------------------
+__device__ __forceinline__ void mma_i8_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair when the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+// TMA load by either CTA of the pair into ITS OWN shared memory; the bytes are credited to the LEADER's barrier at the same offset
+// (CTA-rank bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// arrive (count 1) on the LEADER's copy of a barrier from either CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -392,6 +422,169 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
+// The same pipeline on CTA PAIRS (cta_group::2, cluster 2x1x1): a pair owns a 256 x 256 tile, each CTA stages its 128 rows of the A
+// slice and its 128-column half of the B slice (32 KB per stage instead of 48 KB, 6 stages), the leader's MMA warp issues UMMA
+// 256x256x32 for both, TMA completions of both CTAs are credited to the leader's `full` barrier, stage releases and accumulator-ready
+// signals are multicast commits, the epilogue warps of both CTAs drain their own 128 TMEM lanes and release the accumulator on the
+// leader's `tmem_empty` barrier (count 8). Shared-memory fill traffic per SM and MMA drops by a third, which is what limited the
+// single-CTA mainloop (r27 harness, one 8192^3 int8 GEMM: 2.53 vs 2.31 POP/s). Mp is padded to a multiple of 256.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+ozaki_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C, uint64_t M, uint64_t N,
+                  int Mp, int Np, int Kp, int S, int bits, const unsigned long long* __restrict__ amax, const unsigned long long* __restrict__ bmax,
+                  const __grid_constant__ OzEpilogue ep, int* __restrict__ flags, int* __restrict__ tileflags, long long guard_min) {
+  extern __shared__ uint8_t smem_raw[];
+  if (flags[0]) return;  // non-finite input (uniform for the grid): the conditional FP64 kernel computes every tile
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + P_STAGES * P_STAGE_BYTES);
+  uint64_t* empty = full + P_STAGES;
+  uint64_t* tmem_full = empty + P_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  int* err = flags + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
+  const int tiles_m = Mp / (2 * BM), tiles_n = Np / BN, ntiles = tiles_m * tiles_n;  // pair tiles: 256 x 256
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nk = Kp / BK;
+  const int npass = S + 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }  // 4 epilogue warps x 2 CTAs release an accumulator
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before a remote completion or a multicast commit can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;  // global k-block counter -> stage / phase
+      bool ok = true;
+      for (int tile = pair_id; tile < ntiles && ok; tile += npairs) {
+        int m0, n0;
+        tile_coords(tile, tiles_m, tiles_n, &m0, &n0);
+        m0 = 2 * m0 + (int)rank * BM;  // tile_coords counts in BM rows; pair tiles are 2 BM tall
+        for (int pi = 0; pi < npass && ok; ++pi) {
+          const int np = pass_pairs(pi, S);
+          for (int idx = 0; idx < np && ok; ++idx) {
+            int s, t;
+            pass_pair(pi, S, idx, &s, &t);
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int st = it % P_STAGES;
+              if (!mbar_wait(&empty[st], ((it / P_STAGES) & 1) ^ 1, err)) { ok = false; break; }
+              if (rank == 0) mbar_expect_tx(&full[st], 2 * P_STAGE_BYTES);  // the leader's barrier collects the bytes of both CTAs
+              tma_load_2d_pair(smem + st * P_STAGE_BYTES, &tmA, &full[st], kb * BK, s * Mp + m0);
+              tma_load_2d_pair(smem + st * P_STAGE_BYTES + A_STAGE, &tmB, &full[st], kb * BK, t * Np + n0 + (int)rank * (BN / 2));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256
+      uint32_t it = 0, g = 0;  // g: global pass counter -> TMEM buffer / phase
+      bool ok = true;
+      for (int tile = pair_id; tile < ntiles && ok; tile += npairs) {
+        for (int pi = 0; pi < npass && ok; ++pi, ++g) {
+          const uint32_t buf = g & 1;
+          if (!mbar_wait(&tmem_empty[buf], ((g >> 1) & 1) ^ 1, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + buf * BN;
+          uint32_t first = 1;
+          const int np = pass_pairs(pi, S);
+          for (int idx = 0; idx < np && ok; ++idx)
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int st = it % P_STAGES;
+              if (!mbar_wait(&full[st], (it / P_STAGES) & 1, err)) { ok = false; break; }
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(smem + st * P_STAGE_BYTES), b_addr = a_addr + A_STAGE;
+              const uint64_t da = make_desc_k_sw128(a_addr), db = make_desc_k_sw128(b_addr);
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) { mma_i8_pair(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u); first = 0; }
+              tc_commit_pair(&empty[st]);
+            }
+          if (ok) tc_commit_pair(&tmem_full[buf]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t g = 0;
+    bool ok = true;
+    for (int tile = pair_id; tile < ntiles && ok; tile += npairs) {
+      int m0, n0;
+      tile_coords(tile, tiles_m, tiles_n, &m0, &n0);
+      m0 = 2 * m0 + (int)rank * BM;
+      const uint64_t row = (uint64_t)m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const int ea = row_ok ? scale_exponent(amax[row], bits) : 0;
+      for (int pi = 0; pi < npass && ok; ++pi, ++g) {
+        const uint32_t buf = g & 1;
+        if (!mbar_wait(&tmem_full[buf], (g >> 1) & 1, err)) { ok = false; break; }
+        tc_fence_after();
+        if (pi < S) {
+          const int d = S - 1 - pi;
+          const double scale = scalbn(1.0, -bits * (d + 2));
+          const bool first = pi == 0, last = d == 0;
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
+            if (row_ok) {
+              double acc[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const uint64_t col = (uint64_t)n0 + c + j;
+                acc[j] = (!first && col < N) ? C[row + col * M] : 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const uint64_t col = (uint64_t)n0 + c + j;
+                if (col < N) {
+                  double r = acc[j] + (double)(int)v[j] * scale;
+                  if (last) {
+                    r = scalbn(r, ea + scale_exponent(bmax[col], bits));
+                    if (ep.active) r = oz_apply_epilogue(r, ep, row, col);
+                  }
+                  C[row + col * M] = r;
+                }
+              }
+            }
+          }
+        } else {
+          // accuracy guard: L_ij = sum_k |qa0||qb0| must reach guard_min, else the tile is recomputed in native f64
+          bool weak = false;
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) weak |= row_ok && ((uint64_t)n0 + c + j < N) && ((long long)(int)v[j] < guard_min);
+          }
+          if (__any_sync(0xffffffffu, weak) && lane == 0) {
+            if (atomicExch(&tileflags[m0 / BM + (n0 / BN) * (Mp / BM)], 1) == 0) atomicAdd(&flags[2], 1);  // flags stay per 128 x 256 tile
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's shared memory and TMEM stay alive until the leader's last MMA has retired and both epilogues are done
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -446,6 +639,7 @@ struct OzWorkspace {
   CUtensorMap tmA, tmB;
   void *mapA_ptr = nullptr, *mapB_ptr = nullptr;
   uint64_t mapA_rows = 0, mapB_rows = 0, mapA_k = 0, mapB_k = 0;
+  uint32_t mapB_box = 0;
   int last_gemms = 0;  // int8 GEMMs per output tile of the last product: S(S+1)/2 digit products + the guard's magnitude product
 };
 
@@ -479,7 +673,10 @@ rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double*
                        const rm_matmul_epilogue* epd, const void* prow, const void* pcol, void* pdiag, bool ep_active, bool* used, OzGuard* guard) {
   *used = false;
   if (k > 65536 || m == 0 || n == 0 || k == 0) return RM_OK;  // int32 headroom of the 7-bit split: S*K*64^2 < 2^31
-  const uint64_t Mp = (m + BM - 1) / BM * BM, Np = (n + BN - 1) / BN * BN, Kp = (k + BK - 1) / BK * BK;
+  // CTA pairs (cta_group::2, 256 x 256 tiles) unless switched off; Mp is then a multiple of 256
+  const bool pair = getenv("RUNMAT_B200_OZAKI_1CTA") == nullptr;
+  const uint64_t MT = pair ? 2 * BM : BM;
+  const uint64_t Mp = (m + MT - 1) / MT * MT, Np = (n + BN - 1) / BN * BN, Kp = (k + BK - 1) / BK * BK;
   // Digit width. 8-bit digits (|q| <= 128) cover 48 bits with S = 6 slices = 21 int8 GEMMs instead of the 28 of the 7-bit split
   // (S = 7, 49 bits); an anti-diagonal of up to 6 pairs then needs 6 * K * 128^2 < 2^31, i.e. K <= 21760. Longer products keep
   // the 7-bit digits. RUNMAT_B200_OZAKI_BITS / RUNMAT_B200_OZAKI_SLICES override.
@@ -513,6 +710,7 @@ rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double*
     OZ_CUDA(cudaFuncSetAttribute(slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_smem));
     OZ_CUDA(cudaFuncSetAttribute(slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_smem));
     OZ_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    OZ_CUDA(cudaFuncSetAttribute(ozaki_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_PAIR));
     w.attrs_set = true;
     w.attr_slices = S;
   }
@@ -522,9 +720,10 @@ rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double*
     RM_TRY(make_map(w.As, (uint64_t)(S + 1) * Mp, Kp, BM, &w.tmA));
     w.mapA_ptr = w.As; w.mapA_rows = (uint64_t)(S + 1) * Mp; w.mapA_k = Kp;
   }
-  if (w.mapB_ptr != w.Bs || w.mapB_rows != (uint64_t)(S + 1) * Np || w.mapB_k != Kp) {
-    RM_TRY(make_map(w.Bs, (uint64_t)(S + 1) * Np, Kp, BN, &w.tmB));
-    w.mapB_ptr = w.Bs; w.mapB_rows = (uint64_t)(S + 1) * Np; w.mapB_k = Kp;
+  const uint32_t boxB = pair ? BN / 2 : BN;  // a CTA of a pair stages its 128-column half of the B tile
+  if (w.mapB_ptr != w.Bs || w.mapB_rows != (uint64_t)(S + 1) * Np || w.mapB_k != Kp || w.mapB_box != boxB) {
+    RM_TRY(make_map(w.Bs, (uint64_t)(S + 1) * Np, Kp, boxB, &w.tmB));
+    w.mapB_ptr = w.Bs; w.mapB_rows = (uint64_t)(S + 1) * Np; w.mapB_k = Kp; w.mapB_box = boxB;
   }
   OzEpilogue ep{};
   ep.alpha = 1.0;
@@ -535,8 +734,14 @@ rm_status ozaki_matmul(rm_provider* p, const double* A, const double* B, double*
   // e_S = B^-S * (1/2 + S/4), i.e. L_ij must reach K * (1/2 + S/4) * 2^(37 + 2 bits - bits S)   (bits = 7: 2^(51 - 7S))
   const double gmin = std::ceil((double)k * std::ldexp(0.5 + 0.25 * S, 37 + 2 * bits - bits * S));
   const long long guard_min = gmin >= 4.0e18 ? (long long)4e18 : std::max<long long>(1, (long long)gmin);
-  const int grid = (int)std::min<size_t>(ntiles, (size_t)p->prop.multiProcessorCount);
-  ozaki_gemm_kernel<<<grid, NTHREADS, OZ_SMEM, st>>>(w.tmA, w.tmB, C, m, n, (int)Mp, (int)Np, (int)Kp, S, bits, w.amax, w.bmax, ep, w.flags, w.tileflags, guard_min);
+  if (pair) {
+    const size_t npair_tiles = (size_t)(Mp / (2 * BM)) * (Np / BN);
+    const int grid = 2 * (int)std::min<size_t>(npair_tiles, (size_t)p->prop.multiProcessorCount / 2);
+    ozaki_gemm_pair_kernel<<<grid, NTHREADS, OZ_SMEM_PAIR, st>>>(w.tmA, w.tmB, C, m, n, (int)Mp, (int)Np, (int)Kp, S, bits, w.amax, w.bmax, ep, w.flags, w.tileflags, guard_min);
+  } else {
+    const int grid = (int)std::min<size_t>(ntiles, (size_t)p->prop.multiProcessorCount);
+    ozaki_gemm_kernel<<<grid, NTHREADS, OZ_SMEM, st>>>(w.tmA, w.tmB, C, m, n, (int)Mp, (int)Np, (int)Kp, S, bits, w.amax, w.bmax, ep, w.flags, w.tileflags, guard_min);
+  }
   OZ_CUDA(cudaGetLastError());
   count_launch(p, 5);
 #undef OZ_CUDA

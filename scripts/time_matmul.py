@@ -17,3 +17,14 @@ for bits in ("8", "7", "8"):
     ms = p.timer_end_ms() / 5
     st = p.ozaki_stats()
     print(f"bits {bits}: {ms:.3f} ms  {2.0 * n ** 3 / ms / 1e9:.1f} f64-equivalent TFLOP/s  int8 GEMMs {st['int8_gemms']}  {st['int8_gemms'] * 2.0 * n ** 3 / ms / 1e9:.0f} TOP/s   [{mid}]")
+os.environ.pop("RUNMAT_B200_OZAKI_BITS", None)
+for name, env in (("pair (cta_group::2)", {}), ("single CTA", {"RUNMAT_B200_OZAKI_1CTA": "1"}), ("pair (cta_group::2)", {})):
+    os.environ.pop("RUNMAT_B200_OZAKI_1CTA", None)
+    os.environ.update(env)
+    for _ in range(2): p.free(p.matmul(hA, hB))
+    p.synchronize(); p.timer_begin()
+    for _ in range(5): p.free(p.matmul(hA, hB))
+    mid = clk()
+    ms = p.timer_end_ms() / 5
+    st = p.ozaki_stats()
+    print(f"{name}: {ms:.3f} ms  {2.0 * n ** 3 / ms / 1e9:.1f} f64-equivalent TFLOP/s  {st['int8_gemms'] * 2.0 * n ** 3 / ms / 1e9:.0f} TOP/s  err {st['pipeline_error']}  [{mid}]")
