@@ -216,10 +216,29 @@ __device__ __forceinline__ float pow_nonneg_f32(float a, float g) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
   return r;
 }
+// VEC = 8 (B % 8 == 0): 256-bit accesses like the fused elementwise kernel (LDG.E.256 / STG.E.256, L1 no-allocate); VEC = 4 otherwise.
+struct __align__(32) f32x8 { float x[8]; };
+template <int VEC>
+__device__ __forceinline__ void ld_stream_f32(const float* p, float* e) {
+  if (VEC == 8)
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(e[0]), "=f"(e[1]), "=f"(e[2]), "=f"(e[3]), "=f"(e[4]), "=f"(e[5]), "=f"(e[6]), "=f"(e[7]) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e[0]), "=f"(e[1]), "=f"(e[2]), "=f"(e[3]) : "l"(p));
+}
+template <int VEC>
+__device__ __forceinline__ void st_stream_f32(float* p, const float* e) {
+  if (VEC == 8)
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7]) : "memory");
+  else
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3]) : "memory");
+}
+template <int VEC>
 __global__ void __launch_bounds__(256)
 normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
                                       const __grid_constant__ NormParams np) {
-  constexpr int VEC = 4, U = 4;
+  constexpr int U = VEC == 8 ? 2 : 4;  // 64 bytes per thread in flight
   const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t b0 = (uint32_t)((v0 * VEC) % B);
@@ -228,10 +247,7 @@ normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __rest
   for (int l = 0; l < VEC; ++l) { mean[l] = (float)stats[2 * (b0 + l)]; inv[l] = (float)stats[2 * (b0 + l) + 1]; }
   const float gain = np.has_gain ? (float)np.gain : 1.0f, bias = (float)np.bias, gamma = (float)np.gamma;  // v * 1.0f is the identity, bit for bit
   const bool has_bias = np.has_bias != 0;
-  const float4* xv = reinterpret_cast<const float4*>(x);
-  float4* yv = reinterpret_cast<float4*>(y);
-  auto body = [&](float4 a) {
-    float* e = reinterpret_cast<float*>(&a);
+  auto body = [&](float* e) {
 #pragma unroll
     for (int l = 0; l < VEC; ++l) {
       float val = (e[l] - mean[l]) * inv[l];
@@ -240,17 +256,21 @@ normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __rest
       val = val > 0.0f ? val : 0.0f;  // f64::max(v, 0.0): NaN -> 0
       e[l] = pow_nonneg_f32(val, gamma);
     }
-    return a;
   };
   uint64_t v = v0;
   for (; v + (U - 1) * nthr < nvec; v += U * nthr) {
-    float4 a[U];
+    float a[U][VEC];
 #pragma unroll
-    for (int u = 0; u < U; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
+    for (int u = 0; u < U; ++u) ld_stream_f32<VEC>(x + (v + (uint64_t)u * nthr) * VEC, a[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) __stcs(yv + v + (uint64_t)u * nthr, body(a[u]));
+    for (int u = 0; u < U; ++u) { body(a[u]); st_stream_f32<VEC>(y + (v + (uint64_t)u * nthr) * VEC, a[u]); }
   }
-  for (; v < nvec; v += nthr) __stcs(yv + v, body(__ldcs(xv + v)));
+  for (; v < nvec; v += nthr) {
+    float a[VEC];
+    ld_stream_f32<VEC>(x + v * VEC, a);
+    body(a);
+    st_stream_f32<VEC>(y + v * VEC, a);
+  }
 }
 
 template <typename T, int VEC>
@@ -995,8 +1015,13 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
       moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
     }
     moments_finalize_kernel<float><<<(unsigned)B, 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
-    if (fast_blocks && d->clamp_zero && d->has_gamma && (float)d->gamma != 0.0f && !getenv("RUNMAT_B200_NORMALIZE_GENERIC"))
-      normalize_fixed_clampgamma_f32_kernel<<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+    if (fast_blocks && d->clamp_zero && d->has_gamma && (float)d->gamma != 0.0f && !getenv("RUNMAT_B200_NORMALIZE_GENERIC")) {
+      // 256-bit accesses when a thread's 8 lanes stay on fixed images (B % 8 == 0 and the grid stride a multiple of B)
+      if (B % 8 == 0 && total % 8 == 0 && ((uint64_t)fast_blocks * 256ull * 8) % B == 0 && !getenv("RUNMAT_B200_NORMALIZE_VEC4"))
+        normalize_fixed_clampgamma_f32_kernel<8><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+      else
+        normalize_fixed_clampgamma_f32_kernel<4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+    }
     else if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
     else normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
   }
