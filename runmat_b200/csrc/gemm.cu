@@ -328,6 +328,92 @@ rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, co
   return st;
 }
 
+// Skinny-update kernel for the blocked LU (solve.cu): C -= A * B with a 64 x 64 x 16 CTA tile, 8 warps as 2(M) x 4(N) with
+// 32 x 16 warp tiles. The LU's in-block, U12 and back-substitution updates are k = 64 products with a 64..256-wide N: on the
+// 128 x 128 kernel above they fill 30-60 CTAs, each of which is DMMA-bound for 8+ us (a 128 x 128 x 16 step is 2.1 us of one SM's
+// FP64 tensor pipe) and ran at a ~30 us floor (r17 launch list: 181 such launches = 6.4 ms of a 27 ms solve). Quartering the tile
+// spreads the same flops over 4x the SMs. Aligned operands only (even leading dimensions, 16-byte pointers): the caller falls
+// back to the large kernel otherwise.
+constexpr int SBM = 64, SBN = 64;
+constexpr int SLDA_S = SBM + 4;
+constexpr int SA_STAGE = BK * SLDA_S, SB_STAGE = SBN * LDB_S;
+constexpr size_t SGEMM_SMEM = (size_t)STAGES * (SA_STAGE + SB_STAGE) * sizeof(double);
+__global__ void __launch_bounds__(256)
+dgemm_sub_small_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, uint64_t m, uint64_t n, uint64_t k,
+                       uint64_t lda, uint64_t ldb, uint64_t ldc) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;                               // [STAGES][BK][SLDA_S]
+  double* Bs = smem + (size_t)STAGES * SA_STAGE;   // [STAGES][SBN][LDB_S]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  const uint64_t m0 = (uint64_t)blockIdx.x * SBM, n0 = (uint64_t)blockIdx.y * SBN;
+  const uint64_t ktiles = (k + BK - 1) / BK;
+  auto load_stage = [&](int stage, uint64_t kt) {
+    const uint64_t k0 = kt * BK;
+    double* as = As + (size_t)stage * SA_STAGE;
+    double* bs = Bs + (size_t)stage * SB_STAGE;
+#pragma unroll
+    for (int c = tid; c < BK * (SBM / 2); c += 256) {
+      const int kc = c / (SBM / 2), mr = (c % (SBM / 2)) * 2;
+      const uint64_t gi = m0 + mr, gk = k0 + kc;
+      const bool ok = gi < m && gk < k;
+      cp_async16(as + kc * SLDA_S + mr, A + (ok ? gk * lda + gi : 0), ok);
+    }
+#pragma unroll
+    for (int c = tid; c < SBN * (BK / 2); c += 256) {
+      const int nc = c / (BK / 2), kr = (c % (BK / 2)) * 2;
+      const uint64_t gj = n0 + nc, gk = k0 + kr;
+      const bool ok = gj < n && gk < k;
+      cp_async16(bs + nc * LDB_S + kr, B + (ok ? gj * ldb + gk : 0), ok);
+    }
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if ((uint64_t)s < ktiles) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (uint64_t kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const uint64_t next = kt + STAGES - 1;
+    if (next < ktiles) load_stage((int)(next % STAGES), next);
+    cp_async_commit();
+    const double* as = As + (size_t)(kt % STAGES) * SA_STAGE;
+    const double* bs = Bs + (size_t)(kt % STAGES) * SB_STAGE;
+#pragma unroll
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = as[(k4 + t) * SLDA_S + wm + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bf[j] = bs[(wn + j * 8 + g) * LDB_S + k4 + t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t row = m0 + wm + i * 8 + g;
+    if (row >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const uint64_t col = n0 + wn + j * 8 + 2 * t + e;
+        if (col < n) C[row + col * ldc] -= acc[i][j][e];
+      }
+  }
+}
+
 // C (ldc) -= A (lda) * B (ldb) on sub-matrices of column-major storage: the GEMM core of mldivide's blocked LU / solves.
 rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const double* B, uint64_t ldb, double* C, uint64_t ldc,
                             uint64_t m, uint64_t n, uint64_t k, cudaStream_t stream) {
@@ -338,7 +424,12 @@ rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const
   dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN));
   RM_REQUIRE(grid.y <= 65535, RM_UNSUPPORTED, "gemm update: n too large");
   const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A) % 16 == 0) && (((uintptr_t)B) % 16 == 0);
-  if (aligned) {
+  if (aligned && (uint64_t)grid.x * grid.y < 2ull * (uint64_t)p->prop.multiProcessorCount && !getenv("RUNMAT_B200_LU_NO_SMALL_GEMM")) {
+    // too few 128 x 128 tiles to fill the SMs: the 64 x 64 kernel
+    dim3 sgrid((unsigned)((m + SBM - 1) / SBM), (unsigned)((n + SBN - 1) / SBN));
+    cudaFuncSetAttribute(dgemm_sub_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGEMM_SMEM);
+    dgemm_sub_small_kernel<<<sgrid, 256, SGEMM_SMEM, stream>>>(A, B, C, m, n, k, lda, ldb, ldc);
+  } else if (aligned) {
     cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     dgemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, stream>>>(A, B, C, m, n, k, lda, ldb, ldc, 1, ep, OzGuard{});
   } else {

@@ -96,7 +96,13 @@ __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, 
 
 // One thread per Box-Muller pair of the GLOBAL path vector. `first_pair` is the global index of this
 // launch's first pair; local element e_local = e_global - path_offset.
-template <typename T, bool LEAN>
+// SUMLOG: S_T = S_0 * exp(sum_t term_t) with ONE exponential at the end instead of S *= exp(term_t) every step. Same quantity; the
+// two roundings differ by ~sqrt(T) ulp (2e-15 at T = 256, the host's own product carries as much), far inside the 1e-10 parity
+// bar, and it removes 2 exps = 34 of the ~98 FP64 instructions per pair-step from an FP64-pipe-bound kernel (r24 ncu:
+// math_pipe_throttle is the top stall). Only taken when no partial product can overflow or underflow (the host decides from
+// T * (|drift| + 8.6 |scale|) < 600; 8.57 = the largest |z| a 53-bit Box-Muller uniform can produce), so Inf / 0 / NaN patterns of
+// the per-step product cannot differ; otherwise, or with RUNMAT_B200_MC_STEPWISE=1, the per-step form runs.
+template <typename T, bool LEAN, bool SUMLOG>
 __global__ void __launch_bounds__(256)
 evolve_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t len, uint64_t path_offset, uint64_t first_pair,
               uint64_t n_pairs, uint64_t state0, uint64_t step_mult, uint64_t step_plus, double drift, double scale, uint32_t steps) {
@@ -109,15 +115,22 @@ evolve_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t len, uint6
   double s0v = has0 ? (double)in[e0 - path_offset] : 0.0;
   double s1v = has1 ? (double)in[e1 - path_offset] : 0.0;
   uint64_t s = lcg_advance(state0, 2 * pair);  // before (u1,u2) of step 0 for this pair
+  double a0 = 0.0, a1 = 0.0;
   for (uint32_t t = 0; t < steps; ++t) {
     uint64_t s2 = s;
     double z0, z1;
     box_muller<LEAN>(s2, z0, z1);
     // stochastic_evolution.rs:25-27: term = drift + scale*noise; value *= exp(term)   (no FMA: -fmad=false)
-    s0v *= mc_exp<LEAN>(drift + scale * z0);
-    s1v *= mc_exp<LEAN>(drift + scale * z1);
+    if (SUMLOG) {
+      a0 += drift + scale * z0;
+      a1 += drift + scale * z1;
+    } else {
+      s0v *= mc_exp<LEAN>(drift + scale * z0);
+      s1v *= mc_exp<LEAN>(drift + scale * z1);
+    }
     s = step_mult * s + step_plus;  // one whole pass (2*ceil(global_len/2) draws) ahead
   }
+  if (SUMLOG) { s0v *= exp(a0); s1v *= exp(a1); }
   if (has0) out[e0 - path_offset] = (T)s0v;
   if (has1) out[e1 - path_offset] = (T)s1v;
 }
@@ -148,10 +161,13 @@ rm_status evolve(rm_provider* p, const rm_handle* state, double drift, double sc
   const uint64_t last_pair = (path_offset + len - 1) / 2;
   const uint64_t n_pairs = last_pair - first_pair + 1;
   const unsigned blocks = (unsigned)((n_pairs + 255) / 256);
-  if (p->precision == RM_F64)
-    (mc_lean() ? evolve_kernel<double, true> : evolve_kernel<double, false>)<<<blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps);
-  else
-    (mc_lean() ? evolve_kernel<float, true> : evolve_kernel<float, false>)<<<blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps);
+  const bool lean = mc_lean();
+  const double span = (double)steps * (fabs(drift) + 8.6 * fabs(scale));
+  const bool sumlog = lean && span < 600.0 && !getenv("RUNMAT_B200_MC_STEPWISE");  // NaN / Inf parameters fail the comparison -> per-step form
+#define RM_EVOLVE(TT, L, SL) evolve_kernel<TT, L, SL><<<blocks, 256, 0, p->stream>>>((const TT*)src, (TT*)dst, len, path_offset, first_pair, n_pairs, state0, sm, sp, drift, scale, steps)
+  if (p->precision == RM_F64) { if (sumlog) RM_EVOLVE(double, true, true); else if (lean) RM_EVOLVE(double, true, false); else RM_EVOLVE(double, false, false); }
+  else { if (sumlog) RM_EVOLVE(float, true, true); else if (lean) RM_EVOLVE(float, true, false); else RM_EVOLVE(float, false, false); }
+#undef RM_EVOLVE
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "stochastic_evolution launch failed: %s", cudaGetErrorString(e)); }
   count_launch(p);

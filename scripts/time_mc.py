@@ -6,8 +6,8 @@ p = B200Provider(0)
 M, T = 100_000_000, 256
 h = p.fill((M, 1), 100.0)
 res = {}
-for name, env in (("lean", {}), ("libm", {"RUNMAT_B200_MC_LIBM": "1"})):
-    os.environ.pop("RUNMAT_B200_MC_LIBM", None)
+for name, env in (("lean", {}), ("lean stepwise", {"RUNMAT_B200_MC_STEPWISE": "1"}), ("libm", {"RUNMAT_B200_MC_LIBM": "1"})):
+    os.environ.pop("RUNMAT_B200_MC_LIBM", None); os.environ.pop("RUNMAT_B200_MC_STEPWISE", None)
     os.environ.update(env)
     p.set_rng_state(42)
     p.free(p.stochastic_evolution(h, 0.0001, 0.0126, 4))
@@ -18,5 +18,6 @@ for name, env in (("lean", {}), ("libm", {"RUNMAT_B200_MC_LIBM": "1"})):
     res[name] = x
     print(f"{name}: {ms:.2f} ms  {M * T / ms / 1e6:.1f} G path-steps/s  mean {x.mean():.6f}")
     p.free(out)
-d = np.abs(res["lean"] - res["libm"]) / np.abs(res["libm"])
-print(f"lean vs libm on the first 200000 paths: max rel diff {d.max():.3e}")
+for a in ("lean", "lean stepwise"):
+    d = np.abs(res[a] - res["libm"]) / np.abs(res["libm"])
+    print(f"{a} vs libm on the first 200000 paths: max rel diff {d.max():.3e}")

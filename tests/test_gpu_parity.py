@@ -1088,6 +1088,34 @@ def test_stochastic_evolution_vs_host(prov, orc, n, steps):
     assert prov.get_rng_state() == new_state
 
 
+def test_stochastic_evolution_forms_and_extremes(prov, orc, monkeypatch):
+    """The kernel sums the log-returns and exponentiates once when no partial product can leave the f64 range, and multiplies step
+    by step (the host's form) otherwise: both forms, the lean and the library math, 256 steps, against the host oracle at 1e-10; a
+    drift / scale that overflows must reproduce the host's Inf / 0 pattern."""
+    drift, scale = (0.05 - 0.5 * 0.2 ** 2) / 252.0, 0.2 * math.sqrt(1.0 / 252.0)
+    s0 = np.linspace(50.0, 150.0, 3001).reshape(-1, 1)
+    want, _ = orc.stochastic_evolution(4242, s0, drift, scale, 256)
+    for env in ({}, {"RUNMAT_B200_MC_STEPWISE": "1"}, {"RUNMAT_B200_MC_LIBM": "1"}):
+        for k in ("RUNMAT_B200_MC_STEPWISE", "RUNMAT_B200_MC_LIBM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        prov.set_rng_state(4242)
+        got = prov.download(prov.stochastic_evolution(prov.upload(s0), drift, scale, 256))
+        close(got, want, rtol=1e-10, atol=0)
+    for k in ("RUNMAT_B200_MC_STEPWISE", "RUNMAT_B200_MC_LIBM"):
+        monkeypatch.delenv(k, raising=False)
+    # products that overflow / underflow on the way: span = steps * (|drift| + 8.6 |scale|) >= 600 selects the per-step form
+    for d_, sc_, steps in ((40.0, 1.0, 20), (-40.0, 1.0, 20), (0.0, 60.0, 30)):
+        s1 = np.array([[1.0], [2.0], [1e-300], [-3.0]])
+        prov.set_rng_state(99)
+        got = prov.download(prov.stochastic_evolution(prov.upload(s1), d_, sc_, steps))
+        want1, _ = orc.stochastic_evolution(99, s1, d_, sc_, steps)
+        assert np.array_equal(np.isinf(got), np.isinf(want1)) and np.array_equal(got == 0, want1 == 0) and np.array_equal(np.isnan(got), np.isnan(want1))
+        fin = np.isfinite(want1) & (want1 != 0)
+        assert np.all(np.abs(got[fin] - want1[fin]) <= 1e-9 * np.abs(want1[fin]))
+
+
 def test_stochastic_evolution_sharding_is_invariant(prov, orc):
     """Union of shards == single-GPU run, bit for bit."""
     n, steps = 10001, 12
