@@ -682,11 +682,11 @@ def extra_workloads(p, ex, rank, world, local_rank, dist, torch):
 
 
 # FP64 arithmetic instructions (DFMA + DMUL + DADD, thread-level, predicated-on) evolve_kernel executes per path-step, MEASURED
-# with ncu's SASS opcode counters on the 1e8 x 256 run (profiles/r24_summary.md, r24_gemm_mc.ncu-rep, evolve_kernel<double, lean>:
-# 4129.1 + 1501.5 + 500.5 thread-instr/clk over 104.19 ms at 1.9637 GHz = 1.254e12 instructions / 2.56e10 path-steps; the
-# library-math kernel of round 1 executed 48.5). It is the dynamic count of 1/2 (log + sqrt + sincos) + exp + the state update;
-# the pipe issues 64 such instructions per SM per clock.
-MC_FP64_INSTR_PER_PATH_STEP = 49.0
+# with ncu's SASS opcode counters on the 1e8 x 256 run (profiles/r34_summary.md, r34_gemm_mc.ncu-rep, evolve_kernel<double, lean,
+# sum-of-log-returns>: 3351.3 + 1671.5 + 880.1 thread-instr/clk over 74.17 ms at 1.9624 GHz = 8.59e11 instructions / 2.56e10
+# path-steps; the per-step-exp lean kernel executed 49.0, the library-math kernel of round 1 48.5). It is the dynamic count of
+# 1/2 (log + sqrt + sincos) + the state update; the pipe issues 64 such instructions per SM per clock.
+MC_FP64_INSTR_PER_PATH_STEP = 33.6
 
 
 def image_batch_leg(p, rank, world, local_rank, dist, torch, peak_hbm):

@@ -336,6 +336,11 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 int red_unroll() { return env_int("RUNMAT_B200_RED_UNROLL", 2, 1, 8); }
 // 4 resident CTAs/SM (<= 64 registers) + two independent accumulators: 49.2 us vs 53.9 us for the r01 structure on the headline
 // reduction (profiles/r04_harness_results.txt: occupancy is the lever, a third/fourth accumulator costs registers and loses)
+// Contig reductions sweep their input from the END to the front. The elementwise kernels sweep front to end, so in the common
+// sequence "C = f(A, B); s = sum(g(A, B))" (the benchmark's step) the reduction starts on the ~40 % of A and B that the previous
+// kernel left in the 126 MB L2, and it finishes at the front, where the next forward sweep starts. Any fixed order is
+// deterministic; RUNMAT_B200_RED_FORWARD=1 restores the forward sweep.
+int red_reverse() { return env_int("RUNMAT_B200_RED_FORWARD", 0, 0, 1) ? 0 : 1; }
 int red_minblocks() { return env_int("RUNMAT_B200_RED_MINB", 4, 0, 8); }
 
 std::string input_params(uint32_t n_inputs) {
@@ -511,6 +516,7 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
   if (layout == RedLayout::Contig) {
     // slice s occupies [s*len, (s+1)*len). grid = (blocks_per_slice, num_slices).
     o << "#define RED_U " << red_unroll() << "\n";
+    o << "#define RED_IDX(j) (" << (red_reverse() ? "(nvec - 1 - (j))" : "(j)") << ")\n";
     if (red_minblocks() > 0) o << "extern \"C\" __global__ void __launch_bounds__(256, " << red_minblocks() << ") rm_fused_red(";
     else o << "extern \"C\" __global__ void __launch_bounds__(256) rm_fused_red(";
     o << input_params(ni)
@@ -530,13 +536,13 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
       o << "    vec_t a" << k << "[RED_U];\n";
     }
     o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n";
-    for (uint32_t k = 0; k < ni; ++k) o << "      a" << k << "[u] = ldv(in" << k << " + base + (i + (u64)u * nthr) * VEC);\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "      a" << k << "[u] = ldv(in" << k << " + base + RED_IDX(i + (u64)u * nthr) * VEC);\n";
     o << "    }\n";
     o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n      #pragma unroll\n      for (int l = 0; l < VEC; ++l) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = a" << k << "[u].x[l];\n";
     o << "        if (l & 1) accumulate(acc1, " << prog.val_expr << "); else accumulate(acc0, " << prog.val_expr << ");\n      }\n    }\n  }\n";
     o << "  for (; i < nvec; i += nthr) {\n";
-    for (uint32_t k = 0; k < ni; ++k) o << "    const vec_t a" << k << " = ldv(in" << k << " + base + i * VEC);\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "    const vec_t a" << k << " = ldv(in" << k << " + base + RED_IDX(i) * VEC);\n";
     o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = a" << k << ".x[l];\n";
     o << "      if (l & 1) accumulate(acc1, " << prog.val_expr << "); else accumulate(acc0, " << prog.val_expr << ");\n    }\n  }\n";
