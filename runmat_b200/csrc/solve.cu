@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 
 #include "common.h"
+#include "lu_panel_push.h"
 
 namespace cg = cooperative_groups;
 
@@ -134,11 +135,8 @@ lu_panel_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, i
 // pivot search result and the two exchanged rows cross CTAs (global scratch + grid.sync): 2 grid syncs per column and
 // no dependent L2 round trips in the update (the first version spent ~6 us per column waiting on them).
 constexpr int SLAB_ROWS = 256;
-struct RowMoves {
-  uint32_t count;
-  unsigned long long dst[2 * NB];
-  unsigned long long src[2 * NB];
-};
+// RowMoves (net row permutation of a panel) lives in lu_panel_push.h, shared with the register-resident cluster kernel.
+static_assert(NB == LU_NB, "panel width");
 // Per-CTA candidate published before the (single) grid.sync of a column: local max |a(r,c)|, its row, that row's panel
 // values, and — from the CTA that owns row c — row c itself (it moves to the pivot's position).
 struct Candidate {
@@ -706,6 +704,23 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     }
     cudaGetLastError();
   }
+  // register-resident push kernel (lu_panel_push.h): the default whenever a full 64-column panel fits one cluster
+  unsigned push_cluster_max = 0;
+  if (cluster_max && !getenv("RUNMAT_B200_LU_PANEL_V1")) {
+    cudaFuncSetAttribute(lupush::lu_panel_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lupush::Smem));
+    cudaFuncSetAttribute(lupush::lu_panel_push_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (unsigned cs = 16; cs >= 1 && !push_cluster_max; cs >>= 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs); cfg.blockDim = dim3(lupush::ROWS); cfg.dynamicSmemBytes = sizeof(lupush::Smem); cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, lupush::lu_panel_push_kernel, &cfg) == cudaSuccess && nc >= 1) push_cluster_max = cs;
+    }
+    cudaGetLastError();
+  }
   int slab_blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slab_blocks_per_sm, lu_panel_smem_kernel<false>, SLAB_ROWS, SLAB_SMEM);
   const unsigned slab_max_grid = (unsigned)std::max(0, slab_blocks_per_sm) * (unsigned)p->prop.multiProcessorCount;
@@ -776,7 +791,15 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
       const unsigned slab_grid = (unsigned)((m + SLAB_ROWS - 1) / SLAB_ROWS);
       unsigned cl = 1;
       while (cl < slab_grid) cl <<= 1;
-      if (cl <= cluster_max && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+      if (jb == NB && cl <= push_cluster_max && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cl); cfg.blockDim = dim3(lupush::ROWS); cfg.dynamicSmemBytes = sizeof(lupush::Smem); cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        loop_err = cudaLaunchKernelEx(&cfg, lupush::lu_panel_push_kernel, LU, lda, nn, jj, ipiv, info, pivmm, mv);
+      } else if (cl <= cluster_max && !getenv("RUNMAT_B200_LU_GLOBAL_PANEL")) {
         // whole panel inside one thread-block cluster (grid rounded up to a power of two; surplus CTAs own no rows)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cl); cfg.blockDim = dim3(SLAB_ROWS); cfg.dynamicSmemBytes = SLAB_SMEM; cfg.stream = st;
@@ -854,6 +877,7 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   p->host_syncs.fetch_add(1, std::memory_order_relaxed);
   double amaxv;
   memcpy(&amaxv, &h_amax, 8);
+  if (h_info[0] == lupush::INFO_TIMEOUT) { cleanup(true); return fail(RM_ERROR, "mldivide: the panel kernel's cluster exchange timed out (device protocol failure)"); }
   if (h_info[1]) { cleanup(true); return fail(RM_UNSUPPORTED, "mldivide: non-finite input not supported by provider"); }
   if (h_info[0] || !(h_mm[0] > (double)n * 2.220446049250313e-16 * amaxv)) {
     cleanup(true);
