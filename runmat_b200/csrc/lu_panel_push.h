@@ -12,6 +12,10 @@
 //   * the exchange is `st.async ... mbarrier::complete_tx::bytes` (SASS: STAS.128): every CTA PUSHES {|candidate| key, row id,
 //     candidate row[c..64)} into a mailbox in EVERY peer's shared memory and each peer's mbarrier counts the bytes; a CTA waits
 //     (mbarrier.try_wait, hardware sleep) on its own barrier only -- one one-way DSMEM latency per column, no fences, no remote loads;
+//   * the 64 columns are factored in 8-column blocks with DELAYED updates: inside a block a column step only exchanges and updates
+//     the block's own <= 8 columns (a 64-byte row per CTA); the winner of each column pushes its whole (stale) register window once,
+//     off the critical path, and at the block end every thread folds the 8 pivot rows into its trailing columns with a rank-8
+//     update whose multipliers are corrected by the block's 8 x 8 unit-lower factor (l' L = l), so the stale rows need no fix-up;
 //   * pivoting is IMPLICIT: rows never move between threads. The winner's thread just stops updating (its registers now hold the
 //     U row); the LAPACK swap sequence is replayed on 64-entry position tables after the column loop and only decides WHERE each
 //     thread writes its row back, plus the net (dst <- src) move list the other columns are permuted with.
@@ -38,18 +42,19 @@ constexpr int INFO_SINGULAR = 1, INFO_TIMEOUT = 3;
 
 struct __align__(16) Smem {
   double slab[ROWS][NB + 1];               // finished columns of every local row (written once per 8-column block; +1: conflict-free)
-  double pad_;                             // keeps mb_row 16-byte aligned (ROWS*(NB+1) is even, so this is only a guard for edits)
-  double pad2_;
-  double mb_row[2][MAXC][NB];              // [column parity][sender][window-relative column]: candidate rows pushed by every CTA
-  unsigned long long mb_meta[2][MAXC][2];  // {key, row}
-  double stage[NB];                        // the local candidate's register window, staged by its owner thread for the push
+  double pad_[2];                          // keeps the mailboxes 16-byte aligned
+  double mb_row[2][MAXC][BLK];             // [column parity][sender]: in-block window of every CTA's candidate row
+  unsigned long long mb_meta[2][MAXC][4];  // {key, row, bits of 1/candidate, -}
+  double tr_row[2][BLK][NB];               // [block parity][pivot k of the block]: the winner's whole register window at the time it won
+  double stage[BLK];                       // the local candidate's in-block window, staged by its owner thread for the push
+  double tstage[NB];                       // a winner's whole window, staged for the deferred push
   unsigned long long wkey[2][ROWS / 32];   // per-warp candidates of the next column
+  unsigned long long wrcp[2][ROWS / 32];
   unsigned wrow[2][ROWS / 32];
-  unsigned long long bar[2];               // mbarriers, one per column parity
+  unsigned long long bar[2];               // mbarriers: in-block exchange, one per column parity
+  unsigned long long tbar[2];              //            winners' windows, one per block parity
   unsigned long long piv_key[NB];          // replay input: key and original row of every pivot
   unsigned piv_home[NB];
-  unsigned cur[NB], inv[NB];               // replay: current position of original row d < NB; original row at position c < NB
-  unsigned char was_pivot[NB];
   unsigned fin[ROWS];                      // final panel-local position of every local row
   int abort_flag;
 };
@@ -65,12 +70,31 @@ __device__ __forceinline__ void st_async16(uint32_t remote, unsigned long long a
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote), "l"(a), "l"(b), "r"(remote_bar)
                : "memory");
 }
-__device__ __forceinline__ void argmax3(unsigned long long& key, unsigned& row) {  // max key, ties -> smallest row; result in every lane
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait on one of OUR barriers; a protocol failure raises info and makes every later wait of this CTA fall through
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, int* abort_flag, int* info) {
+  if (*(volatile int*)abort_flag) return;
+  const uint32_t b = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 200000000LL) { *(volatile int*)abort_flag = 1; atomicExch(info, INFO_TIMEOUT); return; }
+  }
+}
+__device__ __forceinline__ unsigned long long max_u64(unsigned long long key) {  // warp-wide, result in every lane
   const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
   const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
   const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-  row = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? row : 0xffffffffu);
-  key = ((unsigned long long)mh << 32) | ml;
+  return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ void argmax3(unsigned long long& key, unsigned& row) {  // max key, ties -> smallest row; result in every lane
+  const unsigned long long mine = key;
+  key = max_u64(key);
+  row = __reduce_min_sync(0xffffffffu, mine == key ? row : 0xffffffffu);
 }
 // order-preserving key of |v| for a live row: 0 = no candidate, 1 = zero or NaN (never preferred over a real value)
 __device__ __forceinline__ unsigned long long cand_key(double v, bool live) {
@@ -79,7 +103,7 @@ __device__ __forceinline__ unsigned long long cand_key(double v, bool live) {
 }
 
 // One cluster = the whole grid (gridDim.x = cluster size <= 16, a power of two >= ceil((n - j0) / 256)); exactly NB columns.
-// info[0]: INFO_SINGULAR when a pivot is exactly zero, INFO_TIMEOUT when the bounded mailbox wait expired (protocol failure: the
+// info[0]: INFO_SINGULAR when a pivot is exactly zero, INFO_TIMEOUT when a bounded mailbox wait expired (protocol failure: the
 // host turns it into an error; later panels return at once). piv_minmax: running min / max |pivot| for the conditioning gate.
 __global__ void __launch_bounds__(ROWS, 1)
 lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t j0, unsigned long long* __restrict__ ipiv, int* __restrict__ info,
@@ -98,142 +122,229 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
 #pragma unroll
   for (int e = 0; e < NB; ++e) a[e] = valid ? P[r + (uint64_t)e * lda] : 0.0;
   S.fin[tid] = r;
-  if (tid < NB) { S.cur[tid] = tid; S.inv[tid] = tid; S.was_pivot[tid] = 0; }
   if (tid == 0) {
     S.abort_flag = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.bar[0])) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.bar[1])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.tbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.tbar[1])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  bool live = valid;
+  int died = valid ? NB : -1;  // column at which this row became a pivot row (NB: still live, -1: no row)
+  int tpush = -1;              // warp-uniform: block-relative column this warp's thread `tlane` won and has not yet pushed its window for
+  int tlane = 0;
   {  // per-warp candidates of column 0
-    unsigned long long key = cand_key(a[0], live);
+    const double rc = 1.0 / a[0];
+    unsigned long long key = cand_key(a[0], valid);
+    const unsigned long long mine = key;
     unsigned row = r;
     argmax3(key, row);
-    if (lane == 0) { S.wkey[0][warp] = key; S.wrow[0][warp] = row; }
+    if (row == r && mine == key) { S.wkey[0][warp] = key; S.wrow[0][warp] = row; S.wrcp[0][warp] = (unsigned long long)__double_as_longlong(rc); }
+    if (lane == 0 && key == 0ull) { S.wkey[0][warp] = 0ull; S.wrow[0][warp] = 0xffffffffu; S.wrcp[0][warp] = 0ull; }
   }
   cooperative_groups::this_cluster().sync();  // barriers initialised everywhere before the first push; also the block barrier for wkey
 
   for (int b = 0; b < NB / BLK; ++b) {
     const int len = NB - BLK * b;  // live width of the register window
+    const int bp = b & 1;
+    const unsigned tparity = (unsigned)(b >> 1) & 1u;
+    const bool trailing = len > BLK;
+    if (tid == 0 && trailing) mbar_expect(&S.tbar[bp], (unsigned)(BLK * 8 * len));  // 8 winners x their whole window
 #pragma unroll
     for (int k = 0; k < BLK; ++k) {
       const int c = BLK * b + k;
       const int buf = k & 1;
       const unsigned parity = (unsigned)(k >> 1) & 1u;  // use index of bar[buf] is c >> 1 = 4*b + (k >> 1)
-      const int e_lo = k & ~1;                          // first window column that travels (even: 16-byte units)
+      const int e_lo = k & ~1;                          // first in-block column that travels (even: 16-byte units)
+      const int npairs = (BLK - e_lo) / 2;
       // ---- (1) this CTA's candidate: fold the 8 warp candidates (every warp, redundantly) ----
       unsigned long long lkey = lane < ROWS / 32 ? S.wkey[buf][lane] : 0ull;
       unsigned lrow = lane < ROWS / 32 ? S.wrow[buf][lane] : 0xffffffffu;
+      const unsigned long long lrcp_mine = lane < ROWS / 32 ? S.wrcp[buf][lane] : 0ull;
       argmax3(lkey, lrow);
       const unsigned lp = lkey ? lrow - base : 0u;  // owner thread of the candidate row (thread 0 sends a never-winning dummy otherwise)
-      if (tid == 0) {
-        const unsigned bytes = nblk * (16u + 8u * (unsigned)(len - e_lo));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.bar[buf])), "r"(bytes) : "memory");
-      }
-      // ---- (2) the owner's warp pushes {key, row, window[e_lo, len)} into every CTA's mailbox (its own included) ----
+      if (tid == 0) mbar_expect(&S.bar[buf], nblk * (32u + 16u * (unsigned)npairs));
+      // ---- (2) the owner's warp pushes {key, row, 1/candidate, window[e_lo, 8)} into every CTA's mailbox (its own included) ----
       if (warp == (int)(lp >> 5)) {
+        const unsigned long long lrcp = __shfl_sync(0xffffffffu, lrcp_mine, (int)(lp >> 5));  // the owner's warp slot holds its reciprocal
         if (lane == (int)(lp & 31)) {
 #pragma unroll
-          for (int e = e_lo; e < NB; e += 2)
-            if (e < len) *reinterpret_cast<double2*>(&S.stage[e]) = make_double2(a[e], a[e + 1]);
+          for (int e = e_lo; e < BLK; e += 2) *reinterpret_cast<double2*>(&S.stage[e]) = make_double2(a[e], a[e + 1]);
         }
         __syncwarp();
-        const int e0 = 2 * lane;
-        if (e0 >= e_lo && e0 < len) {
-          const double2 v = *reinterpret_cast<const double2*>(&S.stage[e0]);
-          const uint32_t dst = smem_u32(&S.mb_row[buf][me][e0]), bar = smem_u32(&S.bar[buf]);
-          for (unsigned pr = 0; pr < nblk; ++pr)
-            st_async16(mapa(dst, pr), (unsigned long long)__double_as_longlong(v.x), (unsigned long long)__double_as_longlong(v.y), mapa(bar, pr));
+        const unsigned pr = (unsigned)lane & 15u;
+        if (pr < nblk) {
+          const uint32_t rbar = mapa(smem_u32(&S.bar[buf]), pr);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int pair = (lane >> 4) + 2 * q;  // 0 .. 3
+            if (2 * pair >= e_lo) {
+              const double2 v = *reinterpret_cast<const double2*>(&S.stage[2 * pair]);
+              st_async16(mapa(smem_u32(&S.mb_row[buf][me][2 * pair]), pr), (unsigned long long)__double_as_longlong(v.x),
+                         (unsigned long long)__double_as_longlong(v.y), rbar);
+            }
+          }
+          if (lane < 16) st_async16(mapa(smem_u32(&S.mb_meta[buf][me][0]), pr), lkey, (unsigned long long)(lkey ? lrow : 0xffffffffu), rbar);
+          else st_async16(mapa(smem_u32(&S.mb_meta[buf][me][2]), pr), lrcp, 0ull, rbar);
         }
-        if ((unsigned)lane < nblk)
-          st_async16(mapa(smem_u32(&S.mb_meta[buf][me][0]), lane), lkey, (unsigned long long)(lkey ? lrow : 0xffffffffu), mapa(smem_u32(&S.bar[buf]), lane));
+      }
+      // ---- (2b) deferred: the warp that holds the previous column's winner ships that row's whole window (needed at the block end) ----
+      if (tpush >= 0) {
+        if (lane == tlane) {
+#pragma unroll
+          for (int e = 0; e < NB; e += 2)
+            if (e < len) *reinterpret_cast<double2*>(&S.tstage[e]) = make_double2(a[e], a[e + 1]);
+        }
+        __syncwarp();
+        if (2 * lane < len) {
+          const double2 v = *reinterpret_cast<const double2*>(&S.tstage[2 * lane]);
+          const uint32_t dst = smem_u32(&S.tr_row[bp][tpush][2 * lane]), tb = smem_u32(&S.tbar[bp]);
+          for (unsigned pr = 0; pr < nblk; ++pr)
+            st_async16(mapa(dst, pr), (unsigned long long)__double_as_longlong(v.x), (unsigned long long)__double_as_longlong(v.y), mapa(tb, pr));
+        }
+        tpush = -1;
       }
       // ---- (3) wait until every peer's push has landed in OUR shared memory (bounded) ----
-      if (!*(volatile int*)&S.abort_flag) {
-        const uint32_t bar = smem_u32(&S.bar[buf]);
-        const long long t0 = clock64();
-        for (;;) {
-          uint32_t ok;
-          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-          if (ok) break;
-          if (clock64() - t0 > 200000000LL) { S.abort_flag = 1; atomicExch(info, INFO_TIMEOUT); break; }
-        }
-      }
+      mbar_wait(&S.bar[buf], parity, &S.abort_flag, info);
       // ---- (4) global pivot (every warp, redundantly) ----
       unsigned long long gkey = (unsigned)lane < nblk ? S.mb_meta[buf][lane][0] : 0ull;
       unsigned grow = (unsigned)lane < nblk ? (unsigned)S.mb_meta[buf][lane][1] : 0xffffffffu;
       argmax3(gkey, grow);
       if (grow >= nblk * ROWS) grow = 0;  // only after a protocol failure; keeps the mailbox index in bounds
-      const double* prow = S.mb_row[buf][grow / ROWS];
-      if (r == grow) live = false;  // this thread's registers now hold row c of U (and its L part)
+      const unsigned gb = grow / ROWS;
+      const double* prow = S.mb_row[buf][gb];
+      const double rp = __longlong_as_double((long long)S.mb_meta[buf][gb][2]);
+      if (r == grow) died = c;  // this thread's registers now hold row c of U (and its L part)
+      if (trailing && gb == me && warp == (int)((grow - base) >> 5)) { tpush = k; tlane = (int)((grow - base) & 31); }
       if (tid == 0) { S.piv_key[c] = gkey; S.piv_home[c] = grow; }
-      // ---- (5) rank-1 update of the live rows, all in registers ----
-      const double pv = prow[k];
-      if (live && pv != 0.0) {
-        const double l = a[k] * (1.0 / pv);
+      const bool live = died == NB;
+      // ---- (5) rank-1 update of the live rows inside the block, all in registers ----
+      if (live && gkey > 1ull) {
+        const double l = a[k] * rp;
         a[k] = l;
 #pragma unroll
-        for (int j = (k + 1) / 2; j < NB / 2; ++j) {
-          if (2 * j < len) {
-            const double2 u = *reinterpret_cast<const double2*>(&prow[2 * j]);
-            if (2 * j > k) a[2 * j] = fma(-l, u.x, a[2 * j]);
-            a[2 * j + 1] = fma(-l, u.y, a[2 * j + 1]);
-          }
+        for (int j = (k + 1) / 2; j < BLK / 2; ++j) {
+          const double2 u = *reinterpret_cast<const double2*>(&prow[2 * j]);
+          if (2 * j > k) a[2 * j] = fma(-l, u.x, a[2 * j]);
+          a[2 * j + 1] = fma(-l, u.y, a[2 * j + 1]);
         }
       }
-      // ---- (6) block end: park the 8 finished columns, shift the window ----
+      // ---- (6) block end: fold the block's 8 pivot rows into the trailing columns, park the finished columns, shift the window ----
       if (k == BLK - 1) {
+        if (trailing) {
+          if (tpush >= 0) {  // the last winner cannot defer
+            if (lane == tlane) {
+#pragma unroll
+              for (int e = 0; e < NB; e += 2)
+                if (e < len) *reinterpret_cast<double2*>(&S.tstage[e]) = make_double2(a[e], a[e + 1]);
+            }
+            __syncwarp();
+            if (2 * lane < len) {
+              const double2 v = *reinterpret_cast<const double2*>(&S.tstage[2 * lane]);
+              const uint32_t dst = smem_u32(&S.tr_row[bp][tpush][2 * lane]), tb = smem_u32(&S.tbar[bp]);
+              for (unsigned pr = 0; pr < nblk; ++pr)
+                st_async16(mapa(dst, pr), (unsigned long long)__double_as_longlong(v.x), (unsigned long long)__double_as_longlong(v.y), mapa(tb, pr));
+            }
+            tpush = -1;
+          }
+          mbar_wait(&S.tbar[bp], tparity, &S.abort_flag, info);
+        }
 #pragma unroll
         for (int e = 0; e < BLK; ++e) S.slab[tid][BLK * b + e] = a[e];
+        if (trailing && died >= BLK * b) {
+          // multipliers of this row against the block's pivots (a row that became pivot j of the block only has j of them), corrected
+          // for the fact that the pivot rows in tr_row are STALE (no update of this block applied): l' L = l, L = the block's
+          // unit-lower factor = the winners' own in-block multipliers tr_row[.][i][j], i > j.
+          const int nmul = died - BLK * b;  // >= 8 for a live row
+#pragma unroll
+          for (int e = 0; e < BLK; ++e) if (e >= nmul) a[e] = 0.0;
+#pragma unroll
+          for (int j = BLK - 2; j >= 0; --j) {
+#pragma unroll
+            for (int i = j + 1; i < BLK; ++i) a[j] = fma(-a[i], S.tr_row[bp][i][j], a[j]);
+          }
+#pragma unroll
+          for (int t = BLK / 2; t < NB / 2; ++t) {
+            if (2 * t < len) {
+#pragma unroll
+              for (int j = 0; j < BLK; ++j) {
+                const double2 u = *reinterpret_cast<const double2*>(&S.tr_row[bp][j][2 * t]);
+                a[2 * t] = fma(-a[j], u.x, a[2 * t]);
+                a[2 * t + 1] = fma(-a[j], u.y, a[2 * t + 1]);
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int e = 0; e < NB - BLK; ++e) a[e] = a[e + BLK];
 #pragma unroll
         for (int e = NB - BLK; e < NB; ++e) a[e] = 0.0;
       }
-      // ---- (7) per-warp candidates of the next column ----
+      // ---- (7) per-warp candidates of the next column (with the reciprocal its winner will be divided by) ----
       {
-        unsigned long long key = cand_key(a[(k + 1) & (BLK - 1)], live);
+        const double v = a[(k + 1) & (BLK - 1)];
+        const double rc = 1.0 / v;
+        unsigned long long key = cand_key(v, live);
+        const unsigned long long mine = key;
         unsigned row = r;
         argmax3(key, row);
-        if (lane == 0) { S.wkey[buf ^ 1][warp] = key; S.wrow[buf ^ 1][warp] = row; }
+        if (row == r && mine == key) { S.wkey[buf ^ 1][warp] = key; S.wrow[buf ^ 1][warp] = row; S.wrcp[buf ^ 1][warp] = (unsigned long long)__double_as_longlong(rc); }
+        if (lane == 0 && key == 0ull) { S.wkey[buf ^ 1][warp] = 0ull; S.wrow[buf ^ 1][warp] = 0xffffffffu; S.wrcp[buf ^ 1][warp] = 0ull; }
       }
       __syncthreads();
     }
   }
 
-  // ---- replay of the LAPACK swap sequence on position tables (every CTA, one thread: 64 O(1) steps) ----
-  if (tid == 0) {
-    double pmin = 1.7976931348623157e308, pmax = 0.0;
-    bool singular = false;
+  // ---- replay of the LAPACK swap sequence on position tables: warp 0 of every CTA, tables in registers (lane l: entries l, l+32) ----
+  if (warp == 0) {
+    unsigned cur0 = lane, cur1 = lane + 32;   // current position of original row d < NB
+    unsigned inv0 = lane, inv1 = lane + 32;   // original row sitting at position c < NB
+    bool wp0 = false, wp1 = false;            // original row d < NB became a pivot row
+    const unsigned ph0 = S.piv_home[lane], ph1 = S.piv_home[lane + 32];
     for (int c = 0; c < NB; ++c) {
-      const unsigned h = S.piv_home[c];          // original row of the pivot
-      const unsigned d = S.inv[c];               // original row sitting at position c (always < NB)
-      const unsigned p = h < (unsigned)NB ? S.cur[h] : h;  // where the pivot row sits now
-      if (p != (unsigned)c) {                    // swap(position c, position p)
-        S.cur[d] = p;
-        if (p < (unsigned)NB) S.inv[p] = d;
-        if (me == 0) S.fin[d] = p;               // original rows < NB live in CTA 0
+      const unsigned h = __shfl_sync(0xffffffffu, c < 32 ? ph0 : ph1, c & 31);   // original row of pivot c
+      const unsigned d = __shfl_sync(0xffffffffu, c < 32 ? inv0 : inv1, c & 31); // original row at position c (always < NB)
+      const unsigned ch = __shfl_sync(0xffffffffu, (h & 32u) ? cur1 : cur0, h & 31u);
+      const unsigned p = h < (unsigned)NB ? ch : h;                              // where the pivot row sits now
+      if (p != (unsigned)c) {                                                    // swap(position c, position p)
+        if (lane == (int)(d & 31u)) { if (d & 32u) cur1 = p; else cur0 = p; }
+        if (p < (unsigned)NB && lane == (int)(p & 31u)) { if (p & 32u) inv1 = d; else inv0 = d; }
+        if (me == 0 && lane == 0) S.fin[d] = p;                                  // original rows < NB live in CTA 0
       }
-      if (h < (unsigned)NB) { S.cur[h] = (unsigned)c; S.was_pivot[h] = 1; }
-      if (h / ROWS == me) S.fin[h - base] = (unsigned)c;
-      if (me == 0) {
-        ipiv[j0 + c] = j0 + p;
-        const unsigned long long key = S.piv_key[c];
-        if (key <= 1ull) singular = true;
-        else { const double av = __longlong_as_double((long long)(key - 1ull)); pmin = fmin(pmin, av); pmax = fmax(pmax, av); }
+      if (h < (unsigned)NB && lane == (int)(h & 31u)) { if (h & 32u) { cur1 = (unsigned)c; wp1 = true; } else { cur0 = (unsigned)c; wp0 = true; } }
+      if (lane == 0) {
+        if (h / ROWS == me) S.fin[h - base] = (unsigned)c;
+        if (me == 0) ipiv[j0 + c] = j0 + p;
       }
     }
     if (me == 0) {
-      if (singular) atomicCAS(info, 0, INFO_SINGULAR);
-      if (pmin < piv_minmax[0]) piv_minmax[0] = pmin;
-      if (pmax > piv_minmax[1]) piv_minmax[1] = pmax;
-      uint32_t cnt = 0;
-      for (int c = 0; c < NB; ++c)
-        if (S.piv_home[c] != (unsigned)c) { moves->dst[cnt] = j0 + c; moves->src[cnt] = j0 + S.piv_home[c]; ++cnt; }
-      for (int d = 0; d < NB; ++d)
-        if (!S.was_pivot[d] && S.cur[d] != (unsigned)d) { moves->dst[cnt] = j0 + S.cur[d]; moves->src[cnt] = j0 + d; ++cnt; }
-      moves->count = cnt;
+      // net move list: position c <- pivot c's original row; displaced rows d < NB that never became pivots end at cur[d]
+      const bool a0 = ph0 != (unsigned)lane, a1 = ph1 != (unsigned)(lane + 32);
+      const bool b0 = !wp0 && cur0 != (unsigned)lane, b1 = !wp1 && cur1 != (unsigned)(lane + 32);
+      const unsigned ma0 = __ballot_sync(0xffffffffu, a0), ma1 = __ballot_sync(0xffffffffu, a1);
+      const unsigned mb0 = __ballot_sync(0xffffffffu, b0), mb1 = __ballot_sync(0xffffffffu, b1);
+      const unsigned lt = (1u << lane) - 1u;
+      unsigned off = __popc(ma0 & lt);
+      if (a0) { moves->dst[off] = j0 + lane; moves->src[off] = j0 + ph0; }
+      off = __popc(ma0) + __popc(ma1 & lt);
+      if (a1) { moves->dst[off] = j0 + lane + 32; moves->src[off] = j0 + ph1; }
+      off = __popc(ma0) + __popc(ma1) + __popc(mb0 & lt);
+      if (b0) { moves->dst[off] = j0 + cur0; moves->src[off] = j0 + lane; }
+      off = __popc(ma0) + __popc(ma1) + __popc(mb0) + __popc(mb1 & lt);
+      if (b1) { moves->dst[off] = j0 + cur1; moves->src[off] = j0 + lane + 32; }
+      if (lane == 0) moves->count = __popc(ma0) + __popc(ma1) + __popc(mb0) + __popc(mb1);
+      // extreme |pivot| of the panel from the order-preserving keys
+      const unsigned long long k0 = S.piv_key[lane], k1 = S.piv_key[lane + 32];
+      const unsigned long long kmax = max_u64(k0 > k1 ? k0 : k1);
+      const unsigned long long kmin = ~max_u64(~(k0 < k1 ? k0 : k1));
+      if (lane == 0) {
+        if (kmin <= 1ull) atomicCAS(info, 0, INFO_SINGULAR);
+        else {
+          const double pmin = __longlong_as_double((long long)(kmin - 1ull)), pmax = __longlong_as_double((long long)(kmax - 1ull));
+          if (pmin < piv_minmax[0]) piv_minmax[0] = pmin;
+          if (pmax > piv_minmax[1]) piv_minmax[1] = pmax;
+        }
+      }
     }
   }
   __syncthreads();

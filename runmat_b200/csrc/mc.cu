@@ -41,24 +41,44 @@ __device__ __forceinline__ double lcg_next_uniform(uint64_t& s) {
   s = s * LCG_MULT + LCG_INC;
   return (double)(s >> 11) * (1.0 / 9007199254740992.0);
 }
-// LEAN: log / sincos from mc_math.h (coefficients in __constant__ memory: one DFMA per Horner step; the CUDA library versions
-// rebuild their coefficients as immediates every iteration, r06 SASS). false = the CUDA math library (RUNMAT_B200_MC_LIBM=1).
+__device__ __forceinline__ uint64_t lcg_next_u53(uint64_t& s) {
+  s = s * LCG_MULT + LCG_INC;
+  return s >> 11;
+}
+// One Box-Muller pair as (radius, cos, sin): element 2j gets radius*cos, 2j+1 gets radius*sin (random.rs:271-288).
+// LEAN: -2 log(u1) and sincos(2 pi u2) from mc_math.h, computed from the 53-bit LCG integers with a shared-memory table (`tab`,
+// filled by load_log_table); false = the CUDA math library on the converted uniforms (RUNMAT_B200_MC_LIBM=1).
 template <bool LEAN>
-__device__ __forceinline__ void box_muller(uint64_t& s, double& z0, double& z1) {
-  double u1 = lcg_next_uniform(s);
-  if (u1 <= 0.0) u1 = 2.2250738585072014e-308;  // f64::MIN_POSITIVE
-  const double u2 = lcg_next_uniform(s);
-  double sn, cs, radius;
+__device__ __forceinline__ void box_muller_polar(uint64_t& s, const double* tab, double& radius, double& cs, double& sn) {
   if (LEAN) {
-    radius = sqrt(-2.0 * rm_mc::log_unit(u1));
-    rm_mc::sincos_turn(u2, &sn, &cs);
+    const uint64_t x1 = lcg_next_u53(s), x2 = lcg_next_u53(s);
+    radius = sqrt(rm_mc::neg2log_u53(x1, tab));
+    rm_mc::sincos_turn_u53(x2, &sn, &cs);
   } else {
+    double u1 = lcg_next_uniform(s);
+    if (u1 <= 0.0) u1 = 2.2250738585072014e-308;  // f64::MIN_POSITIVE
+    const double u2 = lcg_next_uniform(s);
     radius = sqrt(-2.0 * log(u1));
     const double angle = 2.0 * 3.14159265358979323846 * u2;
     sincos(angle, &sn, &cs);
   }
+}
+template <bool LEAN>
+__device__ __forceinline__ void box_muller(uint64_t& s, const double* tab, double& z0, double& z1) {
+  double radius, cs, sn;
+  box_muller_polar<LEAN>(s, tab, radius, cs, sn);
   z0 = radius * cs;
   z1 = radius * sn;
+}
+// 256 threads copy the 256-entry {1/c, -2 log c} table into shared memory (4 KB): the per-lane lookups are bank-conflict limited
+// there, but a divergent index into __constant__ memory would serialise completely.
+template <bool LEAN>
+__device__ __forceinline__ void load_log_table(double* tab) {
+  if (LEAN) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+      *reinterpret_cast<double2*>(&tab[2 * i]) = *reinterpret_cast<const double2*>(&rm_mc::kNeg2LogTab[2 * i]);
+    __syncthreads();
+  }
 }
 template <bool LEAN>
 __device__ __forceinline__ double mc_exp(double x) { return LEAN ? rm_mc::exp_fast(x) : exp(x); }
@@ -79,6 +99,8 @@ __global__ void uniform_kernel(T* __restrict__ out, uint64_t n, uint64_t state0,
 
 template <typename T, bool LEAN>
 __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, uint64_t hop_mult, uint64_t hop_plus) {
+  __shared__ __align__(16) double tab[512];
+  load_log_table<LEAN>(tab);
   const uint64_t pairs = (n + 1) / 2;
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= pairs) return;
@@ -87,7 +109,7 @@ __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, 
   for (uint64_t j = tid; j < pairs; j += nthr) {
     uint64_t s2 = s;
     double z0, z1;
-    box_muller<LEAN>(s2, z0, z1);
+    box_muller<LEAN>(s2, tab, z0, z1);
     out[2 * j] = (T)z0;
     if (2 * j + 1 < n) out[2 * j + 1] = (T)z1;
     s = hop_mult * s + hop_plus;  // 2*nthr draws ahead
@@ -96,9 +118,9 @@ __global__ void normal_kernel(T* __restrict__ out, uint64_t n, uint64_t state0, 
 
 // One thread per Box-Muller pair of the GLOBAL path vector. `first_pair` is the global index of this
 // launch's first pair; local element e_local = e_global - path_offset.
-// SUMLOG: S_T = S_0 * exp(sum_t term_t) with ONE exponential at the end instead of S *= exp(term_t) every step. Same quantity; the
-// two roundings differ by ~sqrt(T) ulp (2e-15 at T = 256, the host's own product carries as much), far inside the 1e-10 parity
-// bar, and it removes 2 exps = 34 of the ~98 FP64 instructions per pair-step from an FP64-pipe-bound kernel (r24 ncu:
+// SUMLOG: S_T = S_0 * exp(steps*drift + scale * sum_t z_t) with ONE exponential at the end instead of S *= exp(drift + scale z_t)
+// every step. Same quantity; the roundings differ by ~sqrt(T) ulp (2e-15 at T = 256, the host's own product carries as much), far
+// inside the 1e-10 parity bar, and it removes 2 exps + 2 multiplies + 4 adds per pair-step from an FP64-pipe-bound kernel (r24 ncu:
 // math_pipe_throttle is the top stall). Only taken when no partial product can overflow or underflow (the host decides from
 // T * (|drift| + 8.6 |scale|) < 600; 8.57 = the largest |z| a 53-bit Box-Muller uniform can produce), so Inf / 0 / NaN patterns of
 // the per-step product cannot differ; otherwise, or with RUNMAT_B200_MC_STEPWISE=1, the per-step form runs.
@@ -106,6 +128,8 @@ template <typename T, bool LEAN, bool SUMLOG>
 __global__ void __launch_bounds__(256)
 evolve_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t len, uint64_t path_offset, uint64_t first_pair,
               uint64_t n_pairs, uint64_t state0, uint64_t step_mult, uint64_t step_plus, double drift, double scale, uint32_t steps) {
+  __shared__ __align__(16) double tab[512];
+  load_log_table<LEAN>(tab);
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n_pairs) return;
   const uint64_t pair = first_pair + tid;
@@ -118,19 +142,26 @@ evolve_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t len, uint6
   double a0 = 0.0, a1 = 0.0;
   for (uint32_t t = 0; t < steps; ++t) {
     uint64_t s2 = s;
-    double z0, z1;
-    box_muller<LEAN>(s2, z0, z1);
-    // stochastic_evolution.rs:25-27: term = drift + scale*noise; value *= exp(term)   (no FMA: -fmad=false)
     if (SUMLOG) {
-      a0 += drift + scale * z0;
-      a1 += drift + scale * z1;
+      // sum_t (drift + scale z_t) = steps*drift + scale * sum_t z_t: the noise sum is one DFMA per path-step
+      double radius, cs, sn;
+      box_muller_polar<LEAN>(s2, tab, radius, cs, sn);
+      a0 = fma(radius, cs, a0);
+      a1 = fma(radius, sn, a1);
     } else {
+      // stochastic_evolution.rs:25-27: term = drift + scale*noise; value *= exp(term)   (no FMA: -fmad=false)
+      double z0, z1;
+      box_muller<LEAN>(s2, tab, z0, z1);
       s0v *= mc_exp<LEAN>(drift + scale * z0);
       s1v *= mc_exp<LEAN>(drift + scale * z1);
     }
     s = step_mult * s + step_plus;  // one whole pass (2*ceil(global_len/2) draws) ahead
   }
-  if (SUMLOG) { s0v *= exp(a0); s1v *= exp(a1); }
+  if (SUMLOG) {
+    const double base = (double)steps * drift;
+    s0v *= exp(fma(scale, a0, base));
+    s1v *= exp(fma(scale, a1, base));
+  }
   if (has0) out[e0 - path_offset] = (T)s0v;
   if (has1) out[e1 - path_offset] = (T)s1v;
 }
