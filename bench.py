@@ -662,15 +662,20 @@ def extra_workloads(p, ex, rank, world, local_rank, dist, torch):
     ms = max_over_ranks(ms)
     p.free(hS0)
     p.free(hScr)
-    # work model: one path-step = 1/2 Box-Muller pair (log, sqrt, sincos for two paths) + one exp + the S *= e multiply + the LCG hop
+    # work model: one path-step = 1/2 Box-Muller pair (-2 log u1, sqrt, sincos 2 pi u2 for two paths) + the noise-sum DFMA + the LCG hops.
+    # The kernel is ISSUE-bound: 64.4 instruction slots per path-step, of which 18.1 go to the FP64 pipe (2 issue cycles each).
     psps = M * T / (ms * 1e-3)
-    fp64_per_step = MC_FP64_INSTR_PER_PATH_STEP
-    pipe_rate = 148 * 64 * 1.965e9 * world  # FP64 lane-instructions/s the SMs can issue (64 lanes/SM/clk)
+    issue_rate = 148 * 4 * 32 * 1.965e9 * world  # thread-instructions/s at one warp instruction per clock per SM sub-partition
+    pipe_rate = 148 * 64 * 1.965e9 * world       # FP64 lane-instructions/s (64 lanes/SM/clk)
     out["monte_carlo"] = {"paths": M, "steps": T, "ms": ms, "path_steps_per_s": psps, "price": price, "scaling": "strong",
                           "exchange": ex.describe() if world > 1 else None,
-                          "roofline": {"bound": "fp64 pipe (ALU/issue; HBM traffic is 16 B/path total)", "work_model": f"{fp64_per_step} FP64 arithmetic instructions (DFMA+DMUL+DADD) per path-step, measured with ncu SASS opcode counters; peak = 148 SM x 64 lanes x 1.965 GHz per GPU",
-                                       "achieved": psps * fp64_per_step / 1e12, "peak": pipe_rate / 1e12, "unit": "T FP64-instr/s",
-                                       "frac": psps * fp64_per_step / pipe_rate}}
+                          "roofline": {"bound": "instruction issue (1 warp instruction/clk/SM sub-partition; HBM traffic is 16 B/path total)",
+                                       "work_model": f"{MC_INSTR_PER_PATH_STEP} executed instructions per path-step ({MC_FP64_INSTR_PER_PATH_STEP} of them DFMA+DMUL+DADD), "
+                                                     "measured with ncu (smsp__inst_executed, SASS opcode counters; profiles/r40_mc_counters.txt); "
+                                                     "peak = 148 SM x 4 sub-partitions x 32 lanes x 1.965 GHz per GPU",
+                                       "achieved": psps * MC_INSTR_PER_PATH_STEP / 1e12, "peak": issue_rate / 1e12, "unit": "T thread-instr/s",
+                                       "frac": psps * MC_INSTR_PER_PATH_STEP / issue_rate,
+                                       "fp64_pipe_frac": psps * MC_FP64_INSTR_PER_PATH_STEP / pipe_rate}}
 
     # ---- configs[3]: 4K image batch, B = 64 images sharded by image (batch is the stride-1 axis: each rank owns its own
     #      [B/N, H, W] tensor), per batch: image_normalize -> squared error vs input -> ONE scalar exchange (MSE) ------------------
@@ -681,12 +686,13 @@ def extra_workloads(p, ex, rank, world, local_rank, dist, torch):
     return out
 
 
-# FP64 arithmetic instructions (DFMA + DMUL + DADD, thread-level, predicated-on) evolve_kernel executes per path-step, MEASURED
-# with ncu's SASS opcode counters on the 1e8 x 256 run (profiles/r34_summary.md, r34_gemm_mc.ncu-rep, evolve_kernel<double, lean,
-# sum-of-log-returns>: 3351.3 + 1671.5 + 880.1 thread-instr/clk over 74.17 ms at 1.9624 GHz = 8.59e11 instructions / 2.56e10
-# path-steps; the per-step-exp lean kernel executed 49.0, the library-math kernel of round 1 48.5). It is the dynamic count of
-# 1/2 (log + sqrt + sincos) + the state update; the pipe issues 64 such instructions per SM per clock.
-MC_FP64_INSTR_PER_PATH_STEP = 33.6
+# Instructions evolve_kernel<double, lean, sum-of-log-returns> executes per path-step, MEASURED with ncu on the 1e8 x 256 run
+# (r40_mc.ncu-rep, extract in profiles/r40_mc_counters.txt): smsp__inst_executed.sum = 5.151e10 warp instructions / (2.56e10 / 32)
+# warp path-steps = 64.4; DFMA + DMUL + DADD thread instructions (3322.5 + 663.2 + 0.9 per clk over 1.1606e8 cycles) = 4.63e11 /
+# 2.56e10 path-steps = 18.1 (round-2 start: 33.6 with the atanh-series log on converted uniforms; library math of round 1: 48.5).
+# Issue slots are the binding resource (smsp__issue_active 75 %), the FP64 pipe is 42 % busy.
+MC_INSTR_PER_PATH_STEP = 64.4
+MC_FP64_INSTR_PER_PATH_STEP = 18.1
 
 
 def image_batch_leg(p, rank, world, local_rank, dist, torch, peak_hbm):

@@ -259,6 +259,8 @@ rm_status compile_cuda_to_cubin(const std::string& src, const char* name, std::v
 
 // ---- other translation units ---------------------------------------------------------------------------------
 rm_status matmul_impl(rm_provider* p, const rm_handle* a, const rm_handle* b, const rm_matmul_epilogue* ep, rm_handle* out);
+// out = a' * a, every entry divided by divisor_vec[col] when given (device vector of a->shape[1] doubles); no materialised transpose on f64
+rm_status syrk_impl(rm_provider* p, const rm_handle* a, const double* divisor_vec, rm_handle* out);
 // gemm_ozaki.cu: f64 GEMM on tcgen05 (int8 Ozaki split). *used=false => shape outside the engine's range, caller runs the
 // DMMA engine unconditionally; *used=true => caller enqueues the DMMA kernel CONDITIONALLY on `guard` (device flags: non-finite
 // inputs or tiles that failed the element-wise accuracy guard), while still holding p->oz_mu.

@@ -24,6 +24,9 @@ constexpr int LDB_S = BK + 4;  // doubles per n-row of the B tile  (20 % 16 == 4
 constexpr int A_STAGE = BK * LDA_S;
 constexpr int B_STAGE = BN * LDB_S;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+// TRANSA (C = A' * B, the Gram / SYRK form): the left operand is read k-contiguous like B, so its tile is staged [m][k] like B's
+constexpr int A_STAGE_T = BM * LDB_S;
+constexpr size_t GEMM_SMEM_T = (size_t)STAGES * (A_STAGE_T + B_STAGE) * sizeof(double);
 
 struct Epilogue {
   double alpha, beta;
@@ -67,7 +70,8 @@ __device__ __forceinline__ double apply_epilogue(double v, const Epilogue& ep, u
 }
 
 // ALIGNED2: m and k are even -> 16-byte cp.async on both operands; otherwise 8-byte copies.
-template <bool ALIGNED2>
+// TRANSA: A points at a [k x m] column-major matrix (leading dimension lda) and the product is A' * B (no materialised transpose).
+template <bool ALIGNED2, bool TRANSA = false>
 __global__ void __launch_bounds__(256, 1)
 dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                   uint64_t m, uint64_t n, uint64_t k, uint64_t lda, uint64_t ldb, uint64_t ldc, int subtract,
@@ -75,8 +79,9 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
   extern __shared__ __align__(16) double smem[];
   // conditional mode (behind the tcgen05 engine): only tiles its accuracy guard / non-finite scan handed over are computed
   if (guard.flags && !(guard.flags[0] | guard.tileflags[blockIdx.x + (blockIdx.y >> 1) * guard.tiles_m])) return;
-  double* As = smem;                              // [STAGES][BK][LDA_S]
-  double* Bs = smem + (size_t)STAGES * A_STAGE;   // [STAGES][BN][LDB_S]
+  constexpr int ASTG = TRANSA ? A_STAGE_T : A_STAGE;
+  double* As = smem;                              // [STAGES][BK][LDA_S]   (TRANSA: [STAGES][BM][LDB_S])
+  double* Bs = smem + (size_t)STAGES * ASTG;      // [STAGES][BN][LDB_S]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -88,12 +93,32 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
 
   auto load_stage = [&](int stage, uint64_t kt) {
     const uint64_t k0 = kt * BK;
-    double* as = As + (size_t)stage * A_STAGE;
+    double* as = As + (size_t)stage * ASTG;
     double* bs = Bs + (size_t)stage * B_STAGE;
+    if (TRANSA) {
+      // A' tile: BM columns (rows of the product) of BK k-contiguous elements, staged exactly like B's tile
+      if (ALIGNED2) {
+#pragma unroll
+        for (int c = tid; c < BM * (BK / 2); c += 256) {
+          const int mc = c / (BK / 2), kr = (c % (BK / 2)) * 2;
+          const uint64_t gi = m0 + mc, gk = k0 + kr;
+          const bool ok = gi < m && gk < k;
+          cp_async16(as + mc * LDB_S + kr, A + (ok ? gi * lda + gk : 0), ok);
+        }
+      } else {
+#pragma unroll 4
+        for (int c = tid; c < BM * BK; c += 256) {
+          const int mc = c / BK, kr = c % BK;
+          const uint64_t gi = m0 + mc, gk = k0 + kr;
+          const bool ok = gi < m && gk < k;
+          cp_async8(as + mc * LDB_S + kr, A + (ok ? gi * lda + gk : 0), ok);
+        }
+      }
+    }
     if (ALIGNED2) {
       // A tile: BK columns of BM rows; 64 16-byte chunks per column
 #pragma unroll
-      for (int c = tid; c < BK * (BM / 2); c += 256) {
+      for (int c = tid; !TRANSA && c < BK * (BM / 2); c += 256) {
         const int kc = c / (BM / 2), mr = (c % (BM / 2)) * 2;
         const uint64_t gi = m0 + mr, gk = k0 + kc;
         const bool ok = gi < m && gk < k;
@@ -109,7 +134,7 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
       }
     } else {
 #pragma unroll 4
-      for (int c = tid; c < BK * BM; c += 256) {
+      for (int c = tid; !TRANSA && c < BK * BM; c += 256) {
         const int kc = c / BM, mr = c % BM;
         const uint64_t gi = m0 + mr, gk = k0 + kc;
         const bool ok = gi < m && gk < k;
@@ -146,13 +171,13 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
     if (next < ktiles) load_stage((int)(next % STAGES), next);
     cp_async_commit();
 
-    const double* as = As + (size_t)(kt % STAGES) * A_STAGE;
+    const double* as = As + (size_t)(kt % STAGES) * ASTG;
     const double* bs = Bs + (size_t)(kt % STAGES) * B_STAGE;
 #pragma unroll
     for (int k4 = 0; k4 < BK; k4 += 4) {
       double af[4], bf[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = as[(k4 + t) * LDA_S + wm + i * 8 + g];
+      for (int i = 0; i < 4; ++i) af[i] = TRANSA ? as[(wm + i * 8 + g) * LDB_S + k4 + t] : as[(k4 + t) * LDA_S + wm + i * 8 + g];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bf[j] = bs[(wn + j * 8 + g) * LDB_S + k4 + t];
 #pragma unroll
@@ -441,6 +466,47 @@ rm_status dgemm_sub_strided(rm_provider* p, const double* A, uint64_t lda, const
   return RM_OK;
 }
 
+
+// out = a' * a (optionally every entry divided by `divisor`, the covariance normalisation) without materialising a'. f64: the
+// TRANSA form of the DMMA kernel reads `a` k-contiguous for both operands (the reference's SYRK shader, backend/wgpu/shaders/syrk.rs,
+// also reads one input twice). f32 storage keeps the transpose + matmul composition (not on any benchmark config).
+rm_status syrk_impl(rm_provider* p, const rm_handle* a, const double* divisor_vec, rm_handle* out) {
+  RM_REQUIRE(a->rank == 2, RM_ERROR, "syrk: matrix input required");
+  const uint64_t k = a->shape[0], m = a->shape[1];
+  if (p->precision != RM_F64 || k == 0 || m == 0) {
+    RM_REQUIRE(!divisor_vec, RM_UNSUPPORTED, "syrk: fused normalisation needs f64 storage");
+    rm_handle at;
+    RM_TRY(rm_transpose(p, a, &at));
+    rm_status st = matmul_impl(p, &at, a, nullptr, out);
+    std::string msg = st == RM_OK ? "" : last_error();
+    rm_free(p, &at);
+    if (st != RM_OK) set_error("%s", msg.c_str());
+    return st;
+  }
+  void* pa;
+  RM_TRY(resolve(p, a, &pa, nullptr));
+  uint64_t oshape[2] = {m, m};
+  void* pc;
+  RM_TRY(alloc_tensor(p, oshape, 2, out, &pc));
+  Epilogue ep{};
+  ep.alpha = 1.0;
+  if (divisor_vec) { ep.col_scale = divisor_vec; ep.col_div = 1; ep.active = 1; }
+  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((m + BN - 1) / BN));
+  if (grid.y > 65535) { rm_free(p, out); return fail(RM_UNSUPPORTED, "syrk: matrix too wide for this kernel"); }
+  if (k % 2 == 0) {
+    cudaFuncSetAttribute(dgemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_T);
+    dgemm_dmma_kernel<true, true><<<grid, 256, GEMM_SMEM_T, p->stream>>>((const double*)pa, (const double*)pa, (double*)pc, m, m, k, k, k, m, 0, ep, OzGuard{});
+  } else {
+    cudaFuncSetAttribute(dgemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_T);
+    dgemm_dmma_kernel<false, true><<<grid, 256, GEMM_SMEM_T, p->stream>>>((const double*)pa, (const double*)pa, (double*)pc, m, m, k, k, k, m, 0, ep, OzGuard{});
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { rm_free(p, out); return fail(RM_ERROR, "syrk launch failed: %s", cudaGetErrorString(e)); }
+  count_launch(p);
+  record_launch(p, "syrk", {{"rows", k}, {"cols", m}}, {{"transposed_read", 1ull}, {"normalised", divisor_vec ? 1ull : 0ull}});
+  return RM_OK;
+}
+
 }  // namespace rm
 
 using namespace rm;
@@ -460,13 +526,7 @@ RM_EXPORT rm_status rm_matmul_epilogue_apply(rm_provider* p, const rm_handle* a,
 RM_EXPORT rm_status rm_syrk(rm_provider* p, const rm_handle* a, rm_handle* out) {
   RM_REQUIRE(p && a && out, RM_INVALID_ARG, "syrk: bad arguments");
   DeviceGuard g(p->ordinal);
-  rm_handle at;
-  RM_TRY(rm_transpose(p, a, &at));
-  rm_status st = matmul_impl(p, &at, a, nullptr, out);
-  std::string msg = st == RM_OK ? "" : last_error();
-  rm_free(p, &at);
-  if (st != RM_OK) set_error("%s", msg.c_str());
-  return st;
+  return syrk_impl(p, a, nullptr, out);
 }
 RM_EXPORT rm_status rm_set_matmul_engine(rm_provider* p, int engine) {
   RM_REQUIRE(p && engine >= 0 && engine <= 2, RM_INVALID_ARG, "set_matmul_engine: engine must be 0, 1 or 2");

@@ -55,6 +55,8 @@ struct __align__(16) Smem {
   unsigned long long tbar[2];              //            winners' windows, one per block parity
   unsigned long long piv_key[NB];          // replay input: key and original row of every pivot
   unsigned piv_home[NB];
+  unsigned cur[NB], inv[NB];               // replay tables: current position of original row d < NB; original row at position c < NB
+  unsigned was_pivot[NB];
   unsigned fin[ROWS];                      // final panel-local position of every local row
   int abort_flag;
 };
@@ -91,15 +93,49 @@ __device__ __forceinline__ unsigned long long max_u64(unsigned long long key) { 
   const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
   return ((unsigned long long)mh << 32) | ml;
 }
-__device__ __forceinline__ void argmax3(unsigned long long& key, unsigned& row) {  // max key, ties -> smallest row; result in every lane
-  const unsigned long long mine = key;
-  key = max_u64(key);
-  row = __reduce_min_sync(0xffffffffu, mine == key ? row : 0xffffffffu);
+// Lane holding the maximum key (ties -> lowest lane = smallest row: lanes are always ordered by row); same result in every lane.
+// One CREDUX on the top word + a ballot; the low word is only consulted when several lanes share the top word (warp-uniform branch).
+__device__ __forceinline__ int argmax_lane(unsigned long long key) {
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  unsigned cand = __ballot_sync(0xffffffffu, hi == mh);
+  if (cand & (cand - 1u)) {
+    const unsigned lo = (unsigned)key;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    cand = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+  }
+  return __ffs((int)cand) - 1;
+}
+// 1/v without the library's special-case subroutine: MUFU seed (20 bits) + two Newton steps. Zero / denormal pivots are never
+// divided by (the update is skipped for a zero pivot; a denormal pivot fails the host's conditioning gate).
+__device__ __forceinline__ double fast_rcp(double v) {
+  double y;
+  asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));  // volatile: keep it out of the winner-only branch (it overlaps the vote)
+  double e = fma(-v, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-v, y, 1.0);
+  return fma(y, e, y);
 }
 // order-preserving key of |v| for a live row: 0 = no candidate, 1 = zero or NaN (never preferred over a real value)
 __device__ __forceinline__ unsigned long long cand_key(double v, bool live) {
   const double av = fabs(v);
   return !live ? 0ull : (av == av ? (unsigned long long)__double_as_longlong(av) + 1ull : 1ull);
+}
+
+// One step of the LAPACK swap sequence on the position tables (O(1), one thread per CTA): pivot c came from original row h.
+// Original rows < NB are the only ones that can be displaced without being pivots, so 64-entry tables suffice.
+__device__ __forceinline__ void replay_step(Smem& S, int c, unsigned me, unsigned base, uint64_t j0, unsigned long long* __restrict__ ipiv) {
+  const unsigned h = S.piv_home[c];                       // original row of pivot c
+  const unsigned d = S.inv[c];                            // original row sitting at position c (always < NB)
+  const unsigned p = h < (unsigned)NB ? S.cur[h] : h;     // where the pivot row sits now
+  if (p != (unsigned)c) {                                 // swap(position c, position p)
+    S.cur[d] = p;
+    if (p < (unsigned)NB) S.inv[p] = d;
+    if (me == 0) S.fin[d] = p;                            // original rows < NB live in CTA 0
+  }
+  if (h < (unsigned)NB) { S.cur[h] = (unsigned)c; S.was_pivot[h] = 1u; }
+  if (h / ROWS == me) S.fin[h - base] = (unsigned)c;
+  if (me == 0) ipiv[j0 + c] = j0 + p;
 }
 
 // One cluster = the whole grid (gridDim.x = cluster size <= 16, a power of two >= ceil((n - j0) / 256)); exactly NB columns.
@@ -122,6 +158,7 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
 #pragma unroll
   for (int e = 0; e < NB; ++e) a[e] = valid ? P[r + (uint64_t)e * lda] : 0.0;
   S.fin[tid] = r;
+  if (tid < NB) { S.cur[tid] = tid; S.inv[tid] = tid; S.was_pivot[tid] = 0u; }
   if (tid == 0) {
     S.abort_flag = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.bar[0])) : "memory");
@@ -134,13 +171,9 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
   int tpush = -1;              // warp-uniform: block-relative column this warp's thread `tlane` won and has not yet pushed its window for
   int tlane = 0;
   {  // per-warp candidates of column 0
-    const double rc = 1.0 / a[0];
-    unsigned long long key = cand_key(a[0], valid);
-    const unsigned long long mine = key;
-    unsigned row = r;
-    argmax3(key, row);
-    if (row == r && mine == key) { S.wkey[0][warp] = key; S.wrow[0][warp] = row; S.wrcp[0][warp] = (unsigned long long)__double_as_longlong(rc); }
-    if (lane == 0 && key == 0ull) { S.wkey[0][warp] = 0ull; S.wrow[0][warp] = 0xffffffffu; S.wrcp[0][warp] = 0ull; }
+    const double rc = fast_rcp(a[0]);
+    const unsigned long long key = cand_key(a[0], valid);
+    if (lane == argmax_lane(key)) { S.wkey[0][warp] = key; S.wrow[0][warp] = key ? r : 0xffffffffu; S.wrcp[0][warp] = (unsigned long long)__double_as_longlong(rc); }
   }
   cooperative_groups::this_cluster().sync();  // barriers initialised everywhere before the first push; also the block barrier for wkey
 
@@ -158,16 +191,14 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
       const int e_lo = k & ~1;                          // first in-block column that travels (even: 16-byte units)
       const int npairs = (BLK - e_lo) / 2;
       // ---- (1) this CTA's candidate: fold the 8 warp candidates (every warp, redundantly) ----
-      unsigned long long lkey = lane < ROWS / 32 ? S.wkey[buf][lane] : 0ull;
-      unsigned lrow = lane < ROWS / 32 ? S.wrow[buf][lane] : 0xffffffffu;
-      const unsigned long long lrcp_mine = lane < ROWS / 32 ? S.wrcp[buf][lane] : 0ull;
-      argmax3(lkey, lrow);
-      const unsigned lp = lkey ? lrow - base : 0u;  // owner thread of the candidate row (thread 0 sends a never-winning dummy otherwise)
+      const int ow = argmax_lane(lane < ROWS / 32 ? S.wkey[buf][lane] : 0ull);  // the warp that owns the CTA's candidate (warp 0 sends a never-winning dummy when there is none)
       if (tid == 0) mbar_expect(&S.bar[buf], nblk * (32u + 16u * (unsigned)npairs));
       // ---- (2) the owner's warp pushes {key, row, 1/candidate, window[e_lo, 8)} into every CTA's mailbox (its own included) ----
-      if (warp == (int)(lp >> 5)) {
-        const unsigned long long lrcp = __shfl_sync(0xffffffffu, lrcp_mine, (int)(lp >> 5));  // the owner's warp slot holds its reciprocal
-        if (lane == (int)(lp & 31)) {
+      if (warp == ow) {
+        const unsigned long long lkey = S.wkey[buf][ow];
+        const unsigned lrow = S.wrow[buf][ow];
+        const int ol = lkey ? (int)((lrow - base) & 31u) : 0;
+        if (lane == ol) {
 #pragma unroll
           for (int e = e_lo; e < BLK; e += 2) *reinterpret_cast<double2*>(&S.stage[e]) = make_double2(a[e], a[e + 1]);
         }
@@ -184,8 +215,8 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
                          (unsigned long long)__double_as_longlong(v.y), rbar);
             }
           }
-          if (lane < 16) st_async16(mapa(smem_u32(&S.mb_meta[buf][me][0]), pr), lkey, (unsigned long long)(lkey ? lrow : 0xffffffffu), rbar);
-          else st_async16(mapa(smem_u32(&S.mb_meta[buf][me][2]), pr), lrcp, 0ull, rbar);
+          if (lane < 16) st_async16(mapa(smem_u32(&S.mb_meta[buf][me][0]), pr), lkey, (unsigned long long)lrow, rbar);
+          else st_async16(mapa(smem_u32(&S.mb_meta[buf][me][2]), pr), S.wrcp[buf][ow], 0ull, rbar);
         }
       }
       // ---- (2b) deferred: the warp that holds the previous column's winner ships that row's whole window (needed at the block end) ----
@@ -204,14 +235,16 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
         }
         tpush = -1;
       }
+      // ---- (2c) one thread replays the PREVIOUS column's swap on the position tables while its warp would wait for the mailbox anyway ----
+      if (tid == ROWS - 32 && c > 0) replay_step(S, c - 1, me, base, j0, ipiv);
       // ---- (3) wait until every peer's push has landed in OUR shared memory (bounded) ----
       mbar_wait(&S.bar[buf], parity, &S.abort_flag, info);
       // ---- (4) global pivot (every warp, redundantly) ----
-      unsigned long long gkey = (unsigned)lane < nblk ? S.mb_meta[buf][lane][0] : 0ull;
-      unsigned grow = (unsigned)lane < nblk ? (unsigned)S.mb_meta[buf][lane][1] : 0xffffffffu;
-      argmax3(gkey, grow);
-      if (grow >= nblk * ROWS) grow = 0;  // only after a protocol failure; keeps the mailbox index in bounds
-      const unsigned gb = grow / ROWS;
+      unsigned gb = (unsigned)argmax_lane((unsigned)lane < nblk ? S.mb_meta[buf][lane][0] : 0ull);  // CTA of the winner
+      if (gb >= nblk) gb = 0;  // only after a protocol failure
+      const unsigned long long gkey = S.mb_meta[buf][gb][0];
+      unsigned grow = (unsigned)S.mb_meta[buf][gb][1];
+      if (grow >= nblk * ROWS) grow = 0;  // only after a protocol failure; keeps the indices below in bounds
       const double* prow = S.mb_row[buf][gb];
       const double rp = __longlong_as_double((long long)S.mb_meta[buf][gb][2]);
       if (r == grow) died = c;  // this thread's registers now hold row c of U (and its L part)
@@ -283,71 +316,49 @@ lu_panel_push_kernel(double* __restrict__ A, uint64_t lda, uint64_t n, uint64_t 
       // ---- (7) per-warp candidates of the next column (with the reciprocal its winner will be divided by) ----
       {
         const double v = a[(k + 1) & (BLK - 1)];
-        const double rc = 1.0 / v;
-        unsigned long long key = cand_key(v, live);
-        const unsigned long long mine = key;
-        unsigned row = r;
-        argmax3(key, row);
-        if (row == r && mine == key) { S.wkey[buf ^ 1][warp] = key; S.wrow[buf ^ 1][warp] = row; S.wrcp[buf ^ 1][warp] = (unsigned long long)__double_as_longlong(rc); }
-        if (lane == 0 && key == 0ull) { S.wkey[buf ^ 1][warp] = 0ull; S.wrow[buf ^ 1][warp] = 0xffffffffu; S.wrcp[buf ^ 1][warp] = 0ull; }
+        const double rc = fast_rcp(v);
+        const unsigned long long key = cand_key(v, live);
+        if (lane == argmax_lane(key)) { S.wkey[buf ^ 1][warp] = key; S.wrow[buf ^ 1][warp] = key ? r : 0xffffffffu; S.wrcp[buf ^ 1][warp] = (unsigned long long)__double_as_longlong(rc); }
       }
       __syncthreads();
     }
   }
 
-  // ---- replay of the LAPACK swap sequence on position tables: warp 0 of every CTA, tables in registers (lane l: entries l, l+32) ----
-  if (warp == 0) {
-    unsigned cur0 = lane, cur1 = lane + 32;   // current position of original row d < NB
-    unsigned inv0 = lane, inv1 = lane + 32;   // original row sitting at position c < NB
-    bool wp0 = false, wp1 = false;            // original row d < NB became a pivot row
+  // ---- the last column's swap, then every row goes home ----
+  if (tid == ROWS - 32) replay_step(S, NB - 1, me, base, j0, ipiv);
+  __syncthreads();
+  if (me == 0 && warp == 0) {
+    // net move list (lane l: entries l and l + 32): position c <- pivot c's original row; displaced rows d < NB that never became
+    // pivots end at cur[d]. Offsets by ballot prefix sums.
     const unsigned ph0 = S.piv_home[lane], ph1 = S.piv_home[lane + 32];
-    for (int c = 0; c < NB; ++c) {
-      const unsigned h = __shfl_sync(0xffffffffu, c < 32 ? ph0 : ph1, c & 31);   // original row of pivot c
-      const unsigned d = __shfl_sync(0xffffffffu, c < 32 ? inv0 : inv1, c & 31); // original row at position c (always < NB)
-      const unsigned ch = __shfl_sync(0xffffffffu, (h & 32u) ? cur1 : cur0, h & 31u);
-      const unsigned p = h < (unsigned)NB ? ch : h;                              // where the pivot row sits now
-      if (p != (unsigned)c) {                                                    // swap(position c, position p)
-        if (lane == (int)(d & 31u)) { if (d & 32u) cur1 = p; else cur0 = p; }
-        if (p < (unsigned)NB && lane == (int)(p & 31u)) { if (p & 32u) inv1 = d; else inv0 = d; }
-        if (me == 0 && lane == 0) S.fin[d] = p;                                  // original rows < NB live in CTA 0
-      }
-      if (h < (unsigned)NB && lane == (int)(h & 31u)) { if (h & 32u) { cur1 = (unsigned)c; wp1 = true; } else { cur0 = (unsigned)c; wp0 = true; } }
-      if (lane == 0) {
-        if (h / ROWS == me) S.fin[h - base] = (unsigned)c;
-        if (me == 0) ipiv[j0 + c] = j0 + p;
-      }
-    }
-    if (me == 0) {
-      // net move list: position c <- pivot c's original row; displaced rows d < NB that never became pivots end at cur[d]
-      const bool a0 = ph0 != (unsigned)lane, a1 = ph1 != (unsigned)(lane + 32);
-      const bool b0 = !wp0 && cur0 != (unsigned)lane, b1 = !wp1 && cur1 != (unsigned)(lane + 32);
-      const unsigned ma0 = __ballot_sync(0xffffffffu, a0), ma1 = __ballot_sync(0xffffffffu, a1);
-      const unsigned mb0 = __ballot_sync(0xffffffffu, b0), mb1 = __ballot_sync(0xffffffffu, b1);
-      const unsigned lt = (1u << lane) - 1u;
-      unsigned off = __popc(ma0 & lt);
-      if (a0) { moves->dst[off] = j0 + lane; moves->src[off] = j0 + ph0; }
-      off = __popc(ma0) + __popc(ma1 & lt);
-      if (a1) { moves->dst[off] = j0 + lane + 32; moves->src[off] = j0 + ph1; }
-      off = __popc(ma0) + __popc(ma1) + __popc(mb0 & lt);
-      if (b0) { moves->dst[off] = j0 + cur0; moves->src[off] = j0 + lane; }
-      off = __popc(ma0) + __popc(ma1) + __popc(mb0) + __popc(mb1 & lt);
-      if (b1) { moves->dst[off] = j0 + cur1; moves->src[off] = j0 + lane + 32; }
-      if (lane == 0) moves->count = __popc(ma0) + __popc(ma1) + __popc(mb0) + __popc(mb1);
-      // extreme |pivot| of the panel from the order-preserving keys
-      const unsigned long long k0 = S.piv_key[lane], k1 = S.piv_key[lane + 32];
-      const unsigned long long kmax = max_u64(k0 > k1 ? k0 : k1);
-      const unsigned long long kmin = ~max_u64(~(k0 < k1 ? k0 : k1));
-      if (lane == 0) {
-        if (kmin <= 1ull) atomicCAS(info, 0, INFO_SINGULAR);
-        else {
-          const double pmin = __longlong_as_double((long long)(kmin - 1ull)), pmax = __longlong_as_double((long long)(kmax - 1ull));
-          if (pmin < piv_minmax[0]) piv_minmax[0] = pmin;
-          if (pmax > piv_minmax[1]) piv_minmax[1] = pmax;
-        }
+    const unsigned cur0 = S.cur[lane], cur1 = S.cur[lane + 32];
+    const bool a0 = ph0 != (unsigned)lane, a1 = ph1 != (unsigned)(lane + 32);
+    const bool b0 = !S.was_pivot[lane] && cur0 != (unsigned)lane, b1 = !S.was_pivot[lane + 32] && cur1 != (unsigned)(lane + 32);
+    const unsigned ma0 = __ballot_sync(0xffffffffu, a0), ma1 = __ballot_sync(0xffffffffu, a1);
+    const unsigned mb0 = __ballot_sync(0xffffffffu, b0), mb1 = __ballot_sync(0xffffffffu, b1);
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned off = __popc(ma0 & lt);
+    if (a0) { moves->dst[off] = j0 + lane; moves->src[off] = j0 + ph0; }
+    off = __popc(ma0) + __popc(ma1 & lt);
+    if (a1) { moves->dst[off] = j0 + lane + 32; moves->src[off] = j0 + ph1; }
+    off = __popc(ma0) + __popc(ma1) + __popc(mb0 & lt);
+    if (b0) { moves->dst[off] = j0 + cur0; moves->src[off] = j0 + lane; }
+    off = __popc(ma0) + __popc(ma1) + __popc(mb0) + __popc(mb1 & lt);
+    if (b1) { moves->dst[off] = j0 + cur1; moves->src[off] = j0 + lane + 32; }
+    if (lane == 0) moves->count = __popc(ma0) + __popc(ma1) + __popc(mb0) + __popc(mb1);
+    // extreme |pivot| of the panel from the order-preserving keys
+    const unsigned long long k0 = S.piv_key[lane], k1 = S.piv_key[lane + 32];
+    const unsigned long long kmax = max_u64(k0 > k1 ? k0 : k1);
+    const unsigned long long kmin = ~max_u64(~(k0 < k1 ? k0 : k1));
+    if (lane == 0) {
+      if (kmin <= 1ull) atomicCAS(info, 0, INFO_SINGULAR);
+      else {
+        const double pmin = __longlong_as_double((long long)(kmin - 1ull)), pmax = __longlong_as_double((long long)(kmax - 1ull));
+        if (pmin < piv_minmax[0]) piv_minmax[0] = pmin;
+        if (pmax > piv_minmax[1]) piv_minmax[1] = pmax;
       }
     }
   }
-  __syncthreads();
   if (valid) {
     const uint64_t fr = S.fin[tid];
 #pragma unroll 8

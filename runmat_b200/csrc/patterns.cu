@@ -45,26 +45,41 @@ RM_EXPORT rm_status rm_diag_extract(rm_provider* p, const rm_handle* matrix, int
   return RM_OK;
 }
 
-// C = lhs*rhs; every column divided by sqrt(sum(col.^2) + epsilon)
+// C = lhs*rhs; every column divided by sqrt(sum(col.^2) + epsilon)   (simple_provider.rs:7852-7890)
+// Three launches behind the GEMM-shaped pattern: the product, ONE generated reduction that squares while it sums the columns, ONE
+// generated broadcast kernel that applies c / sqrt(ss + eps) (round 1 chained six single-operator kernels and four temporaries).
 RM_EXPORT rm_status rm_matmul_power_step(rm_provider* p, const rm_handle* lhs, const rm_handle* rhs, double epsilon, rm_handle* out) {
   RM_REQUIRE(p && lhs && rhs && out, RM_INVALID_ARG, "matmul_power_step: bad arguments");
   DeviceGuard g(p->ordinal);
   ScopedWall wall(p->t_matmul);
-  Temp c(p), sq(p), ss(p), se(p), nrm(p);
+  Temp c(p), ss(p), eps(p);
   RM_TRY(matmul_impl(p, lhs, rhs, nullptr, &c.h));
   c.live = true;
-  RM_TRY(rm_elem_mul(p, &c.h, &c.h, &sq.h));
-  sq.live = true;
-  RM_TRY(rm_reduce_sum_dim(p, &sq.h, 0, &ss.h));  // [1, cols]
+  const uint64_t rows = c.h.shape[0], cols = c.h.shape[1];
+  if (rows * cols == 0) { *out = c.h; c.live = false; return RM_OK; }
+  ReductionProgram sq;
+  sq.scalar_ty = p->precision == RM_F64 ? "f64" : "f32";
+  sq.n_inputs = 1;
+  sq.axis = 0;
+  sq.val_expr = "(v0 * v0)";
+  uint64_t sshape[2] = {1, cols};
+  RM_TRY(run_reduction_program(p, sq, "pattern:colsumsq", RedOp::Sum, RedLayout::Contig, &c.h, 1, sshape, 2, rows, cols, /*inner=*/cols, 0, 1.0, &ss.h));
   ss.live = true;
-  RM_TRY(rm_scalar_add(p, &ss.h, epsilon, &se.h));
-  se.live = true;
-  RM_TRY(rm_unary_sqrt(p, &se.h, &nrm.h));
-  nrm.live = true;
-  return rm_elem_div(p, &c.h, &nrm.h, out);  // broadcast [rows,cols] ./ [1,cols]
+  uint64_t one[2] = {1, 1};
+  RM_TRY(rm_fill(p, one, 2, epsilon, &eps.h));
+  eps.live = true;
+  ElementwiseProgram nrm;
+  nrm.scalar_ty = sq.scalar_ty;
+  nrm.n_inputs = 3;
+  nrm.n_outputs = 1;
+  nrm.outputs.push_back("(v0 / sqrt(v1 + v2))");  // norm = sqrt(sum + epsilon); value / norm
+  rm_handle in[3] = {c.h, ss.h, eps.h};
+  return run_elementwise_program(p, nrm, "pattern:power_step_normalize", in, 3, c.h.shape, 2, rows * cols, out);
 }
 
 // normalization: 0 = Unbiased (n-1), 1 = Biased (n). Rows = All, no weights (what the CenteredGram pattern requests).
+// mean -> centre (one generated broadcast kernel) -> Xc' * Xc on the FP64 tensor-core GEMM reading Xc transposed in place, the
+// division by (n - 1) fused into its store (round 1: materialised transpose + full GEMM + a separate scalar divide).
 RM_EXPORT rm_status rm_covariance(rm_provider* p, const rm_handle* matrix, int normalization_biased, rm_handle* out) {
   RM_REQUIRE(p && matrix && out, RM_INVALID_ARG, "covariance: bad arguments");
   RM_REQUIRE(matrix->rank == 2, RM_ERROR, "covariance: matrix input required");
@@ -74,12 +89,21 @@ RM_EXPORT rm_status rm_covariance(rm_provider* p, const rm_handle* matrix, int n
   if (cols == 0) return rm_zeros(p, oshape, 2, out);
   const double denom = normalization_biased ? (double)rows : (double)rows - 1.0;
   if (!(denom > 0.0)) return rm_fill(p, oshape, 2, NAN, out);  // cov.rs:931-933
-  Temp mean(p), xc(p), gram(p);
+  Temp mean(p), xc(p), dv(p);
   RM_TRY(rm_reduce_mean_dim(p, matrix, 0, &mean.h));  // [1, cols]
   mean.live = true;
   RM_TRY(rm_elem_sub(p, matrix, &mean.h, &xc.h));     // centred, broadcast over rows
   xc.live = true;
-  RM_TRY(rm_syrk(p, &xc.h, &gram.h));                 // Xc' * Xc on the tensor-core GEMM
-  gram.live = true;
-  return rm_scalar_div(p, &gram.h, denom, out);
+  if (p->precision != RM_F64) {
+    Temp gram(p);
+    RM_TRY(syrk_impl(p, &xc.h, nullptr, &gram.h));
+    gram.live = true;
+    return rm_scalar_div(p, &gram.h, denom, out);
+  }
+  uint64_t vshape[2] = {1, cols};
+  RM_TRY(rm_fill(p, vshape, 2, denom, &dv.h));
+  dv.live = true;
+  void* pdv;
+  RM_TRY(resolve(p, &dv.h, &pdv, nullptr));
+  return syrk_impl(p, &xc.h, (const double*)pdv, out);
 }

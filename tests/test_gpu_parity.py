@@ -900,10 +900,33 @@ def test_fusion_pattern_hooks(prov, orc):
         assert d.shape == (len(np.diag(m, off)), 1) and np.array_equal(d[:, 0], np.diag(m, off))
 
 
-def test_syrk(prov, orc):
-    a = np.random.default_rng(16).uniform(-1, 1, (300, 40))
-    got = prov.download(prov.syrk(prov.upload(a)))
+@pytest.mark.parametrize("rows,cols", [(300, 40), (301, 40), (257, 131), (64, 300), (1, 5)])
+def test_syrk(prov, orc, rows, cols):
+    """a' * a through the transposed-read form of the FP64 tensor-core GEMM: even / odd inner dimension (16- vs 8-byte staging),
+    several 128 x 128 tiles with ragged edges, a single row. No transposed copy is launched."""
+    a = np.random.default_rng(16).uniform(-1, 1, (rows, cols))
+    h = prov.upload(a)
+    l0 = prov.telemetry_snapshot().kernel_launches
+    got = prov.download(prov.syrk(h))
+    assert prov.telemetry_snapshot().kernel_launches - l0 == 1
     matmul_close(got, a.T, a, orc.matmul(np.asfortranarray(a.T), a))
+    assert np.allclose(got, got.T, rtol=1e-13, atol=1e-13)
+
+
+def test_fusion_patterns_launch_counts(prov):
+    """The pattern hooks are short chains of fused kernels: power step = GEMM + one squaring column reduction + one broadcast
+    normalise (+ the epsilon fill); covariance = mean + centre + divisor fill + ONE transposed-read GEMM with the division fused."""
+    rng = np.random.default_rng(52)
+    ha, hb = prov.upload(rng.uniform(-1, 1, (96, 64))), prov.upload(rng.uniform(-1, 1, (64, 12)))
+    prov.free(prov.matmul_power_step(ha, hb, 1e-9))  # warm the kernel cache
+    l0 = prov.telemetry_snapshot().kernel_launches
+    prov.free(prov.matmul_power_step(ha, hb, 1e-9))
+    assert prov.telemetry_snapshot().kernel_launches - l0 <= 4
+    hx = prov.upload(rng.uniform(-1, 1, (200, 33)))
+    prov.free(prov.covariance(hx))
+    l0 = prov.telemetry_snapshot().kernel_launches
+    prov.free(prov.covariance(hx))
+    assert prov.telemetry_snapshot().kernel_launches - l0 <= 4
 
 
 def test_matmul_8192_properties(prov, orc):
