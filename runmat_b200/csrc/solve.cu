@@ -486,16 +486,38 @@ __global__ void __launch_bounds__(256) trsm_block_kernel(const double* __restric
   }
 }
 
-__global__ void absmax_kernel(const double* __restrict__ x, uint64_t n, unsigned long long* __restrict__ out, int* __restrict__ nonfinite) {
+// dst = src while tracking max |x| (as an order-preserving bit pattern) and non-finite entries: 4 independent loads in flight per
+// thread, warp shuffle fold, one atomic per warp. (Round 2's stand-alone scan issued one atomicMax per THREAD on a single address
+// and took 228 us for a 4096 x 4096 matrix: r44 launch list.)
+__global__ void __launch_bounds__(256) copy_absmax_kernel(const double* __restrict__ src, double* __restrict__ dst, uint64_t n,
+                                                          unsigned long long* __restrict__ out, int* __restrict__ nonfinite) {
   double mx = 0.0;
   bool bad = false;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const double v = fabs(x[i]);
-    bad |= !(v <= 1.7976931348623157e308);
-    mx = fmax(mx, v);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = src[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dst[i + u * stride] = v[u];
+      const double av = fabs(v[u]);
+      bad |= !(av <= 1.7976931348623157e308);
+      mx = fmax(mx, av);
+    }
   }
-  if (bad) atomicExch(nonfinite, 1);
-  atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+  for (; i < n; i += stride) {
+    const double v = src[i];
+    dst[i] = v;
+    const double av = fabs(v);
+    bad |= !(av <= 1.7976931348623157e308);
+    mx = fmax(mx, av);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(nonfinite, 1);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 
 // min / max of |diag(T)| (forward/backward_substitution_real track exactly these, linsolve.rs:769-833) as IEEE bit patterns
@@ -741,13 +763,13 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
   SV_CUDA(cudaMemsetAsync(amax, 0, 8, st));
   const double mm0[2] = {1.7976931348623157e308, 0.0};
   SV_CUDA(cudaMemcpyAsync(pivmm, mm0, 16, cudaMemcpyHostToDevice, st));
-  SV_CUDA(cudaMemcpyAsync(LU, pa, n * n * 8, cudaMemcpyDeviceToDevice, st));
+  // A -> LU copy fused with the max |a| / non-finite scan the conditioning gate needs (one pass over A instead of a copy plus a scan)
+  copy_absmax_kernel<<<(unsigned)p->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)pa, LU, n * n, amax, info + 1);
+  count_launch(p);
   SV_TRY(alloc_tensor(p, oshape, 2, out, &px));
   have_out = true;
   double* X = LU + n * n;  // the right-hand sides ride in the augmented columns; copied to the result tensor at the end
   SV_CUDA(cudaMemcpyAsync(X, pb, n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
-  absmax_kernel<<<(unsigned)std::min<uint64_t>((n * n + 255) / 256, (uint64_t)p->prop.multiProcessorCount * 8), 256, 0, st>>>(LU, n * n, amax, info + 1);
-  count_launch(p);
 
   // Two-level blocking with look-ahead on two streams.
   //  * 64-wide panels are factored and applied only inside the current NBO-wide outer block (stream A = the provider stream: the
@@ -835,25 +857,29 @@ RM_EXPORT rm_status rm_mldivide(rm_provider* p, const rm_handle* a, const rm_han
     if (lookahead) { cudaEventRecord(evE[K], st); cudaStreamWaitEvent(sb, evE[K], 0); }
     const uint64_t right = ntot - Jend;
     if (right > 0) {
-      for (uint64_t j0 = J0; j0 < Jend; j0 += NB)
-        perm_apply_kernel<<<(unsigned)std::min<uint64_t>(right, 4096), 2 * NB, 0, sb>>>(LU + Jend * n, n, right, right, 0, moves + j0 / NB);
-      count_launch(p, (Jend - J0 + NB - 1) / NB);
-      for (uint64_t i0 = J0; i0 < Jend && loop_status == RM_OK; i0 += NB) {
-        const int ib = (int)std::min<uint64_t>(NB, Jend - i0);
-        trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((right + 31) / 32), 256, TRSM_SMEM, sb>>>(LU + i0 + i0 * n, n, ib, LU + i0 + Jend * n, n, right);
-        count_launch(p);
-        const uint64_t below = Jend - (i0 + ib);
-        if (below > 0) loop_status = dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, LU + i0 + Jend * n, n, LU + (i0 + ib) + Jend * n, n, below, right, (uint64_t)ib, sb);
-      }
-      if (n > Jend && loop_status == RM_OK) {
-        // the next block's columns first (then A may start its panels), the rest afterwards
-        const uint64_t next_cols = std::min<uint64_t>(NBO, n - Jend);
-        loop_status = dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + Jend * n, n, LU + Jend + Jend * n, n, n - Jend, next_cols, Jend - J0, sb);
-        if (lookahead) cudaEventRecord(evF[K + 1], sb);
-        if (right > next_cols && loop_status == RM_OK)
-          loop_status = dgemm_sub_strided(p, LU + Jend + J0 * n, n, LU + J0 + (Jend + next_cols) * n, n, LU + Jend + (Jend + next_cols) * n, n, n - Jend, right - next_cols,
-                                          Jend - J0, sb);
-      }
+      // The next outer block's columns go FIRST through the whole chain (interchanges, U12 solves, their trailing update) and
+      // release stream A; the remaining columns follow. (r44 launch list: with one pass over all right-hand columns A waited
+      // ~170 us per outer block for 4 interchange + 4 solve + 3 update launches over up to 3900 columns before its panels could start.)
+      const uint64_t next_cols = n > Jend ? std::min<uint64_t>(NBO, n - Jend) : 0;
+      auto right_pass = [&](uint64_t c0, uint64_t nc) {  // columns [Jend + c0, Jend + c0 + nc) of the augmented matrix
+        if (nc == 0 || loop_status != RM_OK) return;
+        double* Mc = LU + (Jend + c0) * n;
+        for (uint64_t j0 = J0; j0 < Jend; j0 += NB)
+          perm_apply_kernel<<<(unsigned)std::min<uint64_t>(nc, 4096), 2 * NB, 0, sb>>>(Mc, n, nc, nc, 0, moves + j0 / NB);
+        count_launch(p, (Jend - J0 + NB - 1) / NB);
+        for (uint64_t i0 = J0; i0 < Jend && loop_status == RM_OK; i0 += NB) {
+          const int ib = (int)std::min<uint64_t>(NB, Jend - i0);
+          trsm_block_kernel<TRSM_LOWER_UNIT><<<(unsigned)((nc + 31) / 32), 256, TRSM_SMEM, sb>>>(LU + i0 + i0 * n, n, ib, Mc + i0, n, nc);
+          count_launch(p);
+          const uint64_t below = Jend - (i0 + ib);
+          if (below > 0) loop_status = dgemm_sub_strided(p, LU + (i0 + ib) + i0 * n, n, Mc + i0, n, Mc + (i0 + ib), n, below, nc, (uint64_t)ib, sb);
+        }
+        if (n > Jend && loop_status == RM_OK)
+          loop_status = dgemm_sub_strided(p, LU + Jend + J0 * n, n, Mc + J0, n, Mc + Jend, n, n - Jend, nc, Jend - J0, sb);
+      };
+      right_pass(0, next_cols);
+      if (lookahead && next_cols > 0) cudaEventRecord(evF[K + 1], sb);
+      right_pass(next_cols, right - next_cols);
     }
   }
   if (lookahead) {

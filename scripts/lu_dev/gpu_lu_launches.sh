@@ -3,6 +3,9 @@
 set -u
 TAG=${1:-r43}
 mkdir -p gpurun_out
+timeout 120 scripts/lu_dev/panel_test > gpurun_out/${TAG}_lu_panel.txt 2>&1; echo "panel_test rc=$?" >> gpurun_out/${TAG}_lu_panel.txt
+grep -o "PASS.*info=.\|FAIL.*info=.\|time median.*\|ALL PASS\|FAILED.*" gpurun_out/${TAG}_lu_panel.txt | paste - - | head -20
+timeout 300 python scripts/time_mldivide.py 4096 > gpurun_out/${TAG}_mldivide.txt 2>&1; cat gpurun_out/${TAG}_mldivide.txt
 timeout 600 python -m pytest tests -m gpu -q -x -k "mldivide or linsolve or mrdivide or syrk or pattern" -p no:cacheprovider > gpurun_out/${TAG}_pytest_lu.log 2>&1
 tail -5 gpurun_out/${TAG}_pytest_lu.log
 cat > /tmp/one_solve.py <<'PY'
@@ -18,5 +21,5 @@ hM, hR = p.upload(A), p.upload(B)
 for _ in range(3):
     p.free(p.mldivide(hM, hR)); p.synchronize()
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none --print-gpu-trace --csv --log-file gpurun_out/${TAG}_mldivide_launches.csv python /tmp/one_solve.py > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none --csv --log-file gpurun_out/${TAG}_mldivide_launches.csv python /tmp/one_solve.py > gpurun_out/${TAG}_mldivide_launches.log 2>&1
 wc -l gpurun_out/${TAG}_mldivide_launches.csv
