@@ -35,7 +35,9 @@ INTEREST = {
     "trsm_block_kernelILi0": ["SHFL", "DFMA", "LDS", "BAR"],
     "moments_partial_fold_kernel": ["SHFL", "DADD", "DFMA", "ATOM"],
     "normalize_fixed_kernel": ["MUFU", "FMUL", "FADD"],
-    "lu_panel_smem_kernel": ["DFMA", "DMUL", "BAR", "UCGABAR"],
+    "lu_panel_smem_kernel": ["DFMA", "DMUL", "BAR", "UCGABAR", "MEMBAR"],
+    "lu_panel_push_kernel": ["STAS", "SYNCS", "CREDUX", "VOTE", "DFMA", "MUFU", "BAR", "UCGABAR", "MEMBAR"],
+    "dgemm_dmma_kernelILb1ELb1E": ["DMMA", "LDGSTS"],
     "p2p_publish_kernel": ["ST.E", "STG", "MEMBAR", "FENCE"],
     "p2p_combine_kernel": ["LD.E", "LDG", "NANOSLEEP"],
     "rm_fused_ew": ["LDG", "STG"],
