@@ -18,7 +18,8 @@ rng = np.random.default_rng(0)
 hA = p.upload(rng.uniform(0, 4*math.pi, n*n), (n, n)); hB = p.upload(rng.uniform(-1, 1, n*n), (n, n))
 sh = ft.sum_sin_mul_add_wgsl()
 plain = ft.reduction_wgsl([0], [], 0, axis=0)
-for name, shader, ins, nbytes in (("sum(sin(A).*B+1)", sh, [hA, hB], 16*n*n), ("sum(A)", plain, [hA], 8*n*n)):
+muladd = ft.reduction_wgsl([0, 1], [ft.FusionOp("primitive", "ElemMul", [0, 1], 11), ft.FusionOp("primitive", "Add", [11, 2], 12)], 12, axis=0, const_values={2: 1.0})
+for name, shader, ins, nbytes in (("sum(sin(A).*B+1)", sh, [hA, hB], 16*n*n), ("sum(A.*B+1)", muladd, [hA, hB], 16*n*n), ("sum(A)", plain, [hA], 8*n*n)):
     for _ in range(5): p.free(p.fused_reduction(shader, ins, (1, 1), n*n, 1))
     p.synchronize(); p.timer_begin()
     for _ in range(50): p.free(p.fused_reduction(shader, ins, (1, 1), n*n, 1))
@@ -26,7 +27,7 @@ for name, shader, ins, nbytes in (("sum(sin(A).*B+1)", sh, [hA, hB], 16*n*n), ("
     print(f"{name}: {ms*1e3:.1f} us {nbytes/ms/1e6:.0f} GB/s", end="  |  ")
 print()
 ''' % (ROOT, ROOT)
-for unroll, minb, bpsm in itertools.product((2, 4), (0, 5, 6, 8), (4, 8, 16)):
+for unroll, minb, bpsm in itertools.product((1, 2), (4, 5, 6), (4, 8, 16, 32)):
     env = dict(os.environ, RUNMAT_B200_RED_UNROLL=str(unroll), RUNMAT_B200_RED_MINB=str(minb), RUNMAT_B200_RED_BPSM=str(bpsm))
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     print(f"unroll={unroll} minb={minb} bpsm={bpsm}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
