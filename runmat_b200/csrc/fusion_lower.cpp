@@ -84,7 +84,7 @@ bool tokenize(const std::string& s, std::vector<Tok>* out, std::string* err) {
 // WGSL builtin -> CUDA device function (prelude below defines the rm_* ones).
 const char* map_function(const std::string& id) {
   static const std::unordered_map<std::string, const char*> table = {
-      {"sin", "sin"},     {"cos", "cos"},     {"tan", "tan"},     {"asin", "asin"},   {"acos", "acos"},
+      {"sin", "rm_sin"},  {"cos", "rm_cos"},     {"tan", "tan"},     {"asin", "asin"},   {"acos", "acos"},
       {"atan", "atan"},   {"atan2", "atan2"}, {"sinh", "sinh"},   {"cosh", "cosh"},   {"tanh", "tanh"},
       {"asinh", "asinh"}, {"acosh", "acosh"}, {"atanh", "atanh"}, {"exp", "exp"},     {"exp2", "exp2"},
       {"log", "log"},     {"log2", "log2"},   {"sqrt", "sqrt"},   {"abs", "fabs"},    {"floor", "floor"},
@@ -326,6 +326,56 @@ __device__ __forceinline__ T rm_rem(T a, T b) {
 __device__ __forceinline__ T rm_heaviside(T x) { return x != x ? x : (x > (T)0 ? (T)1 : (x == (T)0 ? (T)0.5 : (T)0)); }
 __device__ __forceinline__ double rm_f64(double x) { return x; }
 __device__ __forceinline__ float rm_f32(double x) { return (float)x; }
+#if RM_F32 || RM_LIBM_TRIG
+#define rm_sin(x) sin(x)
+#define rm_cos(x) cos(x)
+#else
+// ---- rm_trig begin (tests/test_lowering.py compiles this block for the host and compares it with glibc) ----------------------
+// f64 sin / cos for the generated kernels. r47 ncu + SASS of the headline reduction sum(sin(A).*B+1): 62 instructions per element
+// of which 17 go to the FP64 pipe; the rest is the CUDA library's quadrant logic (two coefficient sets fetched from a table with
+// three LDG.128, FSEL pairs, F2I/I2F, UMOV pairs that rebuild immediates): issue slots 59 % busy, and the kernel runs at 50 us
+// where the same chain without the sin runs at 42 us (profiles/r49_red_sweep.txt). Here the argument is reduced modulo pi
+// instead of pi/2 (three-part pi, the first two parts 33 bits wide so q * part is exact for |q| < 2^20), ONE odd minimax
+// polynomial covers |r| <= pi/2 (degree 17, 3.9e-17 relative; Chebyshev-node fit in 60-digit arithmetic), the quadrant is a sign
+// flip on the integer side, and every constant is a __constant__ bank operand of its DFMA. cos uses half-integer multiples of pi,
+// so it keeps full relative accuracy next to its zeros as well. ~25 instructions, 15 FP64. Measured against glibc on the host:
+// <= 1.5 ulp over the fast range. |x| < 2^-27 returns the fdlibm answer (x, 1); |x| >= 105615, Inf and NaN take the library
+// routine out of line. RUNMAT_B200_LIBM_TRIG=1 restores the library functions.
+__constant__ double rm_kTrig[14] = {
+  0x1.45f306dc9c883p-2, 6755399441055744.0,                                      // 1/pi, 1.5 * 2^52
+  -0x1.921fb54400000p+1, -0x1.0b4611a600000p-33, -0x1.3198a2e037073p-68,         // -pi in three parts
+  0x1.899d1babb713bp-49, -0x1.ae50fd31b6504p-41, 0x1.612400a095576p-33, -0x1.ae64559f961c0p-26,
+  0x1.71de3a5452e63p-19, -0x1.a01a01a018a59p-13, 0x1.1111111111107p-7, -0x1.5555555555555p-3,
+  0.5};
+__device__ __noinline__ double rm_sin_slow(double x) { return sin(x); }
+__device__ __noinline__ double rm_cos_slow(double x) { return cos(x); }
+// sin(x - h*pi) with the sign of bit 0 of `flip` applied; |x - h*pi| <= pi/2 (+ rounding slop)
+__device__ __forceinline__ double rm_sin_reduced(double x, double h, int flip) {
+  double r = fma(h, rm_kTrig[2], x);
+  r = fma(h, rm_kTrig[3], r);
+  r = fma(h, rm_kTrig[4], r);
+  const double z = r * r;
+  double p = rm_kTrig[5];
+  #pragma unroll
+  for (int i = 6; i < 13; ++i) p = fma(p, z, rm_kTrig[i]);
+  const double s = fma(r * z, p, r);
+  return __hiloint2double(__double2hiint(s) ^ (flip << 31), __double2loint(s));
+}
+__device__ __forceinline__ double rm_sin(double x) {
+  const u32 hx = (u32)__double2hiint(x) & 0x7fffffffu;
+  if (hx - 0x3e400000u >= 0x40f9c8f0u - 0x3e400000u) return hx < 0x3e400000u ? x : rm_sin_slow(x);
+  const double t = fma(x, rm_kTrig[0], rm_kTrig[1]);   // round(x / pi) in the low mantissa bits
+  return rm_sin_reduced(x, t - rm_kTrig[1], __double2loint(t));
+}
+__device__ __forceinline__ double rm_cos(double x) {
+  const u32 hx = (u32)__double2hiint(x) & 0x7fffffffu;
+  if (hx - 0x3e400000u >= 0x40f9c8f0u - 0x3e400000u) return hx < 0x3e400000u ? 1.0 : rm_cos_slow(x);
+  const double t = fma(x, rm_kTrig[0], -rm_kTrig[13]) + rm_kTrig[1];   // n = round(x / pi - 1/2)
+  // cos(x) = cos(r + (n + 1/2) pi) = (-1)^(n+1) sin(r)
+  return rm_sin_reduced(x, (t - rm_kTrig[1]) + rm_kTrig[13], __double2loint(t) + 1);
+}
+// ---- rm_trig end
+#endif
 )CUDA";
 
 // tuning knobs (defaults chosen from the r01 sweep on B200; overridable for experiments)
@@ -333,6 +383,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   if (const char* e = getenv(name)) { int v = atoi(e); if (v >= lo && v <= hi) return v; }
   return dflt;
 }
+int libm_trig() { return env_int("RUNMAT_B200_LIBM_TRIG", 0, 0, 1); }
 int red_unroll() { return env_int("RUNMAT_B200_RED_UNROLL", 2, 1, 8); }
 // 4 resident CTAs/SM (<= 64 registers) + two independent accumulators: 49.2 us vs 53.9 us for the r01 structure on the headline
 // reduction (profiles/r04_harness_results.txt: occupancy is the lever, a third/fourth accumulator costs registers and loses)
@@ -353,7 +404,7 @@ std::string input_params(uint32_t n_inputs) {
 
 std::string emit_elementwise_cuda(const ElementwiseProgram& prog, EwVariant variant, uint32_t scalar_mask) {
   std::ostringstream o;
-  o << "#define RM_F32 " << (prog.scalar_ty == "f32" ? 1 : 0) << "\n" << kPrelude;
+  o << "#define RM_F32 " << (prog.scalar_ty == "f32" ? 1 : 0) << "\n#define RM_LIBM_TRIG " << libm_trig() << "\n" << kPrelude;
   const uint32_t ni = prog.n_inputs, no = prog.n_outputs;
   std::string body;
   for (auto& s : prog.stmts) body += "      " + s + "\n";
@@ -420,7 +471,7 @@ std::string emit_elementwise_cuda(const ElementwiseProgram& prog, EwVariant vari
 
 std::string emit_reduction_cuda(const ReductionProgram& prog, RedOp op, RedLayout layout) {
   std::ostringstream o;
-  o << "#define RM_F32 " << (prog.scalar_ty == "f32" ? 1 : 0) << "\n" << kPrelude;
+  o << "#define RM_F32 " << (prog.scalar_ty == "f32" ? 1 : 0) << "\n#define RM_LIBM_TRIG " << libm_trig() << "\n" << kPrelude;
   const uint32_t ni = prog.n_inputs;
   const char* identity = op == RedOp::Sum ? "0.0" : op == RedOp::Prod ? "1.0" : op == RedOp::Max ? "-CUDART_INF" : "CUDART_INF";
   o << "#define CUDART_INF __longlong_as_double(0x7ff0000000000000LL)\n";

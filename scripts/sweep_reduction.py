@@ -25,9 +25,16 @@ for name, shader, ins, nbytes in (("sum(sin(A).*B+1)", sh, [hA, hB], 16*n*n), ("
     for _ in range(50): p.free(p.fused_reduction(shader, ins, (1, 1), n*n, 1))
     ms = p.timer_end_ms() / 50
     print(f"{name}: {ms*1e3:.1f} us {nbytes/ms/1e6:.0f} GB/s", end="  |  ")
-print()
+h1 = p.upload(np.array([1.0]), (1, 1)); ew = ft.sin_mul_add_wgsl()
+for _ in range(5): p.free(p.fused_elementwise(ew, [hA, hB, h1], (n, n), n*n))
+p.synchronize(); p.timer_begin()
+for _ in range(50): p.free(p.fused_elementwise(ew, [hA, hB, h1], (n, n), n*n))
+ms = p.timer_end_ms() / 50
+print(f"C=sin(A).*B+1: {ms*1e3:.1f} us {24*n*n/ms/1e6:.0f} GB/s")
 ''' % (ROOT, ROOT)
-for unroll, minb, bpsm in itertools.product((1, 2), (4, 5, 6), (4, 8, 16, 32)):
-    env = dict(os.environ, RUNMAT_B200_RED_UNROLL=str(unroll), RUNMAT_B200_RED_MINB=str(minb), RUNMAT_B200_RED_BPSM=str(bpsm))
+grid = [(2, 4, 4, 1)] + [(u, m, b, 0) for u, m, b in itertools.product((1, 2, 4), (4, 5, 6), (4, 8))]
+for unroll, minb, bpsm, libm in grid:
+    env = dict(os.environ, RUNMAT_B200_RED_UNROLL=str(unroll), RUNMAT_B200_RED_MINB=str(minb), RUNMAT_B200_RED_BPSM=str(bpsm),
+               RUNMAT_B200_LIBM_TRIG=str(libm), RUNMAT_B200_NO_KCACHE="1")
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
-    print(f"unroll={unroll} minb={minb} bpsm={bpsm}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
+    print(f"libm_trig={libm} unroll={unroll} minb={minb} bpsm={bpsm}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
