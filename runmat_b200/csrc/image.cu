@@ -103,7 +103,9 @@ moments_partial_vec_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, 
 // contended, and summed in arrival order). Consecutive threads own consecutive vectors, so the lanes of a warp cycle through
 // the G = B / VEC image groups with period G. For G a power of two <= 32 an xor-butterfly over the offsets 16 .. G folds exactly
 // the lanes that share a group; lanes 0 .. G-1 then publish per-warp slots and the slots are folded in warp order.
-template <typename T, int VEC>
+// KEEP: plain read-only loads instead of evict-first streaming loads, so the end of the tensor is still in L2 when the normalise
+// sweep starts there (it runs end-to-front).
+template <typename T, int VEC, bool KEEP>
 __global__ void __launch_bounds__(256)
 moments_partial_fold_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, double* __restrict__ partial /*[grid][2][B]*/) {
   extern __shared__ double shw[];  // [8 warps][2][B]
@@ -119,7 +121,7 @@ moments_partial_fold_kernel(const T* __restrict__ x, uint32_t B, uint64_t total,
   for (; v + 7 * nthr < nvec; v += 8 * nthr) {
     V a[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) a[u] = __ldcs(xv + v + (uint64_t)u * nthr);
+    for (int u = 0; u < 8; ++u) a[u] = KEEP ? __ldg(xv + v + (uint64_t)u * nthr) : __ldcs(xv + v + (uint64_t)u * nthr);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const T* e = reinterpret_cast<const T*>(&a[u]);
@@ -128,7 +130,7 @@ moments_partial_fold_kernel(const T* __restrict__ x, uint32_t B, uint64_t total,
     }
   }
   for (; v < nvec; v += nthr) {
-    const V a = __ldcs(xv + v);
+    const V a = KEEP ? __ldg(xv + v) : __ldcs(xv + v);
     const T* e = reinterpret_cast<const T*>(&a);
 #pragma unroll
     for (int l = 0; l < VEC; ++l) { const double d = (double)e[l] - K[l]; s1[l] += d; s2[l] += d * d; }
@@ -237,11 +239,14 @@ __device__ __forceinline__ void st_stream_f32(float* p, const float* e) {
 template <int VEC>
 __global__ void __launch_bounds__(256)
 normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
-                                      const __grid_constant__ NormParams np) {
+                                      const __grid_constant__ NormParams np, int rev) {
   constexpr int U = VEC == 8 ? 2 : 4;  // 64 bytes per thread in flight
   const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t b0 = (uint32_t)((v0 * VEC) % B);
+  // rev: sweep from the end of the tensor to the front (vector v -> nvec-1-v). The moments sweep has just read the tensor front to
+  // end, so its last ~100 MB are still in the 126 MB L2 and serve the first reads here. nthr*VEC %% B == 0 keeps the image fixed.
+  auto at = [&](uint64_t v) { return rev ? nvec - 1 - v : v; };
+  const uint32_t b0 = (uint32_t)((at(v0 < nvec ? v0 : 0) * VEC) % B);
   float mean[VEC], inv[VEC];
 #pragma unroll
   for (int l = 0; l < VEC; ++l) { mean[l] = (float)stats[2 * (b0 + l)]; inv[l] = (float)stats[2 * (b0 + l) + 1]; }
@@ -261,26 +266,27 @@ normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __rest
   for (; v + (U - 1) * nthr < nvec; v += U * nthr) {
     float a[U][VEC];
 #pragma unroll
-    for (int u = 0; u < U; ++u) ld_stream_f32<VEC>(x + (v + (uint64_t)u * nthr) * VEC, a[u]);
+    for (int u = 0; u < U; ++u) ld_stream_f32<VEC>(x + at(v + (uint64_t)u * nthr) * VEC, a[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) { body(a[u]); st_stream_f32<VEC>(y + (v + (uint64_t)u * nthr) * VEC, a[u]); }
+    for (int u = 0; u < U; ++u) { body(a[u]); st_stream_f32<VEC>(y + at(v + (uint64_t)u * nthr) * VEC, a[u]); }
   }
   for (; v < nvec; v += nthr) {
     float a[VEC];
-    ld_stream_f32<VEC>(x + v * VEC, a);
+    ld_stream_f32<VEC>(x + at(v) * VEC, a);
     body(a);
-    st_stream_f32<VEC>(y + v * VEC, a);
+    st_stream_f32<VEC>(y + at(v) * VEC, a);
   }
 }
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 normalize_fixed_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
-                       const __grid_constant__ NormParams np) {
+                       const __grid_constant__ NormParams np, int rev) {
   typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
   const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t b0 = (uint32_t)((v0 * VEC) % B);
+  auto at = [&](uint64_t v) { return rev ? nvec - 1 - v : v; };  // end-to-front sweep: see normalize_fixed_clampgamma_f32_kernel
+  const uint32_t b0 = (uint32_t)((at(v0 < nvec ? v0 : 0) * VEC) % B);
   T mean[VEC], inv[VEC];
 #pragma unroll
   for (int l = 0; l < VEC; ++l) { mean[l] = (T)stats[2 * (b0 + l)]; inv[l] = (T)stats[2 * (b0 + l) + 1]; }
@@ -302,11 +308,11 @@ normalize_fixed_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t B, u
   };
   uint64_t v = v0;
   for (; v + nthr < nvec; v += 2 * nthr) {
-    const V a = __ldcs(xv + v), b = __ldcs(xv + v + nthr);
-    __stcs(yv + v, body(a));
-    __stcs(yv + v + nthr, body(b));
+    const V a = __ldcs(xv + at(v)), b = __ldcs(xv + at(v + nthr));
+    __stcs(yv + at(v), body(a));
+    __stcs(yv + at(v + nthr), body(b));
   }
-  for (; v < nvec; v += nthr) __stcs(yv + v, body(__ldcs(xv + v)));
+  for (; v < nvec; v += nthr) __stcs(yv + at(v), body(__ldcs(xv + at(v))));
 }
 
 template <typename T, int VEC>
@@ -673,6 +679,37 @@ __device__ __forceinline__ bool imf_mbar_wait(uint64_t* bar, uint32_t parity, in
     if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); return false; }  // a protocol bug must surface as an error flag, never as a hung GPU
   }
 }
+// Producer flavour: lets the hardware park the lane for up to ~1 us per try instead of re-issuing the test (r53 ncu: the lone
+// producer lane executed 14 try_wait round trips of 9 instructions per tile-warp, 12 % of the kernel's issue slots).
+__device__ __forceinline__ bool imf_mbar_wait_parked(uint64_t* bar, uint32_t parity, int* err) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(imf_smem_u32(bar)), "r"(parity), "r"(1000u) : "memory");
+    if (ok) return true;
+    if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); return false; }
+  }
+}
+// Tile t = blockIdx.x + it * gridDim.x as (tile column, tile row, plane), advanced incrementally: the stride is decomposed once,
+// a step is three adds and two compare-subtracts. (r53 ncu/SASS: decomposing t with two 32-bit divisions per tile, in 64-bit
+// coordinates, cost ~100 dependent instructions per tile per warp -- I2F/MUFU.RCP/F2I chains the warp sits out -- next to the
+// 400 packed math instructions of a 5x5 tile.)
+struct ImfTileIter {
+  uint32_t tx, ty, plane, dx, dy, dp, ntx, nty;
+  __device__ __forceinline__ void init(uint32_t first, uint32_t stride, uint32_t ntx_, uint32_t nty_) {
+    ntx = ntx_; nty = nty_;
+    tx = first % ntx; uint32_t r = first / ntx; ty = r % nty; plane = r / nty;
+    dx = stride % ntx; r = stride / ntx; dy = r % nty; dp = r / nty;
+  }
+  __device__ __forceinline__ void next() {
+    tx += dx;
+    uint32_t c = 0;
+    if (tx >= ntx) { tx -= ntx; c = 1; }
+    ty += dy + c;
+    plane += dp;
+    if (ty >= nty) { ty -= nty; ++plane; }
+  }
+};
 // MODE 0: scalar FMUL + FADD; 1: packed FMUL2 + FFMA2(x1); 2: mixed -- the first half of a warp's rows packed, the second half scalar
 // Resident CTAs the register allocation is held to: the K*K weights live in registers, so 7x7 gets two CTAs per SM; up to 5x5
 // four fit (RBW = 4: 3 x 10 KB stages each) or three (RBW = 8).
@@ -696,36 +733,42 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  struct TileAt { int64_t t0, t1, h0, h1; uint32_t plane; bool interior, tma; };
+  struct TileAt { int t0, t1, h0, h1; uint32_t plane; bool interior, tma; };  // image extents and tile counts are below 2^31 (launch_imfilter_tma_rb)
   // columns the fetch starts left of the halo; the same for every tile of a launch (tile origins are multiples of FX = 64)
-  const int shift = (int)((((fp.base[0] - fp.origin[0]) % 4) + 4) % 4);
-  auto tile_at = [&](uint32_t t) {
+  const int bo0 = (int)(fp.base[0] - fp.origin[0]), bo1 = (int)(fp.base[1] - fp.origin[1]);
+  const int shift = ((bo0 % 4) + 4) % 4;
+  const int ie0 = (int)fp.ie[0], ie1 = (int)fp.ie[1];
+  const int padding = fp.padding;
+  auto tile_at = [&](const ImfTileIter& ti) {
     TileAt a;
-    const uint32_t tx = t % ntx, r = t / ntx;
-    a.t0 = (int64_t)tx * FX;
-    a.t1 = (int64_t)(r % nty) * C::TY;
-    a.plane = r / nty;
-    a.h0 = a.t0 + fp.base[0] - fp.origin[0];
-    a.h1 = a.t1 + fp.base[1] - fp.origin[1];
-    a.interior = a.h0 >= 0 && a.h1 >= 0 && a.h0 + SX <= (int64_t)fp.ie[0] && a.h1 + SY <= (int64_t)fp.ie[1];
+    a.t0 = (int)ti.tx * FX;
+    a.t1 = (int)ti.ty * C::TY;
+    a.plane = ti.plane;
+    a.h0 = a.t0 + bo0;
+    a.h1 = a.t1 + bo1;
+    a.interior = a.h0 >= 0 && a.h1 >= 0 && a.h0 + SX <= ie0 && a.h1 + SY <= ie1;
     // Border tiles are fetched by the TMA as well (out-of-image elements arrive as zeros) and patched in shared memory from the
     // in-image part of the same box; only circular padding reads from the far side of the image and keeps the manual fill.
-    a.tma = a.interior || fp.padding != 3;
+    a.tma = a.interior || padding != 3;
     return a;
   };
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... (the grid never exceeds the tile count)
+  const uint32_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  ImfTileIter ti;
+  ti.init(blockIdx.x, gridDim.x, ntx, nty);
   if (warp == 8) {
     // ---- producer ------------------------------------------------------------------------------------------------------------
     if (lane == 0) {
-      uint32_t it = 0;
-      for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = (int)(it % IMF_STAGES);
-        const TileAt a = tile_at((uint32_t)t);
+      int s = 0;
+      uint32_t round = 0;  // it / IMF_STAGES
+      for (uint32_t it = 0; it < my_tiles; ++it, ti.next(), s = (s + 1 == IMF_STAGES ? 0 : s + 1), round += (s == 0)) {
+        const TileAt a = tile_at(ti);
         if (!a.tma) continue;  // circular-padding border tiles are filled by the compute warps (they wait for `empty` themselves)
-        if (it >= IMF_STAGES && !imf_mbar_wait(&empty[s], ((it / IMF_STAGES) - 1) & 1u, err)) break;
+        if (it >= IMF_STAGES && !imf_mbar_wait_parked(&empty[s], (round - 1) & 1u, err)) break;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(imf_smem_u32(&full[s])), "r"(C::BOX_BYTES) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(imf_smem_u32(dsm + (size_t)s * C::STAGE_BYTES)), "l"(&tm), "r"(imf_smem_u32(&full[s])), "r"((int)a.h0 - shift), "r"((int)a.h1), "r"((int)a.plane)
+                     ::"r"(imf_smem_u32(dsm + (size_t)s * C::STAGE_BYTES)), "l"(&tm), "r"(imf_smem_u32(&full[s])), "r"(a.h0 - shift), "r"(a.h1), "r"((int)a.plane)
                      : "memory");
       }
     }
@@ -746,11 +789,11 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
   const int ly0 = warp * RBW;
   const unsigned long long one2 = pack_f32x2(fp.one, fp.one);
   uint32_t phase = 0;  // bit s: parity of the next completion of full[s] (it advances on TMA-fetched tiles only)
-  uint32_t it = 0;
-  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-    const int s = (int)(it % IMF_STAGES);
+  int s = 0;
+  uint32_t round = 0;  // it / IMF_STAGES
+  for (uint32_t it = 0; it < my_tiles; ++it, ti.next(), s = (s + 1 == IMF_STAGES ? 0 : s + 1), round += (s == 0)) {
     float* tile = (float*)(dsm + (size_t)s * C::STAGE_BYTES);
-    const TileAt a = tile_at((uint32_t)t);
+    const TileAt a = tile_at(ti);
     if (a.tma) {
       imf_mbar_wait(&full[s], (phase >> s) & 1u, err);
       phase ^= 1u << s;
@@ -775,7 +818,7 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
       }
     } else {
       // every compute warp has released the stage's previous use; then fill it cooperatively and meet on a named barrier
-      if (it >= IMF_STAGES) imf_mbar_wait(&empty[s], ((it / IMF_STAGES) - 1) & 1u, err);
+      if (it >= IMF_STAGES) imf_mbar_wait(&empty[s], (round - 1) & 1u, err);
       const float* src = img + (uint64_t)a.plane * fp.ie[0] * fp.ie[1];
       for (int sy = warp; sy < SY; sy += 8) {
         const int c = remap(a.h1 + sy, (int64_t)fp.ie[1]);
@@ -816,17 +859,31 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     }
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(imf_smem_u32(&empty[s])) : "memory");  // this warp's reads of the stage are done
-    const uint64_t oA = (uint64_t)a.t0 + lane, oB = oA + 32, o1 = (uint64_t)a.t1 + ly0;
-    float* dst = out + o1 * fp.oe[0] + (uint64_t)a.plane * fp.oe[0] * fp.oe[1];
-    const int nvalid = o1 + RBW <= fp.oe[1] ? RBW : (o1 < fp.oe[1] ? (int)(fp.oe[1] - o1) : 0);
+    // stores: one 64-bit base per tile, then a pointer step per row; tiles that lie wholly inside the output (all but the last
+    // tile row / column) take the unguarded path (r53: the guarded form with per-store 64-bit compares was 165 instructions)
+    const int oe0 = (int)fp.oe[0], oe1 = (int)fp.oe[1];
+    const int oA = a.t0 + lane, o1 = a.t1 + ly0;
+    float* dst = out + ((uint64_t)a.plane * (uint32_t)oe1 + (uint32_t)o1) * (uint64_t)(uint32_t)oe0 + (uint32_t)oA;
+    if (a.t0 + FX <= oe0 && o1 + RBW <= oe1) {
 #pragma unroll
-    for (int o = 0; o < RBW; ++o, dst += fp.oe[0]) {
-      if (o < nvalid) {
+      for (int o = 0; o < RBW; ++o, dst += oe0) {
         float va, vb;
         if (MODE == 1 || (MODE == 2 && o < RBW / 2)) unpack_f32x2(acc[o], va, vb);
         else { va = accA[o]; vb = accB[o]; }
-        if (oA < fp.oe[0]) __stcs(dst + oA, va);
-        if (oB < fp.oe[0]) __stcs(dst + oB, vb);
+        __stcs(dst, va);
+        __stcs(dst + 32, vb);
+      }
+    } else {
+      const int nvalid = o1 + RBW <= oe1 ? RBW : (o1 < oe1 ? oe1 - o1 : 0);
+#pragma unroll
+      for (int o = 0; o < RBW; ++o, dst += oe0) {
+        if (o < nvalid) {
+          float va, vb;
+          if (MODE == 1 || (MODE == 2 && o < RBW / 2)) unpack_f32x2(acc[o], va, vb);
+          else { va = accA[o]; vb = accB[o]; }
+          if (oA < oe0) __stcs(dst, va);
+          if (oA + 32 < oe0) __stcs(dst + 32, vb);
+        }
       }
     }
   }
@@ -851,7 +908,7 @@ static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* 
   using C = ImfTma<K, RBW>;
   const uint64_t ntx = (fp.oe[0] + FX - 1) / FX, nty = (fp.oe[1] + C::TY - 1) / C::TY, ntiles = ntx * nty * fp.oe[2];
   // global strides must be multiples of 16 bytes; coordinates are 32-bit; small problems keep the one-CTA-per-tile kernel
-  if (fp.ie[0] % 4 != 0 || fp.ie[0] >= (1ull << 31) || fp.ie[1] >= (1ull << 31) || fp.ie[2] >= (1ull << 31) || ntiles >= (1ull << 32) ||
+  if (fp.ie[0] % 4 != 0 || fp.ie[0] >= (1ull << 31) || fp.ie[1] >= (1ull << 31) || fp.ie[2] >= (1ull << 31) || ntiles >= (1ull << 31) ||
       ntiles < (uint64_t)p->prop.multiProcessorCount * 8 || ((uintptr_t)a & 15) != 0)
     return false;
   ImfEncodeTiledFn enc = imf_encode_tiled();
@@ -993,9 +1050,12 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   const uint64_t groups = B / (uint64_t)VEC;  // image groups a warp's lanes cycle through on the fast path
   const bool fold = fast_blocks && B % VEC == 0 && groups >= 1 && groups <= 32 && (groups & (groups - 1)) == 0 && !getenv("RUNMAT_B200_MOMENTS_ATOMIC");
   const size_t sh_fold = (size_t)8 * 2 * B * sizeof(double);
+  // end-to-front normalise sweep over a tensor the moments sweep has just read front-to-end (L2 reuse of its tail); A/B switches
+  const int rev = getenv("RUNMAT_B200_NORMALIZE_FORWARD") ? 0 : 1;
+  const bool keep = rev && !getenv("RUNMAT_B200_MOMENTS_LDCS");
   if (p->precision == RM_F64) {
     if (fold) {
-      moments_partial_fold_kernel<double, 2><<<nblocks, 256, sh_fold, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
+      (keep ? moments_partial_fold_kernel<double, 2, true> : moments_partial_fold_kernel<double, 2, false>)<<<nblocks, 256, sh_fold, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
     } else if (fast_blocks) {
       moments_partial_vec_kernel<double, 2><<<nblocks, 256, sh, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
     } else {
@@ -1003,11 +1063,11 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
       moments_partial_kernel<double><<<nblocks, threads, sh, p->stream>>>((const double*)src, B, P, partial);
     }
     moments_finalize_kernel<double><<<(unsigned)B, 128, 0, p->stream>>>((const double*)src, partial, nblocks, B, P, d->epsilon, stats);
-    if (fast_blocks) normalize_fixed_kernel<double, 2><<<fast_blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, (uint32_t)B, total, stats, np);
+    if (fast_blocks) normalize_fixed_kernel<double, 2><<<fast_blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, (uint32_t)B, total, stats, np, rev);
     else normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
   } else {
     if (fold) {
-      moments_partial_fold_kernel<float, 4><<<nblocks, 256, sh_fold, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
+      (keep ? moments_partial_fold_kernel<float, 4, true> : moments_partial_fold_kernel<float, 4, false>)<<<nblocks, 256, sh_fold, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
     } else if (fast_blocks) {
       moments_partial_vec_kernel<float, 4><<<nblocks, 256, sh, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
     } else {
@@ -1018,11 +1078,11 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
     if (fast_blocks && d->clamp_zero && d->has_gamma && (float)d->gamma != 0.0f && !getenv("RUNMAT_B200_NORMALIZE_GENERIC")) {
       // 256-bit accesses when a thread's 8 lanes stay on fixed images (B % 8 == 0 and the grid stride a multiple of B)
       if (B % 8 == 0 && total % 8 == 0 && ((uint64_t)fast_blocks * 256ull * 8) % B == 0 && !getenv("RUNMAT_B200_NORMALIZE_VEC4"))
-        normalize_fixed_clampgamma_f32_kernel<8><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+        normalize_fixed_clampgamma_f32_kernel<8><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np, rev);
       else
-        normalize_fixed_clampgamma_f32_kernel<4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+        normalize_fixed_clampgamma_f32_kernel<4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np, rev);
     }
-    else if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np);
+    else if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np, rev);
     else normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
   }
   cudaError_t e = cudaGetLastError();
