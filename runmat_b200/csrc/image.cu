@@ -713,10 +713,15 @@ struct ImfTileIter {
 // MODE 0: scalar FMUL + FADD; 1: packed FMUL2 + FFMA2(x1); 2: mixed -- the first half of a warp's rows packed, the second half scalar
 // Resident CTAs the register allocation is held to: the K*K weights live in registers, so 7x7 gets two CTAs per SM; up to 5x5
 // four fit (RBW = 4: 3 x 10 KB stages each) or three (RBW = 8).
-template <int K, int RBW, int MODE>
-__global__ void __launch_bounds__(288, (K <= 5 ? (RBW == 4 ? 4 : 3) : 2))
+// MB = resident CTAs the register allocation is held to. 5x5 at MB = 3 (75 registers) leaves ptxas ONE product temporary, so every
+// FMUL2 is followed at once by the FFMA2 that consumes it; at MB = 2 (91 registers used) products are issued 2-4 instructions
+// ahead of their accumulation. Measured (r56, 2160x3840x3): 63.6 us at MB = 3 vs 66.4 us at MB = 2 -- the third CTA's eight warps
+// hide that latency better than the wider schedule does, so MB = 3 stays the default (RUNMAT_B200_IMFILTER_MINB2 = the other).
+template <int K, int RBW, int MODE, int MB>
+__global__ void __launch_bounds__(288, MB)
 imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ img, const float* __restrict__ ker, float* __restrict__ out,
-                        const __grid_constant__ FilterParams fp, uint32_t ntx, uint32_t nty, uint32_t ntiles, int* __restrict__ err) {
+                        const __grid_constant__ FilterParams fp, uint32_t ntx, uint32_t nty, uint32_t ntiles, int* __restrict__ err,
+                        uint32_t num_sms, uint32_t cta_stagger_ns, uint32_t warp_stagger_ns) {
   using C = ImfTma<K, RBW>;
   constexpr int SX = C::SX, SY = C::SY, SXP = C::SXP;
   extern __shared__ __align__(128) unsigned char imf_dsm_raw[];
@@ -775,6 +780,19 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     return;
   }
   // ---- compute warps -----------------------------------------------------------------------------------------------------------
+  // Phase stagger. All CTAs start together and every tile costs the same, so without help the warps of an SM sit in their
+  // non-math phases (barrier wait, tile bookkeeping, stores) at the same time and the FP32 pipe idles (r53 ncu: no eligible warp
+  // in 36 % of the cycles while the average is 1.9 eligible warps). The k-th co-resident CTA (blockIdx.x / #SMs) starts its
+  // compute warps k * cta_stagger_ns late, the upper half of each CTA's warps another warp_stagger_ns; the producer is not
+  // delayed, so the ring is full when they start, and the offsets persist because tile times are equal.
+  {
+    const uint32_t delay = (blockIdx.x / num_sms) * cta_stagger_ns + (warp >= 4 ? warp_stagger_ns : 0u);
+    if (delay) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do { __nanosleep(64); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < delay);
+    }
+  }
   float w[K * K];  // application order (already flipped for convolution)
 #pragma unroll
   for (int i = 0; i < K * K; ++i) {
@@ -839,15 +857,35 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
       for (int k0 = 0; k0 < K; ++k0) {
         const float tA = tile[(ly0 + j) * SXP + shift + lane + k0], tB = tile[(ly0 + j) * SXP + shift + lane + 32 + k0];
         const unsigned long long v = pack_f32x2(tA, tB);
+        // The K products of one loaded pair first, then the K accumulations (K different outputs). r53 SASS: with the multiply
+        // and its add written back to back the scheduler walked ONE output's chain at a time -- five dependent FFMA2 in a row, a
+        // warp issued one instruction per 4.7 cycles and it took ~5 warps per sub-partition in the loop to fill the FP32 pipe.
+        // `volatile` pins this order; each output still receives its taps in the host's order.
+        unsigned long long prod[K];
+        if (MODE == 1) {
+#pragma unroll
+          for (int k1 = 0; k1 < K; ++k1) {
+            const int o = j - k1;
+            if (o >= 0 && o < RBW) {
+              const float wk = w[k0 + k1 * K];
+              asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod[k1]) : "l"(pack_f32x2(wk, wk)), "l"(v));
+            }
+          }
+#pragma unroll
+          for (int k1 = 0; k1 < K; ++k1) {
+            const int o = j - k1;
+            if (o >= 0 && o < RBW) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[o]) : "l"(acc[o]), "l"(one2), "l"(prod[k1]));
+          }
+        }
 #pragma unroll
         for (int k1 = 0; k1 < K; ++k1) {
           const int o = j - k1;
-          if (o >= 0 && o < RBW) {
+          if (MODE != 1 && o >= 0 && o < RBW) {
             const float wk = w[k0 + k1 * K];
-            if (MODE == 1 || (MODE == 2 && o < RBW / 2)) {  // o is a compile-time constant after unrolling
-              unsigned long long prod;
-              asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod) : "l"(pack_f32x2(wk, wk)), "l"(v));
-              asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[o]) : "l"(acc[o]), "l"(one2), "l"(prod));
+            if (MODE == 2 && o < RBW / 2) {  // o is a compile-time constant after unrolling
+              unsigned long long pr;
+              asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pack_f32x2(wk, wk)), "l"(v));
+              asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[o]) : "l"(acc[o]), "l"(one2), "l"(pr));
             } else {
               // scalar FMUL + FADD (the library is compiled -fmad=false): one rounding after the multiply, one after the add
               accA[o] = __fadd_rn(accA[o], __fmul_rn(wk, tA));
@@ -903,7 +941,7 @@ static ImfEncodeTiledFn imf_encode_tiled() {
   return fn;
 }
 // Returns false when the TMA path does not apply (the caller then launches the per-tile kernel).
-template <int K, int RBW, int MODE>
+template <int K, int RBW, int MODE, int MB = (K <= 5 ? (RBW == 4 ? 4 : 3) : 2)>
 static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* k, float* o, const FilterParams& fp) {
   using C = ImfTma<K, RBW>;
   const uint64_t ntx = (fp.oe[0] + FX - 1) / FX, nty = (fp.oe[1] + C::TY - 1) / C::TY, ntiles = ntx * nty * fp.oe[2];
@@ -930,12 +968,16 @@ static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* 
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (idempotent; a benign race)
-  if (!attr_set) { cudaFuncSetAttribute(imfilter_tma_f32_kernel<K, RBW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(imfilter_tma_f32_kernel<K, RBW, MODE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr_set = true; }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imfilter_tma_f32_kernel<K, RBW, MODE>, 288, C::SMEM) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imfilter_tma_f32_kernel<K, RBW, MODE, MB>, 288, C::SMEM) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
   const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)p->prop.multiProcessorCount * per_sm);
-  imfilter_tma_f32_kernel<K, RBW, MODE><<<grid, 288, C::SMEM, p->stream>>>(tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty, (uint32_t)ntiles, (int*)p->dev_flags + 0);
+  uint32_t cta_stagger = 0, warp_stagger = 0;
+  if (const char* e = getenv("RUNMAT_B200_IMFILTER_STAGGER")) cta_stagger = (uint32_t)atoi(e);
+  if (const char* e = getenv("RUNMAT_B200_IMFILTER_WSTAGGER")) warp_stagger = (uint32_t)atoi(e);
+  imfilter_tma_f32_kernel<K, RBW, MODE, MB><<<grid, 288, C::SMEM, p->stream>>>(tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty, (uint32_t)ntiles, (int*)p->dev_flags + 0,
+                                                                         (uint32_t)p->prop.multiProcessorCount, cta_stagger, warp_stagger);
   return true;
 }
 template <int K>
@@ -945,6 +987,9 @@ static bool launch_imfilter_tma(rm_provider* p, const float* a, const float* k, 
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_RBW")) rbw = atoi(e);
   int mode = 1;
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_MODE")) mode = atoi(e);
+  if constexpr (K == 5) {
+    if (rbw == 8 && mode == 1 && getenv("RUNMAT_B200_IMFILTER_MINB2")) return launch_imfilter_tma_rb<K, 8, 1, 2>(p, a, k, o, fp);  // A/B: the 91-register build
+  }
   if (rbw == 4) return mode == 0 ? launch_imfilter_tma_rb<K, 4, 0>(p, a, k, o, fp) : mode == 2 ? launch_imfilter_tma_rb<K, 4, 2>(p, a, k, o, fp) : launch_imfilter_tma_rb<K, 4, 1>(p, a, k, o, fp);
   return mode == 0 ? launch_imfilter_tma_rb<K, 8, 0>(p, a, k, o, fp) : mode == 2 ? launch_imfilter_tma_rb<K, 8, 2>(p, a, k, o, fp) : launch_imfilter_tma_rb<K, 8, 1>(p, a, k, o, fp);
 }
