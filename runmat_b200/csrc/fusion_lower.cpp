@@ -392,6 +392,7 @@ int red_unroll() { return env_int("RUNMAT_B200_RED_UNROLL", 2, 1, 8); }
 // kernel left in the 126 MB L2, and it finishes at the front, where the next forward sweep starts. Any fixed order is
 // deterministic; RUNMAT_B200_RED_FORWARD=1 restores the forward sweep.
 int red_reverse() { return env_int("RUNMAT_B200_RED_FORWARD", 0, 0, 1) ? 0 : 1; }
+int red_blocked() { return env_int("RUNMAT_B200_RED_BLOCKED", 0, 0, 1); }
 int red_minblocks() { return env_int("RUNMAT_B200_RED_MINB", 4, 0, 8); }
 
 std::string input_params(uint32_t n_inputs) {
@@ -580,19 +581,29 @@ __device__ __forceinline__ void publish_scalar(void* const* peers, u32 n, u32 ra
     o << "  const u64 tid = (u64)bidx * blockDim.x + threadIdx.x;\n  const u64 nthr = (u64)bps * blockDim.x;\n";
     // two independent accumulators (even / odd vector lanes): halves the dependent DADD chain, fixed fold order at the end
     o << "  double acc0 = IDENT, acc1 = IDENT;\n";
-    o << "  u64 i = tid;\n";
+    // Work split. Grid-stride (thread t takes vectors t, t + nthr, ...) leaves the first (nvec mod nthr) threads one iteration more
+    // than the rest (28 vs 27 on the headline reduction). The alternative -- every CTA owns one contiguous run of ceil(nvec / bps)
+    // vectors -- balances that but measured SLOWER (r57: 46.1 us vs 44.3 us; sum(A) 24.4 vs 23.6): with grid-stride the resident
+    // CTAs sweep one moving window of the array together (DRAM pages and L2 sets shared by neighbours), with blocked runs 592
+    // separate streams are open at once. Grid-stride stays the default; RUNMAT_B200_RED_BLOCKED=1 selects the other.
+    if (red_blocked()) {
+      o << "  const u64 per_cta = (nvec + bps - 1) / bps;\n  const u64 lo = (u64)bidx * per_cta;\n"
+           "  const u64 hi = lo + per_cta < nvec ? lo + per_cta : nvec;\n  const u64 vstep = blockDim.x;\n  u64 i = lo + threadIdx.x;\n";
+    } else {
+      o << "  const u64 hi = nvec;\n  const u64 vstep = nthr;\n  u64 i = tid;\n";
+    }
     // U 256-bit vectors per input in flight per thread per iteration (all loads issued before any math)
-    o << "  for (; i + (u64)(RED_U - 1) * nthr < nvec; i += (u64)RED_U * nthr) {\n";
+    o << "  for (; i + (u64)(RED_U - 1) * vstep < hi; i += (u64)RED_U * vstep) {\n";
     for (uint32_t k = 0; k < ni; ++k) {
       o << "    vec_t a" << k << "[RED_U];\n";
     }
     o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n";
-    for (uint32_t k = 0; k < ni; ++k) o << "      a" << k << "[u] = ldv(in" << k << " + base + RED_IDX(i + (u64)u * nthr) * VEC);\n";
+    for (uint32_t k = 0; k < ni; ++k) o << "      a" << k << "[u] = ldv(in" << k << " + base + RED_IDX(i + (u64)u * vstep) * VEC);\n";
     o << "    }\n";
     o << "    #pragma unroll\n    for (int u = 0; u < RED_U; ++u) {\n      #pragma unroll\n      for (int l = 0; l < VEC; ++l) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "        const T v" << k << " = a" << k << "[u].x[l];\n";
     o << "        if (l & 1) accumulate(acc1, " << prog.val_expr << "); else accumulate(acc0, " << prog.val_expr << ");\n      }\n    }\n  }\n";
-    o << "  for (; i < nvec; i += nthr) {\n";
+    o << "  for (; i < hi; i += vstep) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "    const vec_t a" << k << " = ldv(in" << k << " + base + RED_IDX(i) * VEC);\n";
     o << "    #pragma unroll\n    for (int l = 0; l < VEC; ++l) {\n";
     for (uint32_t k = 0; k < ni; ++k) o << "      const T v" << k << " = a" << k << ".x[l];\n";

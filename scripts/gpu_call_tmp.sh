@@ -1,5 +1,5 @@
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -k "imfilter or conv" --timeout 600 -p no:cacheprovider 2>&1 | tail -3
-timeout 300 python scripts/sweep_imfilter_stagger.py > gpurun_out/r56_imfilter_regs.txt 2>&1
-cat gpurun_out/r56_imfilter_regs.txt
+timeout 300 python scripts/sweep_reduction.py > gpurun_out/r57_red_sweep.txt 2>&1
+cat gpurun_out/r57_red_sweep.txt
+bash scripts/gpu_round.sh r57

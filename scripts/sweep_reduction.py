@@ -32,9 +32,13 @@ for _ in range(50): p.free(p.fused_elementwise(ew, [hA, hB, h1], (n, n), n*n))
 ms = p.timer_end_ms() / 50
 print(f"C=sin(A).*B+1: {ms*1e3:.1f} us {24*n*n/ms/1e6:.0f} GB/s")
 ''' % (ROOT, ROOT)
-grid = [(2, 4, 4, 1)] + [(u, m, b, 0) for u, m, b in itertools.product((1, 2, 4), (4, 5, 6), (4, 8))]
-for unroll, minb, bpsm, libm in grid:
+# (unroll, min CTAs/SM, CTAs per SM in the grid, libm trig, grid-stride split)
+grid = [(2, 4, 4, 1, 0), (2, 4, 4, 0, 1), (2, 4, 4, 0, 0), (1, 4, 4, 0, 0), (2, 4, 8, 0, 0), (2, 5, 5, 0, 0), (2, 4, 4, 0, 1), (2, 4, 4, 0, 0)]
+if len(sys.argv) > 1 and sys.argv[1] == "full":
+    grid += [(u, m, b, 0, 0) for u, m, b in itertools.product((1, 2, 4), (4, 5, 6), (4, 8))]
+for unroll, minb, bpsm, libm, gs in grid:
     env = dict(os.environ, RUNMAT_B200_RED_UNROLL=str(unroll), RUNMAT_B200_RED_MINB=str(minb), RUNMAT_B200_RED_BPSM=str(bpsm),
                RUNMAT_B200_LIBM_TRIG=str(libm), RUNMAT_B200_NO_KCACHE="1")
+    if not gs: env["RUNMAT_B200_RED_BLOCKED"] = "1"
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
-    print(f"libm_trig={libm} unroll={unroll} minb={minb} bpsm={bpsm}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
+    print(f"libm_trig={libm} gridstride={gs} unroll={unroll} minb={minb} bpsm={bpsm}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)

@@ -236,6 +236,29 @@ def test_unary(prov, orc, op):
     prov.free(hr)
 
 
+@pytest.mark.parametrize("op", ["sin", "cos"])
+def test_trig_ranges_and_special_values(prov, orc, op):
+    """The generated kernels' own f64 sin / cos (fusion_lower.cpp prelude, "rm_trig") against the oracle (glibc, what f64::sin /
+    f64::cos call: sin.rs:265-270): the fast range up to 105615, arguments next to the zeros of both functions (relative
+    accuracy there needs the three-part pi), the out-of-line library route for huge arguments, the fdlibm answers for tiny ones,
+    NaN for Inf / NaN, and the sign of sin(-0)."""
+    rng = np.random.default_rng(33)
+    k = np.arange(-2000, 2001, dtype=np.float64)
+    near = np.concatenate([np.nextafter(k * (np.pi / 2), np.inf), k * (np.pi / 2), np.nextafter(k * (np.pi / 2), -np.inf)])
+    x = np.concatenate([rng.uniform(-4 * np.pi, 4 * np.pi, 20000), rng.uniform(-105615, 105615, 20000), near,
+                        rng.uniform(-1, 1, 2000) * 1e-9, 10.0 ** rng.uniform(5, 300, 2000) * rng.choice([-1.0, 1.0], 2000),
+                        np.array([0.0, -0.0, 5e-324, -5e-324, 1e-300, 2.0 ** -27, -(2.0 ** -27), 105614.999, 105615.0, 105615.001, 1e22, -1e22,
+                                  np.inf, -np.inf, np.nan, 1.7976931348623157e308])])
+    h = prov.upload(x.reshape(-1, 1))
+    got, want = prov.download(prov.unary(op, h)).ravel(), orc.unary(op, x.reshape(-1, 1)).ravel()
+    close(got, want, rtol=1e-10, atol=0.0)   # purely relative: also next to the zeros
+    zero = want == 0.0
+    assert np.array_equal(np.signbit(got[zero]), np.signbit(want[zero]))
+    if op == "cos":
+        assert np.all(got[x == 0.0] == 1.0)
+    prov.free(h)
+
+
 @pytest.mark.parametrize("op", ["add", "sub", "mul", "div", "rsub", "rdiv", "max", "min"])
 def test_scalar_ops_exact(prov, orc, op):
     x = np.random.default_rng(3).uniform(-5, 5, (129, 3))
