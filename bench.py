@@ -671,7 +671,7 @@ def extra_workloads(p, ex, rank, world, local_rank, dist, torch):
                           "exchange": ex.describe() if world > 1 else None,
                           "roofline": {"bound": "instruction issue (1 warp instruction/clk/SM sub-partition; HBM traffic is 16 B/path total)",
                                        "work_model": f"{MC_INSTR_PER_PATH_STEP} executed instructions per path-step ({MC_FP64_INSTR_PER_PATH_STEP} of them DFMA+DMUL+DADD), "
-                                                     "measured with ncu (smsp__inst_executed, SASS opcode counters; profiles/r40_mc_counters.txt); "
+                                                     "measured with ncu (smsp__inst_executed, SASS opcode counters; profiles/r40_mc_counters.txt, re-measured in profiles/r57_summary.md); "
                                                      "peak = 148 SM x 4 sub-partitions x 32 lanes x 1.965 GHz per GPU",
                                        "achieved": psps * MC_INSTR_PER_PATH_STEP / 1e12, "peak": issue_rate / 1e12, "unit": "T thread-instr/s",
                                        "frac": psps * MC_INSTR_PER_PATH_STEP / issue_rate,
@@ -691,9 +691,9 @@ def extra_workloads(p, ex, rank, world, local_rank, dist, torch):
 # warp path-steps = 64.4; DFMA + DMUL + DADD thread instructions (3322.5 + 663.2 + 0.9 per clk over 1.1606e8 cycles) = 4.63e11 /
 # 2.56e10 path-steps = 18.1 (round-2 start: 33.6 with the atanh-series log on converted uniforms; library math of round 1: 48.5).
 # Issue slots are the binding resource (smsp__issue_active 75 %), the FP64 pipe is 42 % busy.
-# r48 build (46-register budget): the loop body shrank from 129 to 121 SASS instructions per pair-step with the same 36 FP64 instructions
-# (cuobjdump of evolve_kernel<double, true, true>); scaled by the measured dynamic/static ratio of r40 (64.4 / 64.5) -> 60.4.
-MC_INSTR_PER_PATH_STEP = 60.4
+# r48 build (46-register budget): the loop body shrank from 129 to 121 SASS instructions per pair-step with the same 36 FP64 instructions;
+# re-measured in r57 (r57_mc_lu.ncu-rep): smsp__inst_executed.sum = 4.8757e10 warp instructions / 8e8 warp path-steps = 60.9.
+MC_INSTR_PER_PATH_STEP = 60.9
 MC_FP64_INSTR_PER_PATH_STEP = 18.1
 
 

@@ -1097,7 +1097,7 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   const size_t sh_fold = (size_t)8 * 2 * B * sizeof(double);
   // end-to-front normalise sweep over a tensor the moments sweep has just read front-to-end (L2 reuse of its tail); A/B switches
   const int rev = getenv("RUNMAT_B200_NORMALIZE_FORWARD") ? 0 : 1;
-  const bool keep = rev && !getenv("RUNMAT_B200_MOMENTS_LDCS");
+  const bool keep = rev && getenv("RUNMAT_B200_MOMENTS_KEEP");  // r51: plain loads measured slower (0.1473 vs 0.1421 ms), evict-first stays
   if (p->precision == RM_F64) {
     if (fold) {
       (keep ? moments_partial_fold_kernel<double, 2, true> : moments_partial_fold_kernel<double, 2, false>)<<<nblocks, 256, sh_fold, p->stream>>>((const double*)src, (uint32_t)B, total, partial);

@@ -7,9 +7,9 @@ rng = np.random.default_rng(0)
 for B in (8, 64):
     h = p.upload(rng.uniform(0, 1, (B, 2160, 3840)).astype(np.float32))
     d = ImageNormalizeDescriptor(batch=B, height=2160, width=3840, epsilon=1e-6, gain=1.0123, bias=-0.02, gamma=1.8, clamp_zero=True)
-    for name, env in (("256-bit end-to-front, plain moment loads", {}), ("256-bit end-to-front, evict-first moment loads", {"RUNMAT_B200_MOMENTS_LDCS": "1"}),
+    for name, env in (("256-bit end-to-front, evict-first moment loads", {}), ("256-bit end-to-front, plain moment loads", {"RUNMAT_B200_MOMENTS_KEEP": "1"}),
                       ("256-bit forward", {"RUNMAT_B200_NORMALIZE_FORWARD": "1"}), ("128-bit end-to-front", {"RUNMAT_B200_NORMALIZE_VEC4": "1"})):
-        for k in ("RUNMAT_B200_NORMALIZE_VEC4", "RUNMAT_B200_NORMALIZE_FORWARD", "RUNMAT_B200_MOMENTS_LDCS"): os.environ.pop(k, None)
+        for k in ("RUNMAT_B200_NORMALIZE_VEC4", "RUNMAT_B200_NORMALIZE_FORWARD", "RUNMAT_B200_MOMENTS_KEEP"): os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3): p.free(p.image_normalize(h, d))
         p.flush_l2(); p.synchronize(); p.timer_begin()
