@@ -1,6 +1,7 @@
 // common.h — internal definitions shared by the provider's translation units.
 // The public surface is include/rm_accel.h; nothing here is exported.
 #pragma once
+#include <utility>
 
 #include <cuda_runtime.h>
 
@@ -186,6 +187,31 @@ void p2p_enqueue_combine_locked(rm_provider* p, uint64_t step, void* dst);
 // Resolves a handle to its device pointer, validating device_id and element count.
 rm_status resolve(rm_provider* p, const rm_handle* h, void** dptr, uint64_t* elems);
 rm_status ensure_scratch(rm_provider* p, size_t bytes);
+#if defined(__CUDACC__)
+// Programmatic dependent launch for the hand-written kernels (the generated ones get it in fused.cu). A kernel launched through
+// launch_pdl() opens with pdl_prologue(): it lets the NEXT kernel of the stream become resident as soon as SM resources allow and
+// then waits until the PREVIOUS kernel has completed and its writes are visible -- before it touches global memory, so stream order
+// is kept exactly; what overlaps is launch latency, block scheduling and the smem/barrier set-up of one kernel with the drain of
+// the one before. Both instructions are no-ops in a plain launch; rm_set_launch_overlap(0) turns the attribute off.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool overlap, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
 inline void count_launch(rm_provider* p, uint64_t n = 1) { p->kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 struct LaunchAttr { const char* key; uint64_t value; };
 // record_kernel_launch (accelerate/src/telemetry.rs:219-239): newest last, oldest dropped beyond the cap

@@ -109,6 +109,7 @@ template <typename T, int VEC, bool KEEP>
 __global__ void __launch_bounds__(256)
 moments_partial_fold_kernel(const T* __restrict__ x, uint32_t B, uint64_t total, double* __restrict__ partial /*[grid][2][B]*/) {
   extern __shared__ double shw[];  // [8 warps][2][B]
+  pdl_prologue();
   const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t b0 = (uint32_t)((v0 * VEC) % B);  // fixed for this thread: (nthr*VEC) %% B == 0
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(128)
 moments_finalize_kernel(const T* __restrict__ x, const double* __restrict__ partial, uint32_t nblocks, uint64_t B, uint64_t P,
                         double eps, double* __restrict__ stats) {
   __shared__ double r1[128], r2[128];
+  pdl_prologue();
   const uint64_t b = blockIdx.x;
   double s1 = 0.0, s2 = 0.0;
   for (uint32_t i = threadIdx.x; i < nblocks; i += 128) { s1 += partial[((uint64_t)i * 2 + 0) * B + b]; s2 += partial[((uint64_t)i * 2 + 1) * B + b]; }
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(256)
 normalize_fixed_clampgamma_f32_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
                                       const __grid_constant__ NormParams np, int rev) {
   constexpr int U = VEC == 8 ? 2 : 4;  // 64 bytes per thread in flight
+  pdl_prologue();
   const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // rev: sweep from the end of the tensor to the front (vector v -> nvec-1-v). The moments sweep has just read the tensor front to
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(256)
 normalize_fixed_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t B, uint64_t total, const double* __restrict__ stats,
                        const __grid_constant__ NormParams np, int rev) {
   typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type V;
+  pdl_prologue();
   const uint64_t nvec = total / VEC, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   auto at = [&](uint64_t v) { return rev ? nvec - 1 - v : v; };  // end-to-front sweep: see normalize_fixed_clampgamma_f32_kernel
@@ -738,6 +742,7 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_prologue();  // barrier set-up above overlaps the previous kernel's drain; no global access before this point
   struct TileAt { int t0, t1, h0, h1; uint32_t plane; bool interior, tma; };  // image extents and tile counts are below 2^31 (launch_imfilter_tma_rb)
   // columns the fetch starts left of the halo; the same for every tile of a launch (tile origins are multiples of FX = 64)
   const int bo0 = (int)(fp.base[0] - fp.origin[0]), bo1 = (int)(fp.base[1] - fp.origin[1]);
@@ -818,16 +823,32 @@ imfilter_tma_f32_kernel(const __grid_constant__ CUtensorMap tm, const float* __r
       if (!a.interior) {
         // patch the out-of-image elements of the box (zeros from the TMA): constant -> cval; replicate / symmetric -> the value
         // at the remapped coordinate, which lies in the in-image part of this same box (read from global memory if it does not)
+        // Only the out-of-image cells are visited (r53: scanning all SY*SX cells with 64-bit index math made a border tile cost
+        // ~3x an interior one: 15 % of the compute warps' samples for 9 % of the tiles): the nl / nr out-of-image columns of every
+        // row first, then the nt / nb out-of-image rows of the columns in between.
         const float* src = img + (uint64_t)a.plane * fp.ie[0] * fp.ie[1];
-        for (int idx = tid; idx < SY * SX; idx += 256) {
-          const int sy = idx / SX, sx = idx - sy * SX;
-          const int64_t gx = a.h0 + sx, gy = a.h1 + sy;
-          if (gx >= 0 && gx < (int64_t)fp.ie[0] && gy >= 0 && gy < (int64_t)fp.ie[1]) continue;
-          const int r = remap(gx, (int64_t)fp.ie[0]), c = remap(gy, (int64_t)fp.ie[1]);
+        int nl = a.h0 < 0 ? -a.h0 : 0, nr = a.h0 + SX > ie0 ? a.h0 + SX - ie0 : 0;
+        int nt = a.h1 < 0 ? -a.h1 : 0, nb = a.h1 + SY > ie1 ? a.h1 + SY - ie1 : 0;
+        nl = nl < SX ? nl : SX; nr = nr < SX - nl ? nr : SX - nl;
+        nt = nt < SY ? nt : SY; nb = nb < SY - nt ? nb : SY - nt;
+        const int wside = nl + nr, wmid = SX - wside, nside = SY * wside, ncell = nside + (nt + nb) * wmid;
+        for (int idx = tid; idx < ncell; idx += 256) {
+          int sx, sy;
+          if (idx < nside) {
+            sy = idx / wside;
+            const int c = idx - sy * wside;
+            sx = c < nl ? c : SX - nr + (c - nl);
+          } else {
+            const int j = idx - nside, rr = j / wmid;
+            sx = nl + (j - rr * wmid);
+            sy = rr < nt ? rr : SY - nb + (rr - nt);
+          }
+          const int gx = a.h0 + sx, gy = a.h1 + sy;
+          const int r = remap(gx, (int64_t)ie0), c = remap(gy, (int64_t)ie1);
           float v;
           if (r < 0 || c < 0) v = (float)fp.cval;
           else {
-            const int64_t bx = (int64_t)r - a.h0, by = (int64_t)c - a.h1;
+            const int bx = r - a.h0, by = c - a.h1;
             v = (bx >= 0 && bx < SX && by >= 0 && by < SY) ? tile[by * SXP + shift + bx] : src[(uint64_t)r + (uint64_t)c * fp.ie[0]];
           }
           tile[sy * SXP + shift + sx] = v;
@@ -976,8 +997,10 @@ static bool launch_imfilter_tma_rb(rm_provider* p, const float* a, const float* 
   uint32_t cta_stagger = 0, warp_stagger = 0;
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_STAGGER")) cta_stagger = (uint32_t)atoi(e);
   if (const char* e = getenv("RUNMAT_B200_IMFILTER_WSTAGGER")) warp_stagger = (uint32_t)atoi(e);
-  imfilter_tma_f32_kernel<K, RBW, MODE, MB><<<grid, 288, C::SMEM, p->stream>>>(tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty, (uint32_t)ntiles, (int*)p->dev_flags + 0,
-                                                                         (uint32_t)p->prop.multiProcessorCount, cta_stagger, warp_stagger);
+  // r58: programmatic dependent launch pays from 5x5 up (61.5 -> 58.3 us, 7x7 96.1 -> 93.5); the bandwidth-bound 3x3 loses 3 % to
+  // the next launch's early-resident CTAs (42.2 -> 43.7 us), so it keeps the plain launch
+  launch_pdl(p->launch_overlap && K > 3, imfilter_tma_f32_kernel<K, RBW, MODE, MB>, dim3(grid), dim3(288), C::SMEM, p->stream, tm, a, k, o, fp, (uint32_t)ntx, (uint32_t)nty,
+             (uint32_t)ntiles, (int*)p->dev_flags + 0, (uint32_t)p->prop.multiProcessorCount, cta_stagger, warp_stagger);
   return true;
 }
 template <int K>
@@ -1097,37 +1120,40 @@ RM_EXPORT rm_status rm_image_normalize(rm_provider* p, const rm_handle* input, c
   const size_t sh_fold = (size_t)8 * 2 * B * sizeof(double);
   // end-to-front normalise sweep over a tensor the moments sweep has just read front-to-end (L2 reuse of its tail); A/B switches
   const int rev = getenv("RUNMAT_B200_NORMALIZE_FORWARD") ? 0 : 1;
+  const bool pdl = p->launch_overlap;  // programmatic dependent launch of the three-kernel chain (common.h launch_pdl)
   const bool keep = rev && getenv("RUNMAT_B200_MOMENTS_KEEP");  // r51: plain loads measured slower (0.1473 vs 0.1421 ms), evict-first stays
   if (p->precision == RM_F64) {
     if (fold) {
-      (keep ? moments_partial_fold_kernel<double, 2, true> : moments_partial_fold_kernel<double, 2, false>)<<<nblocks, 256, sh_fold, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
+      launch_pdl(pdl, keep ? moments_partial_fold_kernel<double, 2, true> : moments_partial_fold_kernel<double, 2, false>, dim3(nblocks), dim3(256), sh_fold, p->stream,
+                 (const double*)src, (uint32_t)B, total, partial);
     } else if (fast_blocks) {
       moments_partial_vec_kernel<double, 2><<<nblocks, 256, sh, p->stream>>>((const double*)src, (uint32_t)B, total, partial);
     } else {
       cudaFuncSetAttribute(moments_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
       moments_partial_kernel<double><<<nblocks, threads, sh, p->stream>>>((const double*)src, B, P, partial);
     }
-    moments_finalize_kernel<double><<<(unsigned)B, 128, 0, p->stream>>>((const double*)src, partial, nblocks, B, P, d->epsilon, stats);
-    if (fast_blocks) normalize_fixed_kernel<double, 2><<<fast_blocks, 256, 0, p->stream>>>((const double*)src, (double*)dst, (uint32_t)B, total, stats, np, rev);
+    launch_pdl(pdl, moments_finalize_kernel<double>, dim3((unsigned)B), dim3(128), 0, p->stream, (const double*)src, (const double*)partial, nblocks, B, P, d->epsilon, stats);
+    if (fast_blocks) launch_pdl(pdl, normalize_fixed_kernel<double, 2>, dim3(fast_blocks), dim3(256), 0, p->stream, (const double*)src, (double*)dst, (uint32_t)B, total, (const double*)stats, np, rev);
     else normalize_kernel<double, 2><<<ngrid, 256, 0, p->stream>>>((const double*)src, (double*)dst, B, total, stats, np);
   } else {
     if (fold) {
-      (keep ? moments_partial_fold_kernel<float, 4, true> : moments_partial_fold_kernel<float, 4, false>)<<<nblocks, 256, sh_fold, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
+      launch_pdl(pdl, keep ? moments_partial_fold_kernel<float, 4, true> : moments_partial_fold_kernel<float, 4, false>, dim3(nblocks), dim3(256), sh_fold, p->stream,
+                 (const float*)src, (uint32_t)B, total, partial);
     } else if (fast_blocks) {
       moments_partial_vec_kernel<float, 4><<<nblocks, 256, sh, p->stream>>>((const float*)src, (uint32_t)B, total, partial);
     } else {
       cudaFuncSetAttribute(moments_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
       moments_partial_kernel<float><<<nblocks, threads, sh, p->stream>>>((const float*)src, B, P, partial);
     }
-    moments_finalize_kernel<float><<<(unsigned)B, 128, 0, p->stream>>>((const float*)src, partial, nblocks, B, P, d->epsilon, stats);
+    launch_pdl(pdl, moments_finalize_kernel<float>, dim3((unsigned)B), dim3(128), 0, p->stream, (const float*)src, (const double*)partial, nblocks, B, P, d->epsilon, stats);
     if (fast_blocks && d->clamp_zero && d->has_gamma && (float)d->gamma != 0.0f && !getenv("RUNMAT_B200_NORMALIZE_GENERIC")) {
       // 256-bit accesses when a thread's 8 lanes stay on fixed images (B % 8 == 0 and the grid stride a multiple of B)
       if (B % 8 == 0 && total % 8 == 0 && ((uint64_t)fast_blocks * 256ull * 8) % B == 0 && !getenv("RUNMAT_B200_NORMALIZE_VEC4"))
-        normalize_fixed_clampgamma_f32_kernel<8><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np, rev);
+        launch_pdl(pdl, normalize_fixed_clampgamma_f32_kernel<8>, dim3(fast_blocks), dim3(256), 0, p->stream, (const float*)src, (float*)dst, (uint32_t)B, total, (const double*)stats, np, rev);
       else
-        normalize_fixed_clampgamma_f32_kernel<4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np, rev);
+        launch_pdl(pdl, normalize_fixed_clampgamma_f32_kernel<4>, dim3(fast_blocks), dim3(256), 0, p->stream, (const float*)src, (float*)dst, (uint32_t)B, total, (const double*)stats, np, rev);
     }
-    else if (fast_blocks) normalize_fixed_kernel<float, 4><<<fast_blocks, 256, 0, p->stream>>>((const float*)src, (float*)dst, (uint32_t)B, total, stats, np, rev);
+    else if (fast_blocks) launch_pdl(pdl, normalize_fixed_kernel<float, 4>, dim3(fast_blocks), dim3(256), 0, p->stream, (const float*)src, (float*)dst, (uint32_t)B, total, (const double*)stats, np, rev);
     else normalize_kernel<float, 4><<<ngrid, 256, 0, p->stream>>>((const float*)src, (float*)dst, B, total, stats, np);
   }
   cudaError_t e = cudaGetLastError();

@@ -221,6 +221,7 @@ RM_EXPORT rm_status rm_provider_create(int ordinal, uint32_t device_id, rm_preci
   p->ordinal = ordinal;
   p->device_id = device_id;
   p->precision = precision;
+  if (getenv("RUNMAT_B200_NO_PDL")) p->launch_overlap = false;  // A/B: plain launches everywhere (fused.cu and common.h launch_pdl)
   RM_CUDA(cudaGetDeviceProperties(&p->prop, ordinal));
   RM_REQUIRE(p->prop.major >= 10, RM_NO_DEVICE, "device %s is sm_%d%d; this backend is built for sm_100a only", p->prop.name, p->prop.major, p->prop.minor);
   RM_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
