@@ -859,5 +859,26 @@ def main():
     return run_ours(args)
 
 
+class _CleanStdout:
+    """Everything libraries write to fd 1 while the bench runs (NCCL prints its version banner there) goes to stderr; the JSON line is
+    written to the real stdout, so stdout carries exactly ONE line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        self.real = os.fdopen(self.saved, "w")
+        self.py_stdout, sys.stdout = sys.stdout, self.real
+        return self
+
+    def __exit__(self, *exc):
+        self.real.flush()
+        sys.stdout = self.py_stdout
+        os.dup2(self.saved, 1)
+        return False
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    with _CleanStdout():
+        rc = main()
+    sys.exit(rc)
