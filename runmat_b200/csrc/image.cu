@@ -698,6 +698,7 @@ __device__ __forceinline__ bool imf_mbar_wait_parked(uint64_t* bar, uint32_t par
 // a step is three adds and two compare-subtracts. (r53 ncu/SASS: decomposing t with two 32-bit divisions per tile, in 64-bit
 // coordinates, cost ~100 dependent instructions per tile per warp -- I2F/MUFU.RCP/F2I chains the warp sits out -- next to the
 // 400 packed math instructions of a 5x5 tile.)
+// ---- imf_tile_iter begin (tests/test_host_logic.py compiles this struct for the host and checks it against the divisions)
 struct ImfTileIter {
   uint32_t tx, ty, plane, dx, dy, dp, ntx, nty;
   __device__ __forceinline__ void init(uint32_t first, uint32_t stride, uint32_t ntx_, uint32_t nty_) {
@@ -714,6 +715,7 @@ struct ImfTileIter {
     if (ty >= nty) { ty -= nty; ++plane; }
   }
 };
+// ---- imf_tile_iter end
 // MODE 0: scalar FMUL + FADD; 1: packed FMUL2 + FFMA2(x1); 2: mixed -- the first half of a warp's rows packed, the second half scalar
 // Resident CTAs the register allocation is held to: the K*K weights live in registers, so 7x7 gets two CTAs per SM; up to 5x5
 // four fit (RBW = 4: 3 x 10 KB stages each) or three (RBW = 8).
