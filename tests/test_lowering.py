@@ -90,6 +90,39 @@ def test_lean_trig_against_libm(lib, tmp_path):
     assert "#define rm_sin(x) sin(x)" in lower_ew(lib, ft.sin_mul_add_wgsl("f32"), 0, 0b100)
 
 
+def test_libm_trig_switch_lowers_and_compiles():
+    """RUNMAT_B200_LIBM_TRIG=1 (the A/B switch of the lean sin / cos) is read when the source is emitted: in a fresh process the
+    generated kernels must define RM_LIBM_TRIG 1, map rm_sin to the library's sin, and still compile for sm_100a."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, ctypes as C\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from runmat_b200 import _capi\n"
+        "import fusion_text as ft\n"
+        "lib = _capi.lib\n"
+        "for red in (0, 1):\n"
+        "    need = C.c_size_t()\n"
+        "    if red:\n"
+        "        lib.rm_debug_lower_reduction(ft.sum_sin_mul_add_wgsl().encode(), 0, 0, None, 0, C.byref(need), None, None)\n"
+        "        buf = C.create_string_buffer(need.value)\n"
+        "        lib.rm_debug_lower_reduction(ft.sum_sin_mul_add_wgsl().encode(), 0, 0, buf, need.value, None, None, None)\n"
+        "    else:\n"
+        "        lib.rm_debug_lower_elementwise(ft.sin_mul_add_wgsl().encode(), 0, 4, None, 0, C.byref(need))\n"
+        "        buf = C.create_string_buffer(need.value)\n"
+        "        lib.rm_debug_lower_elementwise(ft.sin_mul_add_wgsl().encode(), 0, 4, buf, need.value, None)\n"
+        "    src = buf.value.decode()\n"
+        "    assert '#define RM_LIBM_TRIG 1' in src and 'rm_sin(v0)' in src\n"
+        "    assert lib.rm_debug_compile(buf.value, b't.cu', None) == 0, lib.rm_last_error()\n"
+        "print('ok')\n"
+    ) % (str(__import__("pathlib").Path(__file__).resolve().parent.parent), str(__import__("pathlib").Path(__file__).resolve().parent))
+    env = dict(os.environ, RUNMAT_B200_LIBM_TRIG="1", RUNMAT_B200_NO_KCACHE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_multi_output_and_every_builtin_lower(lib):
     names = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "exp", "log", "log2", "sqrt", "abs", "exp2", "floor", "ceil",
              "round", "trunc", "fix", "sign", "heaviside", "isnan", "isinf", "isfinite", "single", "double", "log10", "log1p", "expm1", "asinh",
