@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <random>
 typedef unsigned int u32;
 #define __constant__ static const
@@ -52,6 +53,9 @@ int main(int argc, char** argv) {
   bad |= rm_sin(1e-300) != 1e-300 || rm_sin(-5e-324) != -5e-324 || rm_cos(1e-30) != 1.0;
   bad |= rm_sin(1e6) != sin(1e6) || rm_cos(-1e22) != cos(-1e22) || rm_sin(105615.0) != sin(105615.0);   // out-of-line library route
   bad |= !std::isnan(rm_sin(INFINITY)) || !std::isnan(rm_cos(-INFINITY)) || !std::isnan(rm_sin(NAN)) || !std::isnan(rm_cos(NAN));
+  // the reference's own GPU round-trip test compares sin([0 1 2 3]) with the host's f64::sin by assert_eq (sin.rs:620-634,
+  // sin_gpu_provider_roundtrip): these four must be bit-equal to libm, not just close
+  for (double x : {0.0, 1.0, 2.0, 3.0}) bad |= rm_sin(x) != sin(x);
   if (bad) printf("FAILED\n");
   return bad;
 }
