@@ -54,3 +54,27 @@ def test_missing_extension_raises_at_import(built, tmp_path):
     code = "import os; os.environ['RUNMAT_B200_LIB']='/nonexistent/lib.so'; import runmat_b200"
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_header_is_plain_c_and_a_c_caller_links(built, tmp_path):
+    """The boundary is a C ABI: include/rm_accel.h must compile as C11 (no C++ in the signatures), and a C program must link
+    against the shared library and reach an entry point. Without a GPU the create call has to fail with RM_NO_DEVICE and a
+    message; with one it has to succeed (the program only creates and destroys the provider: no compute)."""
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "rm_accel.h"\n'
+        "int main(void) {\n"
+        "  rm_provider* p = NULL;\n"
+        "  if (rm_abi_version() != 1) return 2;\n"
+        "  rm_status st = rm_provider_create(0, 0, RM_F64, &p);\n"
+        '  if (st == RM_OK) { rm_provider_destroy(p); printf("created\\n"); return 0; }\n'
+        '  printf("status %d: %s\\n", (int)st, rm_last_error());\n'
+        "  return st == RM_NO_DEVICE && strlen(rm_last_error()) > 0 ? 0 : 3;\n"
+        "}\n"
+    )
+    libdir = ROOT / "runmat_b200"
+    exe = tmp_path / "caller"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+                    f"-L{libdir}", "-lrm_accel_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
