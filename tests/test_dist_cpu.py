@@ -155,3 +155,24 @@ def test_numa_binding_is_best_effort():
 
     assert bind_process_to_gpu_numa("0000:ff:1f.7") is None
     assert bind_process_to_gpu_numa("garbage") is None
+
+
+def test_reference_arm_under_torchrun_prints_one_json_line():
+    """bench.py --impl reference launched the way the driver launches it at N > 1 (torchrun, one process per GPU): rank 0 alone runs
+    the CPU reference path and prints exactly ONE JSON line on stdout, the other ranks exit 0 without work; library banners and
+    torchrun's own notices must not reach stdout."""
+    import json
+    import pathlib
+    import subprocess
+    import sys
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["unit"] == "GB/s" and d["higher_is_better"] is True and d["value"] > 0
