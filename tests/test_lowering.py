@@ -126,7 +126,7 @@ def test_libm_trig_switch_lowers_and_compiles():
 def test_multi_output_and_every_builtin_lower(lib):
     names = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "exp", "log", "log2", "sqrt", "abs", "exp2", "floor", "ceil",
              "round", "trunc", "fix", "sign", "heaviside", "isnan", "isinf", "isfinite", "single", "double", "log10", "log1p", "expm1", "asinh",
-             "acosh", "atanh", "pow2"]
+             "acosh", "atanh", "pow2", "gpuarray"]  # every name of the planner tables (fusion.rs:2874-3026)
     ops, vid = [], 100
     for nme in names:
         ops.append(ft.FusionOp("builtin", nme, [0], vid))
